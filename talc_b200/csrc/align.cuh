@@ -1,0 +1,341 @@
+// align.cuh -- integer alignment scores used by path scoring.
+//
+// The reference only ever reads the *score* of its SeqAn alignments (never the traceback), so:
+//   NW(0,-1,-1)  Trajectory.cpp:413, Trail.cpp:422   -> Myers/Hyyro bit-parallel edit distance
+//   SW(1,0,0)    Trajectory.cpp:368,525              -> bit-parallel LCS length
+//   (4,-3,-2) with free leading gaps  Trail.cpp:166-172 -> two-row integer DP (rare: pruning only)
+//   extendSeed(.., GappedXDrop) Trail.cpp:373,391    -> the anti-diagonal X-drop, restated exactly,
+//                                                       because its *end position* is algorithm-defined
+// All sequences are addressed in walk order (see defs.cuh); a LEFT-ward search is the RIGHT-ward
+// algorithm on reversed strings (global/LCS scores are reversal-invariant, EXTEND_LEFT consumes the
+// prefixes back to front, and AlignConfig<false,false,true,true> on reversed strings is
+// AlignConfig<true,true,false,false>).
+// One thread runs one alignment: 64 DP rows per machine word, rows > 64 in stripes with the
+// 2-bit horizontal deltas of the stripe boundary parked in the thread's scratch arena.
+#pragma once
+#include "defs.cuh"
+
+namespace talc {
+
+// either a slice of the raw read (walk order) or a packed trail
+struct SeqView {
+  const u8* s;    // raw read bytes (when w == nullptr)
+  i32 start;
+  i32 step;
+  const u64* w;   // packed trail (when non-null)
+  u32 len;
+  TALC_HD u32 code(u32 i) const {
+    if (w) return (u32)((w[i >> 5] >> (62 - 2 * (i & 31))) & 3ull);
+    return base_code(s[start + (i32)i * step]);
+  }
+};
+TALC_HD SeqView view_of(const RefView& r) { SeqView v; v.s = r.s; v.start = r.start; v.step = r.step; v.w = nullptr; v.len = r.len; return v; }
+TALC_HD SeqView view_of(const PathView& p) { SeqView v; v.s = nullptr; v.start = 0; v.step = 1; v.w = p.w; v.len = p.len; return v; }
+TALC_HD SeqView view_of_path(const u64* w, u32 len) { SeqView v; v.s = nullptr; v.start = 0; v.step = 1; v.w = w; v.len = len; return v; }
+
+struct DpStats {  // algorithmic DP cell updates (SURVEY 8d "integer work")
+  u64 cells_nw, cells_lcs, cells_ovl, cells_xdrop;
+};
+
+// match masks of pattern rows [64*block, 64*block+64) for the five symbols (N matches N)
+TALC_HD void build_peq(const SeqView& pat, u32 pn, u32 block, u64 peq[5]) {
+  peq[0] = peq[1] = peq[2] = peq[3] = peq[4] = 0;
+  const u32 r0 = block * 64;
+  const u32 r1 = (pn - r0 < 64u) ? pn : r0 + 64;
+  if (pat.w && pat.step == 1) {
+    // packed trail: two words hold the 64 rows
+    for (u32 r = r0; r < r1; ++r) {
+      const u32 c = (u32)((pat.w[r >> 5] >> (62 - 2 * (r & 31))) & 3ull);
+      peq[c] |= 1ull << (r - r0);
+    }
+  } else {
+    for (u32 r = r0; r < r1; ++r) peq[pat.code(r)] |= 1ull << (r - r0);
+  }
+}
+
+// unit-cost edit distance between a[0..an) and b[0..bn) (both non-empty)
+TALC_HD int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+  // pattern (rows, bit-parallel) = the shorter one, text (columns) = the longer one
+  const bool a_is_pat = an <= bn;
+  const SeqView& pat = a_is_pat ? a : b;
+  const SeqView& txt = a_is_pat ? b : a;
+  const u32 pn = a_is_pat ? an : bn;
+  const u32 tn = a_is_pat ? bn : an;
+  if (st) st->cells_nw += (u64)an * bn;
+  const u32 nblocks = (pn + 63) / 64;
+  const u32 mk = ar.mark();
+  signed char* h = nullptr;
+  if (nblocks > 1) {
+    h = (signed char*)ar.alloc(tn);
+    if (!h) return 0;
+  }
+  int score = (int)pn;
+  for (u32 blk = 0; blk < nblocks; ++blk) {
+    u64 peq[5];
+    build_peq(pat, pn, blk, peq);
+    const bool last = (blk + 1 == nblocks);
+    const u32 top = last ? (pn - blk * 64 - 1) : 63;
+    u64 Pv = ~0ull, Mv = 0;
+    for (u32 j = 0; j < tn; ++j) {
+      u64 Eq = peq[txt.code(j)];
+      const int hin = (blk == 0) ? 1 : (int)h[j];
+      const u64 hneg = (hin < 0) ? 1ull : 0ull;
+      const u64 Xv = Eq | Mv;
+      Eq |= hneg;
+      const u64 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+      u64 Ph = Mv | ~(Xh | Pv);
+      u64 Mh = Pv & Xh;
+      const int hout = (int)((Ph >> top) & 1ull) - (int)((Mh >> top) & 1ull);
+      Ph <<= 1;
+      Mh <<= 1;
+      Mh |= hneg;
+      Ph |= (hin > 0) ? 1ull : 0ull;
+      Pv = Mh | ~(Xv | Ph);
+      Mv = Ph & Xv;
+      if (last) score += hout;
+      else h[j] = (signed char)hout;
+    }
+  }
+  ar.release(mk);
+  return score;
+}
+
+// length of the longest common subsequence of a[0..an) and b[0..bn) (both non-empty)
+TALC_HD int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+  const bool a_is_pat = an <= bn;
+  const SeqView& pat = a_is_pat ? a : b;
+  const SeqView& txt = a_is_pat ? b : a;
+  const u32 pn = a_is_pat ? an : bn;
+  const u32 tn = a_is_pat ? bn : an;
+  if (st) st->cells_lcs += (u64)an * bn;
+  const u32 nblocks = (pn + 63) / 64;
+  const u32 mk = ar.mark();
+  u8* carry = nullptr;
+  if (nblocks > 1) {
+    carry = (u8*)ar.alloc(tn);
+    if (!carry) return 0;
+  }
+  int lcs = 0;
+  for (u32 blk = 0; blk < nblocks; ++blk) {
+    u64 peq[5];
+    build_peq(pat, pn, blk, peq);
+    const bool last = (blk + 1 == nblocks);
+    const u32 rows = last ? (pn - blk * 64) : 64;
+    u64 V = ~0ull;
+    for (u32 j = 0; j < tn; ++j) {
+      const u64 M = peq[txt.code(j)];
+      const u64 U = V & M;
+      const u64 cin = (blk == 0) ? 0ull : (u64)carry[j];
+      const u64 t = V + U;
+      const u64 sum = t + cin;
+      const u64 cout = (u64)(t < V) | (u64)(sum < t);
+      V = sum | (V & ~M);
+      if (!last) carry[j] = (u8)cout;
+    }
+    const u64 zeros = ~V & ((rows == 64) ? ~0ull : ((1ull << rows) - 1ull));
+#if defined(__CUDA_ARCH__)
+    lcs += __popcll(zeros);
+#else
+    lcs += __builtin_popcountll(zeros);
+#endif
+  }
+  ar.release(mk);
+  return lcs;
+}
+
+// Trail::Overlapscore in walk order: match 4 / mismatch -3 / gap -2, leading gaps of both
+// sequences free, trailing gaps charged; score = bottom-right cell.
+TALC_HD int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {
+  if (st) st->cells_ovl += (u64)rn * cn;
+  const u32 mk = ar.mark();
+  i32* row = (i32*)ar.alloc((cn + 1) * 4);
+  if (!row) return 0;
+  for (u32 j = 0; j <= cn; ++j) row[j] = 0;
+  for (u32 i = 0; i < rn; ++i) {
+    const u32 rc = ref.code(i);
+    i32 diag = row[0];  // S[i][0] = 0
+    row[0] = 0;
+    for (u32 j = 1; j <= cn; ++j) {
+      const i32 up = row[j];
+      i32 v = diag + ((rc == cand.code(j - 1)) ? 4 : -3);
+      const i32 g1 = up - 2;
+      const i32 g2 = row[j - 1] - 2;
+      v = v > g1 ? v : g1;
+      v = v > g2 ? v : g2;
+      diag = up;
+      row[j] = v;
+    }
+  }
+  const int res = row[cn];
+  ar.release(mk);
+  return res;
+}
+
+// SeqAn 2.x _extendSeedGappedXDropOneDirection for Score(0,-1,-1) on query[qoff..qoff+qlen) (V, columns)
+// and database[doff..doff+dlen) (H, rows), both in walk order.  Outputs how far the seed moved along
+// the database (ext_rows) and the query (ext_cols).  `wide` sizes the three anti-diagonals for the
+// worst case instead of the X-drop band (second-tier launch).
+TALC_HD void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen,
+                          int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide, DpStats* st) {
+  ext_rows = 0;
+  ext_cols = 0;
+  const i64 cols = (i64)qlen + 1;
+  const i64 rows = (i64)dlen + 1;
+  if (rows == 1 || cols == 1) return;
+  const int gapCost = -1;                 // max(scoreGap, INT_MIN / len) with scoreGap = -1
+  const int undefined = INT32_MIN + 1;    // INT_MIN - gapCost
+  // anti-diagonal storage: at most (maxCol - minCol) + 2 live entries each
+  i64 capW = cols + 1;
+  if (!wide) {
+    const i64 band = (i64)(scoreDropOff > 0 ? scoreDropOff : 0) + 16;
+    if (band < capW) capW = band;
+  }
+  const u32 mk = ar.mark();
+  i32* buf = (i32*)ar.alloc((u32)(3 * capW * 4));
+  if (!buf) return;
+  i32* antiDiag1 = buf;
+  i32* antiDiag2 = buf + capW;
+  i32* antiDiag3 = buf + 2 * capW;
+  i64 len1 = 0, len2 = 1, len3 = 2;
+
+  i64 minCol = 1, maxCol = 2;
+  i64 offset1 = 0, offset2 = 0, offset3 = 0;
+  antiDiag2[0] = 0;
+  if (-gapCost > scoreDropOff) {
+    antiDiag3[0] = undefined;
+    antiDiag3[1] = undefined;
+  } else {
+    antiDiag3[0] = gapCost;
+    antiDiag3[1] = gapCost;
+  }
+  i64 antiDiagNo = 1;
+  int best = 0;
+  u64 cells = 0;
+
+  while (minCol < maxCol) {
+    ++antiDiagNo;
+    {  // _swapAntiDiags
+      i32* t = antiDiag1;
+      antiDiag1 = antiDiag2;
+      antiDiag2 = antiDiag3;
+      antiDiag3 = t;
+      len1 = len2;
+      len2 = len3;
+    }
+    offset1 = offset2;
+    offset2 = offset3;
+    offset3 = minCol - 1;
+    len3 = maxCol + 1 - offset3;
+    if (len3 > capW) {  // band assumption violated: ask for the wide tier
+      ar.overflow = 1;
+      ar.release(mk);
+      return;
+    }
+    {  // _initAntiDiag3
+      const int minScore = best - scoreDropOff;
+      antiDiag3[0] = undefined;
+      antiDiag3[maxCol - offset3] = undefined;
+      if ((int)antiDiagNo * gapCost > minScore) {
+        if (offset3 == 0) antiDiag3[0] = (int)antiDiagNo * gapCost;
+        if (antiDiagNo - maxCol == 0) antiDiag3[maxCol - offset3] = (int)antiDiagNo * gapCost;
+      }
+    }
+    int antiDiagBest = (int)antiDiagNo * gapCost;
+    for (i64 col = minCol; col < maxCol; ++col) {
+      const i64 i3 = col - offset3, i2 = col - offset2, i1 = col - offset1;
+      const u32 queryPos = (u32)(col - 1);
+      const u32 dbPos = (u32)(antiDiagNo - col - 1);
+      const int d2a = antiDiag2[i2 - 1], d2b = antiDiag2[i2];
+      int tmp = (d2a > d2b ? d2a : d2b) + gapCost;
+      const int sub = antiDiag1[i1 - 1] + ((query.code(qoff + queryPos) == database.code(doff + dbPos)) ? 0 : -1);
+      tmp = tmp > sub ? tmp : sub;
+      if (tmp < best - scoreDropOff) {
+        antiDiag3[i3] = undefined;
+      } else {
+        antiDiag3[i3] = tmp;
+        antiDiagBest = antiDiagBest > tmp ? antiDiagBest : tmp;
+      }
+    }
+    cells += (u64)(maxCol - minCol);
+    best = best > antiDiagBest ? best : antiDiagBest;
+
+    while (minCol - offset3 < len3 && antiDiag3[minCol - offset3] == undefined && minCol - offset2 - 1 < len2 &&
+           antiDiag2[minCol - offset2 - 1] == undefined) {
+      ++minCol;
+    }
+    while (maxCol - offset3 > 0 && (antiDiag3[maxCol - offset3 - 1] == undefined) &&
+           (antiDiag2[maxCol - offset2 - 1] == undefined)) {
+      --maxCol;
+    }
+    ++maxCol;
+    {
+      const i64 lo = antiDiagNo + 2 - rows;  // end of databaseSeg reached?
+      if (lo > minCol) minCol = lo;
+      if (cols < maxCol) maxCol = cols;      // end of querySeg reached?
+    }
+  }
+  if (st) st->cells_xdrop += cells;
+
+  i64 longestExtensionCol = len3 + offset3 - 2;
+  i64 longestExtensionRow = antiDiagNo - longestExtensionCol;
+  int longestExtensionScore = antiDiag3[longestExtensionCol - offset3];
+  if (longestExtensionScore == undefined) {
+    if (antiDiag2[len2 - 2] != undefined) {  // reached end of query segment
+      longestExtensionCol = len2 + offset2 - 2;
+      longestExtensionRow = antiDiagNo - 1 - longestExtensionCol;
+      longestExtensionScore = antiDiag2[longestExtensionCol - offset2];
+    } else if (len2 > 2 && antiDiag2[len2 - 3] != undefined) {  // reached end of database segment
+      longestExtensionCol = len2 + offset2 - 3;
+      longestExtensionRow = antiDiagNo - 1 - longestExtensionCol;
+      longestExtensionScore = antiDiag2[longestExtensionCol - offset2];
+    }
+  }
+  if (longestExtensionScore == undefined) {  // general case: first strictly greatest on antiDiag1
+    for (i64 i = 0; i < len1; ++i) {
+      if (antiDiag1[i] > longestExtensionScore) {
+        longestExtensionScore = antiDiag1[i];
+        longestExtensionCol = i + offset1;
+        longestExtensionRow = antiDiagNo - 2 - longestExtensionCol;
+      }
+    }
+  }
+  if (longestExtensionScore != undefined) {
+    ext_rows = (u32)longestExtensionRow;
+    ext_cols = (u32)longestExtensionCol;
+  }
+  ar.release(mk);
+}
+
+// Trail.cpp:341-437 getSeedAndExtension in walk order.  refArg / candArg are the two arguments in the
+// reference's order; `right` is the search direction.  Extensions are returned as walk-order prefix
+// lengths of refArg and candArg.
+struct SeedExt {
+  u32 ref_ext;   // |refExtension|
+  u32 cand_ext;  // |histExtension|
+  i32 score;     // NW score of the two extensions (<= 0), or -xdrop when the seed could not extend
+  bool stop;
+};
+TALC_HD SeedExt seed_and_extension(const SeqView& refArg, const SeqView& candArg, int xdrop, bool right, u32 K,
+                                   Arena& ar, bool wide, DpStats* st) {
+  SeedExt r;
+  const bool state = !(refArg.len < candArg.len);
+  const SeqView& seq1 = state ? refArg : candArg;   // H / database (the longer one)
+  const SeqView& seq2 = state ? candArg : refArg;   // V / query
+  const u32 s = right ? (K - 1) : K;                // Q18: seed (0,0,K-1,K-1) vs (l1-K,l2-K,..)
+  u32 er = 0, ec = 0;
+  xdrop_extend(seq2, s, seq2.len - s, seq1, s, seq1.len - s, xdrop, er, ec, ar, wide, st);
+  const u32 e1 = s + er, e2 = s + ec;
+  r.ref_ext = state ? e1 : e2;
+  r.cand_ext = state ? e2 : e1;
+  const u32 mx = r.ref_ext > r.cand_ext ? r.ref_ext : r.cand_ext;
+  if (mx >= K) {
+    r.score = -nw_distance(refArg, r.ref_ext, candArg, r.cand_ext, ar, st);
+    r.stop = false;
+  } else {  // Q19
+    r.score = -xdrop;
+    r.stop = true;
+  }
+  return r;
+}
+
+}  // namespace talc

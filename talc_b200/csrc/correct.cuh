@@ -1,0 +1,1218 @@
+// correct.cuh -- per-read segmentation, anchor selection, bounded de Bruijn graph search and
+// path scoring.  One thread owns one read: the oracle's counters show a mean
+// frontier of ~1 trail per step, so the parallelism is across reads, not inside a gap, and the gaps
+// of a read form a dependency chain anyway.
+//
+// Reference files restated here (all under /root/reference/src):
+//   Read.cpp:174-386,440-600   Explorer.cpp:155-297,402-1118   Trail.cpp:48-131,193-216,273-338
+//   Trajectory.cpp:43-48,89-243,282-334,482-528
+// The quirks listed in SURVEY A.7 (Q1-Q23) are reproduced on purpose; each is tagged where it occurs.
+#pragma once
+#include "align.cuh"
+#include "defs.cuh"
+#include "model.cuh"
+#include "stdsort.cuh"
+#include "table.cuh"
+
+namespace talc {
+
+struct Counters {
+  u64 lookups_seg, lookups_deg, lookups_walk;
+  u64 steps_inner, steps_border, frontier_sum;
+  u64 cells_nw, cells_lcs, cells_ovl, cells_xdrop;
+  u64 gaps, gaps_bridged, gap_attempts, borders, borders_corrected;
+  u64 ev_gardening, ev_bridge, ev_edge, ev_cycle;
+  u64 bases_out, reads_ok, reads_overflow;
+};
+static const int kNumCounters = sizeof(Counters) / sizeof(u64);
+
+struct Region {
+  u32 start, end;  // k-mer coordinates, inclusive
+};
+
+struct AnchorRec {  // anchorTuple (kmer, position, count)
+  u64 kmer;
+  u32 pos;
+  u32 count;
+};
+
+struct Trail {  // Trail.hpp:95-107 minus the sequence, which lives in a packed slot
+  u64 kmer;     // last k-mer
+  double dist;  // m_distance
+  u32 count;    // last count
+  i32 score;    // m_lastScore (always integral)
+  u16 slot;
+  u8 failures;  // m_nbFailuresInARow
+  u8 pad;
+};
+
+struct GardenRank {
+  u32 idx, r1, r2, sum;
+};
+struct GardenKey {
+  u32 idx;
+  i32 score;
+  double dist;
+};
+
+// one corrected piece of the read, as ASCII in the persistent arena; len < 0 means "raw slice kept"
+struct Piece {
+  u32 off;
+  i32 len;
+};
+
+// a candidate correction of a border (Trajectory after trim/reshape/cutAnchors), kept only while it
+// is the running best of its list (findBestBORDER is a left fold: Trajectory.cpp:306-334, Q21)
+struct EdgeBest {
+  bool have;
+  double score;     // NW score of the final extension
+  double idscore;   // LCS / longer
+  double md;        // mean distance (Q22)
+  u32 path_keep;    // walk-order prefix of the trail that is kept (before anchor removal)
+  u32 ref_from;     // then the raw border from this walk index on (only when `shorter`), else == ref.len
+  u32 anchor_pos;   // whichStart of the anchor that produced it
+  i32 ref_start;    // RefView of that anchor
+  u32 ref_len;
+  u64* seq;         // packed copy of the kept prefix
+};
+
+struct ReadJob {
+  ReadView rd;
+  const u32* cov;   // coverage counts of this read, C = len-K+1 entries
+  u8* arena;        // per-thread scratch slice
+  u32 arena_bytes;
+  bool wide;        // second tier: worst-case buffer sizing
+};
+
+struct ReadOut {
+  u8 status;
+  u32 out_len;
+};
+
+class Corrector {
+ public:
+  TableView T;
+  Params P;
+  ReadView rd;
+  const u32* cov;
+  u32 C;  // number of k-mers
+  Arena keep;     // persistent per-read data: regions, pieces
+  Arena scratch;  // per-attempt data
+  bool wide;
+  Counters* ctr;  // per-read tallies (may be null); the caller adds them to the batch totals
+  DpStats dps;
+
+  // --- structure
+  Region* regs;
+  u32 nregs;
+  Piece* gapPiece;  // nregs-1 entries
+  Piece headPiece, tailPiece;
+  bool headPresent, tailPresent;
+  double noise;  // m_priorLambda_noise
+
+  // --- explorer state
+  Region L, R;
+  int location;  // 0 HEAD, 1 INNER, 2 TAIL
+  bool dirRight;
+  bool complexRegion;  // Q12: sticky for the rest of the read
+  AnchorRec* ancL;
+  u32 nAncL;
+  AnchorRec* ancR;
+  u32 nAncR;
+  u32 weakLen;
+
+  // --- search state
+  u32 slotWords, nSlots, nFree;
+  u64* slotPool;
+  u16* freeList;
+  Trail* cur;
+  Trail* nxt;
+  u32 nCur, nNxt, maxT;
+
+  TALC_HD u32 K() const { return P.K; }
+
+  // ------------------------------------------------------------------ table access with counters
+  TALC_HD int out_degree(u32 pos, bool right) {
+    if (ctr) ctr->lookups_deg += 4;
+    bool ok;
+    const u64 km = rd.kmer_at(pos, K(), ok);
+    if (!ok) {
+      // a k-mer holding N: its successors x[1..]+b may or may not hold N; look each one up by bases
+      int d = 0;
+      for (u32 b = 0; b < 4; ++b) {
+        bool ok2 = true;
+        u64 v = 0;
+        for (u32 j = 0; j < K(); ++j) {
+          u32 c;
+          if (right) c = (j + 1 < K()) ? rd.code(pos + j + 1) : b;
+          else c = (j == 0) ? b : rd.code(pos + j - 1);
+          if (c > 3) { ok2 = false; break; }
+          v = (v << 2) | c;
+        }
+        if (ok2) {
+          u32 cn, cl;
+          table_lookup(T, v, cn, cl);
+          d += (cn >= P.min_count) ? 1 : 0;
+        }
+      }
+      return d;
+    }
+    return table_out_degree(T, km, right, K(), P.min_count);
+  }
+
+  // ------------------------------------------------------------------ Read.cpp:493-518
+  // robust mean over the [15%,90%) slice of the sorted in-counts, computed without sorting: the sum
+  // of the r smallest values is exact in integers (and in double below 2^53), so order is irrelevant
+  TALC_HD u64 sum_of_smallest(u32 r, u32 maxv) {  // sum of the r smallest values among counts >= MIN
+    if (r == 0) return 0;
+    int top = 7;
+    while (top > 0 && ((maxv >> (4 * top)) & 15u) == 0) --top;  // leading zero nibbles of the maximum
+    u32 prefix = 0, remaining = r;
+    u64 sumBelow = 0;
+    for (int nib = top; nib >= 0; --nib) {  // radix select, most significant nibble first
+      u32 hist[16];
+      u64 hsum[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { hist[i] = 0; hsum[i] = 0; }
+      const u32 shift = 4 * nib;
+      const u32 himask = (nib == 7) ? 0u : (~0u << (shift + 4));
+      for (u32 i = 0; i < C; ++i) {
+        const u32 v = cov[i];
+        if (v < P.min_count) continue;
+        if ((v & himask) != (prefix & himask)) continue;
+        const u32 d = (v >> shift) & 15u;
+        hist[d]++;
+        hsum[d] += v;
+      }
+      u32 d = 0;
+      for (; d < 15; ++d) {
+        if (hist[d] >= remaining) break;
+        remaining -= hist[d];
+        sumBelow += hsum[d];
+      }
+      prefix |= d << shift;
+    }
+    // `remaining` copies of value `prefix` complete the r smallest
+    return sumBelow + (u64)remaining * prefix;
+  }
+
+  TALC_HD double seq_error_threshold() {
+    u32 n = 0, maxv = 0;
+    for (u32 i = 0; i < C; ++i) {
+      n += (cov[i] >= P.min_count) ? 1 : 0;
+      maxv = cov[i] > maxv ? cov[i] : maxv;
+    }
+    u32 first, last;
+    if (n > 10) {
+      first = (u32)(0.15 * (double)n);
+      last = (u32)(0.90 * (double)n);
+    } else {
+      first = 0;
+      last = n;
+    }
+    double robMean = (double)P.min_count;  // Q2
+    const u64 s = sum_of_smallest(last, maxv) - sum_of_smallest(first, maxv);
+    robMean += (double)s;
+    robMean /= (double)(last - first);
+    return robMean * P.sr_error;
+  }
+
+  // ------------------------------------------------------------------ Read.cpp:440-489
+  TALC_HD bool find_in_regions() {
+    // first pass counts, second pass fills
+    u32 n = 0;
+    bool state = false;
+    if (C > 1) {
+      for (u32 pos = 0; pos < C; ++pos) {
+        const bool in = cov[pos] >= P.min_count;
+        if (in & !state) state = true;
+        else if (!in & state) { ++n; state = false; }
+      }
+      if (state) ++n;
+    }
+    nregs = n;
+    regs = (Region*)keep.alloc((n ? n : 1) * sizeof(Region));
+    if (!regs) return false;
+    u32 k = 0, cs = 0;
+    state = false;
+    if (C > 1) {
+      for (u32 pos = 0; pos < C; ++pos) {
+        const bool in = cov[pos] >= P.min_count;
+        if (in & !state) { cs = pos; state = true; }
+        else if (!in & state) { regs[k].start = cs; regs[k].end = pos - 1; ++k; state = false; }
+      }
+      if (state) { regs[k].start = cs; regs[k].end = C - 1; ++k; }
+    }
+    return n > 0;
+  }
+
+  // ------------------------------------------------------------------ Read.cpp:524-600
+  TALC_HD void analyze_in_regions(double thr) {
+    // kept regions overwrite the front of a second array; the input list is mutated in place (Q5)
+    Region* kept = (Region*)keep.alloc((nregs ? nregs : 1) * sizeof(Region));
+    if (!kept) return;
+    u32 nk = 0;
+    for (u32 reg = 0; reg < nregs; ++reg) {
+      int span = 0;
+      bool OK = true;
+      u32 ns = regs[reg].start;
+      const bool lastAndNone = ((nregs == reg + 1) & (nk == 0));
+      const int degL = out_degree(ns, false);
+      if (!lastAndNone & (degL == 0) & (ns != 0)) {
+        OK = false;
+        while ((ns < regs[reg].end) & !OK) {
+          ++ns;
+          if (out_degree(ns, false) > 1) OK = true;  // Q3
+        }
+      }
+      u32 ne = regs[reg].end;
+      if (OK & !lastAndNone) {
+        const int degR = out_degree(ne, true);
+        if ((degR == 0) & (ne != C - 1)) {
+          OK = false;
+          while ((ne > regs[reg].start) & !OK) {  // Q4
+            --ne;
+            if (out_degree(ne, true) > 1) OK = true;
+          }
+        }
+      }
+      if (OK) {
+        if (reg + 1 < nregs) span = ((int)regs[reg + 1].start - (int)(ne + K()));
+        if (span < 0) {
+          if ((int)regs[reg + 1].end + span >= (int)regs[reg + 1].start) regs[reg + 1].start -= span;
+          else {
+            regs[reg + 1].start = ns;
+            OK = false;
+          }
+        }
+        if (OK) {
+          u32 c = 0;
+          for (u32 i = ns; i <= ne; ++i) c = c < cov[i] ? cov[i] : c;
+          if (!expected_by_model(c, (u32)thr, P.alpha, true)) {
+            kept[nk].start = ns;
+            kept[nk].end = ne;
+            ++nk;
+          }
+        }
+      }
+    }
+    if (nk > 0) {
+      for (u32 i = 0; i < nk; ++i) regs[i] = kept[i];
+      nregs = nk;
+    }
+  }
+
+  // ------------------------------------------------------------------ Read.cpp:214-258
+  TALC_HD bool initial_structure() {
+    const u32 Lr = rd.len;
+    u64 len = 0;
+    headPresent = tailPresent = false;
+    if (regs[0].start > 0) { headPresent = true; len += regs[0].start; }
+    if (regs[nregs - 1].end + 1 < C) { tailPresent = true; len += Lr - (regs[nregs - 1].end + K()); }
+    for (u32 i = 0; i + 1 < nregs; ++i) {
+      if (regs[i].end + K() < regs[i].start) return false;  // undefined in the reference; cannot sum to L
+      len += regs[i].end + K() - regs[i].start;
+      if (regs[i + 1].start > regs[i].end + K()) len += regs[i + 1].start - (regs[i].end + K());
+    }
+    if (regs[nregs - 1].end + K() < regs[nregs - 1].start) return false;
+    len += regs[nregs - 1].end + K() - regs[nregs - 1].start;
+    return len == Lr;
+  }
+
+  // ------------------------------------------------------------------ Explorer.cpp:402-411
+  TALC_HD void sort_anchors(AnchorRec* a, u32 n) {
+    const int cc = (int)(noise / P.sr_error);
+    std_sort(a, a + n, [cc](const AnchorRec& l, const AnchorRec& r) {
+      int dl = cc - (int)l.count;
+      int dr = cc - (int)r.count;
+      dl = dl < 0 ? -dl : dl;
+      dr = dr < 0 ? -dr : dr;
+      return dl < dr;
+    });
+  }
+
+  TALC_HD u64 read_kmer(u32 pos) {  // anchors sit on k-mers with count >= MIN, hence without N
+    bool ok;
+    return rd.kmer_at(pos, K(), ok);
+  }
+
+  // Explorer.cpp:413-478 (LEFT region: scan from its last k-mer down) and :480-543 (RIGHT region:
+  // scan from its first k-mer up).  `left` selects which.
+  TALC_HD bool build_anchors(bool left) {
+    const Region& rg = left ? L : R;
+    const u32 nbKmers = rg.end - rg.start + 1;
+    const u32 pivot = left ? rg.end : rg.start;
+    const u32 limit = left ? rg.start : rg.end;
+    const u32 want = kMinStartAnchors < nbKmers ? (u32)kMinStartAnchors : nbKmers;
+    // anchorPos has at most nbKmers entries; anchors at most that plus the top-up
+    u32* anchorPos = (u32*)scratch.alloc(nbKmers * 4);
+    AnchorRec* out = (AnchorRec*)scratch.alloc((nbKmers + 4) * sizeof(AnchorRec));
+    if (!anchorPos || !out) return false;
+    u32 nPos = 0, nOut = 0;
+    bool goFurther = true;
+    double current_count = (double)cov[pivot];
+    double next_count = 0;
+    u32 j = pivot;
+    anchorPos[nPos++] = pivot;
+    while (goFurther & (left ? (j >= limit + 1) : ((j + 1) <= limit))) {
+      const u32 q = left ? j - 1 : j + 1;
+      next_count = (double)cov[q];
+      if ((next_count >= P.min_count) & (next_count < kMaxInCount))
+        goFurther = expected_by_last_node((u32)next_count, (u32)current_count, P.alpha);
+      else goFurther = false;
+      if (!goFurther & (current_count >= P.min_count) & (next_count >= P.min_count) & (next_count < kMaxInCount)) {
+        anchorPos[nPos++] = q;
+        goFurther = true;
+        current_count = next_count;
+      }
+      if (left) --j; else ++j;
+    }
+    for (u32 anc = 0; anc < nPos; ++anc) {
+      const int degree = out_degree(anchorPos[anc], left);  // LEFT region looks RIGHT, and vice versa
+      if ((anc == 0) || ((anc != 0) & (degree > 1))) {
+        out[nOut].kmer = read_kmer(anchorPos[anc]);
+        out[nOut].pos = anchorPos[anc];
+        out[nOut].count = cov[anc];  // Q6: coverage index is the loop index, not the position
+        ++nOut;
+      }
+    }
+    if (nOut < want) {
+      j = pivot;
+      goFurther = true;
+      while ((left ? (j >= limit + 1) : ((j + 1) <= limit)) & (nOut < want)) {
+        const u32 q = left ? j - 1 : j + 1;
+        if (nOut > 0) goFurther &= (out[0].pos != q);  // Q7: only index 0 is ever examined
+        if (!goFurther) break;  // sticky: the reference spins on without any effect (Q8)
+        {
+          const int degree = out_degree(q, left);
+          if (degree > 1) {
+            out[nOut].kmer = read_kmer(q);
+            out[nOut].pos = q;
+            out[nOut].count = cov[q];
+            ++nOut;
+          }
+        }
+        --j;  // Q8: the RIGHT-hand variant also decrements; j wraps below zero and the loop ends
+      }
+    }
+    sort_anchors(out, nOut);
+    if (left) { ancL = out; nAncL = nOut; }
+    else { ancR = out; nAncR = nOut; }
+    return true;
+  }
+
+  // ------------------------------------------------------------------ trail slots
+  TALC_HD bool setup_search(u32 pathMax) {
+    slotWords = (K() + pathMax + 2 + 31) / 32 + 1;
+    maxT = wide ? 208u : 48u;
+    cur = (Trail*)scratch.alloc(maxT * sizeof(Trail));
+    nxt = (Trail*)scratch.alloc(maxT * sizeof(Trail));
+    if (!cur || !nxt) return false;
+    // slots: as many as fit, up to one per possible trail (cur + nxt) plus a few spares
+    const u32 wantSlots = 2 * maxT + 8;
+    u32 avail = scratch.cap - scratch.top;
+    // leave room for DP scratch (horizontal deltas, X-drop diagonals, bridge copies)
+    const u32 reserve = wide ? (avail / 2) : (avail / 2);
+    avail -= reserve;
+    u32 n = avail / (slotWords * 8 + 2);
+    if (n > wantSlots) n = wantSlots;
+    if (n < 6) { scratch.overflow = 1; return false; }
+    nSlots = n;
+    freeList = (u16*)scratch.alloc(n * 2);
+    slotPool = (u64*)scratch.alloc(n * slotWords * 8);
+    if (!freeList || !slotPool) return false;
+    nFree = n;
+    for (u32 i = 0; i < n; ++i) freeList[i] = (u16)(n - 1 - i);
+    nCur = nNxt = 0;
+    return true;
+  }
+  TALC_HD u64* slot_ptr(u32 s) { return slotPool + (u64)s * slotWords; }
+  TALC_HD int slot_alloc() {
+    if (nFree == 0) { scratch.overflow = 1; return -1; }
+    return (int)freeList[--nFree];
+  }
+  TALC_HD void slot_free(u32 s) { freeList[nFree++] = (u16)s; }
+  TALC_HD void slot_copy(u32 dst, u32 src, u32 nbases) {
+    const u32 nw = (nbases + 31) / 32;
+    u64* d = slot_ptr(dst);
+    const u64* s = slot_ptr(src);
+    for (u32 i = 0; i < nw; ++i) d[i] = s[i];
+  }
+
+  // root trail: the anchor k-mer in walk order (Trail.cpp:57-65)
+  TALC_HD bool push_root(const AnchorRec& a) {
+    const int s = slot_alloc();
+    if (s < 0) return false;
+    u64* w = slot_ptr((u32)s);
+    for (u32 i = 0; i < slotWords; ++i) w[i] = 0;
+    for (u32 i = 0; i < K(); ++i) {
+      // walk order: RIGHT = k-mer as is, LEFT = k-mer reversed
+      const u32 src = dirRight ? i : (K() - 1 - i);
+      const u32 c = (u32)((a.kmer >> (2 * (K() - 1 - src))) & 3ull);
+      path_set(w, i, c);
+    }
+    Trail t;
+    t.kmer = a.kmer;
+    t.dist = 0;
+    t.count = cov[a.pos];
+    t.score = 0;
+    t.slot = (u16)s;
+    t.failures = 0;
+    t.pad = 0;
+    cur[0] = t;
+    nCur = 1;
+    return true;
+  }
+
+  // Trail.cpp:289-302 + SeqAn Finder/Pattern<Horspool>: does the child's last k-mer already occur in
+  // the parent's sequence, first occurrence at a position > 0 (Q17)?  parent sequence = slot, plen bases.
+  TALC_HD bool already_got_there(u64 needle, const u64* w, u32 plen) {
+    const u32 k = K();
+    if (!(plen > k)) return false;
+    const u32 stride = (P.cycle_mode == 0) ? k : 1u;
+    if (dirRight) {
+      for (u32 p = 0; p + k <= plen; p += stride)
+        if (path_kmer_fwd(w, p, k) == needle) return p > 0;
+      return false;
+    }
+    // LEFT: actual sequence is the reversed walk; actual window p <-> walk window plen-k-p, reversed
+    u64 rev = 0;
+    for (u32 i = 0; i < k; ++i) rev |= ((needle >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
+    for (u32 p = 0; p + k <= plen; p += stride)
+      if (path_kmer_fwd(w, plen - k - p, k) == rev) return p > 0;
+    return false;
+  }
+
+  // ------------------------------------------------------------------ gardening, Explorer.cpp:773-865
+  // kept[] receives indices into nxt (duplicates possible, Q16); returns isComplex
+  TALC_HD bool gardening(u32* kept, u32& nKept) {
+    if (ctr) ctr->ev_gardening++;
+    const u32 n = nNxt;
+    const u32 MAXP = P.max_branches;
+    nKept = 0;
+    const u32 mk = scratch.mark();
+    GardenKey* t1 = (GardenKey*)scratch.alloc(n * sizeof(GardenKey));
+    GardenRank* rankings = (GardenRank*)scratch.alloc(n * sizeof(GardenRank));
+    GardenRank* newr = (GardenRank*)scratch.alloc((n + 1) * sizeof(GardenRank));
+    if (!t1 || !rankings || !newr) return false;
+    u32 nNew = 0;
+    bool isComplex = false;
+    u32 nb = n < MAXP ? n : MAXP;
+    for (u32 t = 0; t < n; ++t) {
+      rankings[t].idx = t; rankings[t].r1 = 0; rankings[t].r2 = 0; rankings[t].sum = 0;
+      t1[t].idx = t; t1[t].score = nxt[t].score; t1[t].dist = nxt[t].dist;
+    }
+    std_sort(t1, t1 + n, [](const GardenKey& l, const GardenKey& r) { return l.score > r.score; });
+    {
+      u32 rk = 0;
+      rankings[t1[0].idx].r1 = 0;
+      for (u32 t = 1; t < n; ++t) {
+        if (!(t1[t].score == t1[t - 1].score)) rk++;
+        rankings[t1[t].idx].r1 = rk;
+      }
+    }
+    for (u32 t = 0; t < n; ++t) { t1[t].idx = t; t1[t].score = nxt[t].score; t1[t].dist = nxt[t].dist; }
+    std_sort(t1, t1 + n, [](const GardenKey& l, const GardenKey& r) { return l.dist < r.dist; });
+    {
+      u32 rk = 0;
+      rankings[t1[0].idx].r2 = 0;
+      for (u32 t = 1; t < n; ++t) {
+        if (!(t1[t].dist == t1[t - 1].dist)) rk++;
+        rankings[t1[t].idx].r2 = rk;
+      }
+    }
+    for (u32 t = 0; t < n; ++t) {
+      rankings[t].sum = rankings[t].r1 + rankings[t].r2;
+      if ((rankings[t].sum == 0) || (n <= MAXP)) newr[nNew++] = rankings[t];
+    }
+    if (nNew == 0) {
+      std_sort(rankings, rankings + n, [](const GardenRank& l, const GardenRank& r) { return l.r1 < r.r1; });
+      u32 s = 0;
+      bool ties = false;
+      do {
+        if ((s <= nb) || ties) newr[nNew++] = rankings[s];
+        if (s < n - 1) ties = (rankings[s + 1].r1 == rankings[s].r1);
+        ++s;
+      } while (((s <= nb) || ties) & (s < n));
+      if (nNew > MAXP) {
+        const GardenRank atMax = newr[MAXP];
+        if (newr[0].r1 != atMax.r1) {
+          --nNew;
+          ties = true;
+          while ((nNew >= MAXP) & ties) {
+            ties = (newr[nNew - 1].r1 == newr[nNew - 2].r1);
+            ties |= (nNew >= MAXP);
+            if (ties) --nNew;
+          }
+        }
+        if ((nNew > MAXP) & (newr[0].r1 == atMax.r1)) {  // Q16
+          isComplex = true;
+          std_sort(newr, newr + nNew, [](const GardenRank& l, const GardenRank& r) { return l.r2 < r.r2; });
+          for (u32 t = 0; t < MAXP; ++t) kept[nKept++] = newr[t].idx;
+        }
+      }
+      for (u32 t = 0; t < nNew; ++t) kept[nKept++] = newr[t].idx;
+    } else {
+      for (u32 t = 0; t < nNew; ++t) kept[nKept++] = newr[t].idx;
+    }
+    scratch.release(mk);
+    return isComplex;
+  }
+
+  // replace cur by nxt[kept[..]]; trails not kept release their slots, duplicates get copies
+  TALC_HD bool adopt_kept(const u32* kept, u32 nKept, u32 plen) {
+    if (nKept > maxT) { scratch.overflow = 1; return false; }
+    const u32 mk = scratch.mark();
+    u8* used = (u8*)scratch.alloc(nNxt ? nNxt : 1);
+    if (!used) return false;
+    for (u32 i = 0; i < nNxt; ++i) used[i] = 0;
+    for (u32 i = 0; i < nKept; ++i) used[kept[i]] = 1;
+    for (u32 i = 0; i < nNxt; ++i)
+      if (!used[i]) slot_free(nxt[i].slot);
+    for (u32 i = 0; i < nNxt; ++i) used[i] = 0;
+    for (u32 i = 0; i < nKept; ++i) {
+      Trail t = nxt[kept[i]];
+      if (used[kept[i]]) {  // duplicate of an already adopted trail: private copy of the sequence
+        const int s = slot_alloc();
+        if (s < 0) { scratch.release(mk); return false; }
+        slot_copy((u32)s, t.slot, plen);
+        t.slot = (u16)s;
+      }
+      used[kept[i]] = 1;
+      cur[i] = t;
+    }
+    nCur = nKept;
+    scratch.release(mk);
+    return true;
+  }
+  TALC_HD void adopt_all() {
+    Trail* t = cur; cur = nxt; nxt = t;
+    nCur = nNxt;
+  }
+
+  // ------------------------------------------------------------------ inner search, Explorer.cpp:868-989
+  struct BridgeRec {
+    i32 score;       // -editDistance (Trajectory.cpp:241)
+    double idscore;  // LCS / max(len)  (:242)
+    double md;       // Q22
+    u32 leftAnchor, rightAnchor;
+    u32 cutLen;      // sequence length after cutAnchors
+    u32 fullLen;
+    i32 seqSlot;     // index of the retained packed copy, -1 if not retained
+    bool ok;
+  };
+
+  // fold of findBestBridge (Trajectory.cpp:282-303) over a prefix; also usable incrementally
+  TALC_HD static bool fold_better(i32 score, double md, i32 bscore, double bmd) {
+    if (score > bscore) return true;
+    if (score == bscore && md > bmd) return true;  // Q21: later entry with larger mean distance wins
+    return false;
+  }
+
+  TALC_HD bool search_bridge(Piece& weakOut) {
+    const u32 k = K();
+    const AnchorRec* anchors = dirRight ? ancL : ancR;
+    const u32 nAnch = dirRight ? nAncL : nAncR;
+    const AnchorRec* aims = dirRight ? ancR : ancL;
+    const u32 nAims = dirRight ? nAncR : nAncL;
+    u32 limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
+    bool found = false;
+    const u32 mk0 = scratch.mark();
+    for (u32 s = 0; s < limit && !found; ++s) {
+      scratch.release(mk0);
+      if (ctr) ctr->gap_attempts++;
+      const u32 whichStart = anchors[s].pos;
+      u32 gapLen = 0;
+      if (dirRight & (whichStart + k < R.start)) gapLen = R.start - (whichStart + k);
+      else if (!dirRight & (L.end + k < whichStart)) gapLen = whichStart - (L.end + k);
+      const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(3 * k));
+      RefView ref;
+      ref.s = rd.s;
+      if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = R.end + k - whichStart; }
+      else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k - L.start; }
+      if (!setup_search(pathMax)) return false;
+      if (!push_root(anchors[s])) return false;
+      // bridges: metadata for all, sequences only for running-best record setters
+      const u32 maxBridges = wide ? 4096u : 96u;
+      const u32 maxKeep = wide ? 64u : 6u;
+      BridgeRec* br = (BridgeRec*)scratch.alloc(maxBridges * sizeof(BridgeRec));
+      u64* brSeq = (u64*)scratch.alloc(maxKeep * slotWords * 8);
+      if (!br || !brSeq) return false;
+      u32 nBr = 0, nBrSeq = 0;
+      i32 runScore = 0;
+      double runMd = 0;
+      bool runHave = false;
+
+      u32 step = 0;
+      const SeqView refv = view_of(ref);
+      while ((nCur > 0) & (nCur <= kMaxInnerPaths) & (step < pathMax)) {
+        // ---- oneMoreStep, Explorer.cpp:546-612
+        const u32 plen = k + step;  // every trail of the frontier has this length
+        if (ctr) { ctr->steps_inner++; ctr->frontier_sum += nCur; }
+        nNxt = 0;
+        const bool complex_ = (nCur > P.max_branches);
+        for (u32 t = 0; t < nCur; ++t) {
+          const Trail par = cur[t];
+          u32 cnt[4], col[4];
+          table_next_counts(T, par.kmer, dirRight, k, cnt, col);
+          if (ctr) ctr->lookups_walk += 4;
+          u8 tag[4];
+          double dist[4];
+          const int nt = tag_next_nodes(cnt, col, par.count, P, complex_, tag, dist);
+          u32 nChildren = 0;
+          for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
+          bool parentSlotTaken = false;
+          for (int i = 0; i < nt; ++i) {
+            if (tag[i] == kUnexpected) continue;
+            Trail ch;
+            ch.kmer = kmer_next(par.kmer, (u32)i, dirRight, k);
+            ch.count = cnt[i];
+            ch.score = par.score;
+            ch.failures = par.failures;
+            ch.dist = par.dist + dist[i];
+            ch.pad = 0;
+            // sequence: a single child extends the parent's slot in place, siblings copy it
+            if (nChildren == 1) {
+              ch.slot = par.slot;
+              parentSlotTaken = true;
+            } else {
+              const int sl = slot_alloc();
+              if (sl < 0) return false;
+              slot_copy((u32)sl, par.slot, plen);
+              ch.slot = (u16)sl;
+            }
+            // cycle test looks at the parent's sequence only, so it may run before the append
+            bool aim = false;
+            u32 aimPos = 0;
+            for (u32 a = 0; a < nAims; ++a) {  // Trail.cpp:273-285, first match in sorted aim order
+              if (aims[a].kmer == ch.kmer) { aim = true; aimPos = aims[a].pos; break; }
+            }
+            bool drop = false;
+            if (!aim) {
+              if (already_got_there(ch.kmer, slot_ptr(par.slot), plen)) {
+                if (ctr) ctr->ev_cycle++;
+                drop = true;
+              }
+            }
+            path_set(slot_ptr(ch.slot), plen, (u32)i);
+            if (aim) {
+              // recordBridge (:1097) + scoreSequence + cutAnchors evaluated now; inputs are final
+              if (ctr) ctr->ev_bridge++;
+              if (nBr >= maxBridges) { scratch.overflow = 1; return false; }
+              BridgeRec b;
+              const u32 clen = plen + 1;
+              b.fullLen = clen;
+              b.md = ch.dist / ((double)clen + 0.01);
+              b.leftAnchor = dirRight ? whichStart : aimPos;
+              b.rightAnchor = dirRight ? aimPos : whichStart;
+              const SeqView pv = view_of_path(slot_ptr(ch.slot), clen);
+              b.score = -nw_distance(refv, ref.len, pv, clen, scratch, &dps);
+              const int lcs = lcs_length(refv, ref.len, pv, clen, scratch, &dps);
+              b.idscore = (double)lcs / (double)(ref.len > clen ? ref.len : clen);
+              // cutAnchors INNER (Trajectory.cpp:176-197), limit = RIGHT.end
+              b.ok = true;
+              b.cutLen = 0;
+              if (clen >= 2 * k) b.cutLen = clen - 2 * k;
+              else if ((clen < 2 * k) & (clen > k)) {
+                if (b.rightAnchor + 2 * k - clen <= R.end) b.rightAnchor = b.rightAnchor + 2 * k - clen;
+                else b.ok = false;
+              } else b.ok = false;
+              b.seqSlot = -1;
+              if (!runHave || fold_better(b.score, b.md, runScore, runMd)) {
+                runHave = true;
+                runScore = b.score;
+                runMd = b.md;
+                if (nBrSeq >= maxKeep) { scratch.overflow = 1; return false; }
+                u64* dst = brSeq + (u64)nBrSeq * slotWords;
+                const u64* src = slot_ptr(ch.slot);
+                for (u32 wi = 0; wi < (clen + 31) / 32; ++wi) dst[wi] = src[wi];
+                b.seqSlot = (i32)nBrSeq++;
+              }
+              br[nBr++] = b;
+              if (clen > ref.len) drop = true;  // Q10: otherwise the trail keeps exploring
+            }
+            if (drop) {
+              if (ch.slot != par.slot) slot_free(ch.slot);
+              else parentSlotTaken = false;
+            } else {
+              if (nNxt >= maxT) { scratch.overflow = 1; return false; }
+              nxt[nNxt++] = ch;
+            }
+          }
+          if (!parentSlotTaken) slot_free(par.slot);
+        }
+        ++step;
+        if ((nNxt > P.max_branches) & (step % kCheckInterval == 0)) {
+          // scoreBridges, Explorer.cpp:689-706: reference truncated to K+step+WINDOW (walk order)
+          u32 bound = k + step + P.window;
+          const u32 rn = (bound >= ref.len) ? ref.len : bound;
+          if (P.q11_zero) {
+            for (u32 j = 0; j < nNxt; ++j) {
+              const SeqView pv = view_of_path(slot_ptr(nxt[j].slot), k + step);
+              nxt[j].score = overlap_score(refv, rn, pv, k + step, scratch, &dps);
+            }
+          }
+          const u32 mkg = scratch.mark();
+          u32* kept = (u32*)scratch.alloc((nNxt + P.max_branches + 1) * 4);
+          if (!kept) return false;
+          u32 nKept = 0;
+          complexRegion |= gardening(kept, nKept);
+          if (scratch.overflow) return false;
+          if (!adopt_kept(kept, nKept, k + step)) return false;
+          scratch.release(mkg);
+        } else {
+          adopt_all();
+        }
+        if (scratch.overflow) return false;
+      }
+      // release frontier slots (the attempt is over)
+      if (nBr > 0) {
+        // Q9: if cutAnchors rejected some bridges the survivors are the FIRST nOk entries
+        u32 nOk = 0;
+        for (u32 t = 0; t < nBr; ++t) nOk += br[t].ok ? 1 : 0;
+        const u32 nUse = nOk;  // == nBr when nothing was rejected
+        if (nUse > 0) {
+          u32 best = 0;
+          for (u32 i = 1; i < nUse; ++i)
+            if (br[i].score > br[best].score) best = i;
+          for (u32 i = best + 1; i < nUse; ++i)
+            if (br[i].score == br[best].score && br[i].md > br[best].md) best = i;  // sequential update == Q21
+          const BridgeRec& B = br[best];
+          // a rejected bridge inside the surviving prefix has had its sequence emptied (Trajectory.cpp:208)
+          const u32 bestLen = B.ok ? B.cutLen : 0;
+          const double diff = (double)weakLen - (double)bestLen;
+          if ((diff < weakLen * 0.05 || ((weakLen < 6) & (bestLen < 6))) & (B.idscore >= P.min_inner)) {  // Q13
+            L.end = B.leftAnchor;
+            R.start = B.rightAnchor;
+            // corrected weak sequence = path without its two anchors, in read orientation
+            u8* dst = (u8*)keep.alloc(bestLen ? bestLen : 1);
+            if (!dst) return false;
+            if (bestLen > 0) {
+              if (B.seqSlot < 0) { scratch.overflow = 1; return false; }  // cannot happen: see fold argument
+              const u64* w = brSeq + (u64)B.seqSlot * slotWords;
+              PathView pv; pv.w = w; pv.len = B.fullLen;
+              for (u32 i = 0; i < bestLen; ++i) {
+                const u32 wi = dirRight ? (k + i) : (B.fullLen - k - 1 - i);
+                dst[i] = code_char(pv.code(wi));
+              }
+            }
+            weakOut.off = (u32)(dst - keep.base);
+            weakOut.len = (i32)bestLen;
+            found = true;
+          }
+        }
+      }
+    }
+    scratch.release(mk0);
+    return found;
+  }
+
+  // ------------------------------------------------------------------ border search
+  // Trail::seedAndExtend, Trail.cpp:193-216 (reference string vs this trail)
+  TALC_HD bool trail_seed_extend(Trail& t, u32 tlen, const SeqView& refv, int xdrop) {
+    const SeqView pv = view_of_path(slot_ptr(t.slot), tlen);
+    const SeedExt e = seed_and_extension(refv, pv, xdrop, dirRight, K(), scratch, wide, &dps);
+    bool ok = (e.cand_ext == tlen);
+    if (!ok) t.failures++;
+    else t.failures = 0;
+    t.score = e.score;
+    ok = (t.failures <= kMaxBorderFailures);
+    ok &= !e.stop;
+    return ok;
+  }
+
+  // Trajectory.cpp:482-503
+  TALC_HD SeedExt find_stop_position(const SeqView& refArg, const SeqView& candArg, int xdrop) {
+    int xdrop1 = xdrop;
+    bool goFurther = true;
+    SeedExt ext, next;
+    next = seed_and_extension(refArg, candArg, xdrop1, dirRight, K(), scratch, wide, &dps);
+    do {
+      --xdrop1;
+      ext = next;
+      next = seed_and_extension(refArg, candArg, xdrop1, dirRight, K(), scratch, wide, &dps);  // Q20
+      if (next.cand_ext < ext.cand_ext) goFurther = false;
+    } while (goFurther & (xdrop1 > 0));
+    return ext;
+  }
+
+  // Explorer::recordEdge, Explorer.cpp:1103-1118, folded straight into the running best of its list
+  TALC_HD bool record_edge(const Trail& t, u32 tlen, const RefView& ref, u32 whichStart, EdgeBest& bestLong,
+                           EdgeBest& bestShort) {
+    if (ctr) ctr->ev_edge++;
+    const u32 k = K();
+    // trim (Trajectory.cpp:89-112): drop failures*6 bases from the walking end
+    u32 len = tlen;
+    const u32 nbBases = (u32)t.failures * kCheckInterval;
+    if (len >= nbBases + k) len -= nbBases;
+    const bool shorter = (len <= ref.len);
+    const SeqView pv = view_of_path(slot_ptr(t.slot), len);
+    const SeqView refv = view_of(ref);
+    const int xdrop1 = (int)t.score * (-1);
+    SeedExt er;
+    u32 pathKeep, refFrom;
+    if (!shorter) {  // reshape, Trajectory.cpp:128-133: the path plays the reference role
+      er = find_stop_position(pv, refv, xdrop1);
+      pathKeep = er.ref_ext;
+      refFrom = ref.len;
+    } else {
+      er = find_stop_position(refv, pv, xdrop1);
+      pathKeep = len;
+      refFrom = er.ref_ext;
+    }
+    if (scratch.overflow) return false;
+    // computePercentID (Trajectory.cpp:505-528) on the two extensions
+    const SeqView& ea = shorter ? refv : pv;   // "refExtension" argument order of getSeedAndExtension
+    const SeqView& eb = shorter ? pv : refv;
+    const u32 la = er.ref_ext, lb = er.cand_ext;
+    double id;
+    {
+      const int l = (la > 0 && lb > 0) ? lcs_length(ea, la, eb, lb, scratch, &dps) : 0;
+      const double longer = (lb <= la) ? (double)la : (double)lb;
+      id = (double)l / longer;
+    }
+    const double score = (double)er.score;
+    const u32 newLen = pathKeep + (ref.len - refFrom);
+    // cutAnchors HEAD/TAIL (Trajectory.cpp:168-175) never rejects; it only empties short sequences
+    EdgeBest& dst = shorter ? bestShort : bestLong;
+    const double md = t.dist / ((double)tlen + 0.01);
+    bool better;
+    if (!dst.have) better = true;
+    else if (score > dst.score) better = true;
+    else better = (score == dst.score && md > dst.md);
+    if (better) {
+      dst.have = true;
+      dst.score = score;
+      dst.idscore = id;
+      dst.md = md;
+      dst.path_keep = pathKeep;
+      dst.ref_from = refFrom;
+      dst.anchor_pos = whichStart;
+      dst.ref_start = ref.start;
+      dst.ref_len = ref.len;
+      const u64* src = slot_ptr(t.slot);
+      for (u32 wi = 0; wi < (pathKeep + 31) / 32; ++wi) dst.seq[wi] = src[wi];
+    }
+    (void)newLen;
+    return true;
+  }
+
+  // Explorer::scoreEdges, Explorer.cpp:709-740 (operates on nxt)
+  TALC_HD bool score_edges(int& xdrop, u32 tlen, const RefView& ref, u32 whichStart, EdgeBest& bestLong,
+                           EdgeBest& bestShort) {
+    if (nNxt == 0) return true;
+    const SeqView refv = view_of(ref);
+    xdrop += 2;
+    int new_xdrop = 0;
+    const u32 mk = scratch.mark();
+    u8* okf = (u8*)scratch.alloc(nNxt);
+    if (!okf) return false;
+    u32 nSel = 0;
+    for (u32 t = 0; t < nNxt; ++t) {
+      const bool ok = trail_seed_extend(nxt[t], tlen, refv, xdrop);
+      if (scratch.overflow) return false;
+      okf[t] = ok ? 1 : 0;
+      if (ok) {
+        ++nSel;
+        const int current = (int)nxt[t].score * (-1);
+        if ((new_xdrop > current) || (new_xdrop == 0)) new_xdrop = current;  // Q14
+      }
+    }
+    xdrop = new_xdrop;
+    if (nSel == 0) {
+      for (u32 t = 0; t < nNxt; ++t) {
+        if (!record_edge(nxt[t], tlen, ref, whichStart, bestLong, bestShort)) return false;
+        slot_free(nxt[t].slot);
+      }
+      nNxt = 0;
+    } else {
+      u32 w = 0;
+      for (u32 t = 0; t < nNxt; ++t) {
+        if (okf[t]) nxt[w++] = nxt[t];
+        else slot_free(nxt[t].slot);
+      }
+      nNxt = w;
+    }
+    scratch.release(mk);
+    return true;
+  }
+
+  // Explorer::searchEdge, Explorer.cpp:992-1081
+  TALC_HD bool search_edge(Piece& weakOut) {
+    const u32 k = K();
+    const AnchorRec* anchors = dirRight ? ancL : ancR;
+    const u32 nAnch = dirRight ? nAncL : nAncR;
+    const u32 limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
+    // running bests of m_longPaths / m_shortPaths across all anchors
+    u32 maxGap = 0;
+    for (u32 s = 0; s < limit; ++s) {
+      const u32 g = (location == 0) ? anchors[s].pos : (rd.len - (anchors[s].pos + k));
+      maxGap = g > maxGap ? g : maxGap;
+    }
+    const u32 maxPath = (u32)(i32)(1.2 * (double)maxGap + (double)(2 * k));
+    const u32 bestWords = (k + maxPath + 2 + 31) / 32 + 1;
+    EdgeBest bestLong, bestShort;
+    bestLong.have = bestShort.have = false;
+    bestLong.seq = (u64*)scratch.alloc(bestWords * 8);
+    bestShort.seq = (u64*)scratch.alloc(bestWords * 8);
+    if (!bestLong.seq || !bestShort.seq) return false;
+    const u32 mk0 = scratch.mark();
+    for (u32 s = 0; s < limit; ++s) {
+      scratch.release(mk0);
+      int xdrop = (int)((int)kCheckInterval * 0.3 + 1);  // Q15: 2
+      const u32 whichStart = anchors[s].pos;
+      const u32 gapLen = (location == 0) ? whichStart : (rd.len - (whichStart + k));
+      const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(2 * k));
+      RefView ref;
+      ref.s = rd.s;
+      if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = rd.len - whichStart; }
+      else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k; }
+      const SeqView refv = view_of(ref);
+      if (!setup_search(pathMax)) return false;
+      if (!push_root(anchors[s])) return false;
+      u32 step = 0;
+      while ((nCur > 0) & (nCur <= kMaxInnerPaths) & (step < pathMax)) {
+        // ---- oneMoreStepInTheDark, Explorer.cpp:615-687
+        const u32 plen = k + step;
+        if (ctr) { ctr->steps_border++; ctr->frontier_sum += nCur; }
+        nNxt = 0;
+        const bool complex_ = (nCur > 7);
+        for (u32 t = 0; t < nCur; ++t) {
+          Trail par = cur[t];
+          u32 cnt[4], col[4];
+          table_next_counts(T, par.kmer, dirRight, k, cnt, col);
+          if (ctr) ctr->lookups_walk += 4;
+          u8 tag[4];
+          double dist[4];
+          const int nt = tag_next_nodes(cnt, col, par.count, P, complex_, tag, dist);
+          u32 nChildren = 0;
+          for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
+          bool parentSlotTaken = false;
+          for (int i = 0; i < nt; ++i) {
+            if (tag[i] == kUnexpected) continue;
+            Trail ch;
+            ch.kmer = kmer_next(par.kmer, (u32)i, dirRight, k);
+            ch.count = cnt[i];
+            ch.score = par.score;
+            ch.failures = par.failures;
+            ch.dist = par.dist + dist[i];
+            ch.pad = 0;
+            if (nChildren == 1) {
+              ch.slot = par.slot;
+              parentSlotTaken = true;
+            } else {
+              const int sl = slot_alloc();
+              if (sl < 0) return false;
+              slot_copy((u32)sl, par.slot, plen);
+              ch.slot = (u16)sl;
+            }
+            const bool cycle = already_got_there(ch.kmer, slot_ptr(par.slot), plen);
+            path_set(slot_ptr(ch.slot), plen, (u32)i);
+            if (cycle || (step + 1 > pathMax)) {
+              if (cycle && ctr) ctr->ev_cycle++;
+              trail_seed_extend(ch, plen + 1, refv, xdrop);
+              if (scratch.overflow) return false;
+              if (!record_edge(ch, plen + 1, ref, whichStart, bestLong, bestShort)) return false;
+              if (ch.slot != par.slot) slot_free(ch.slot);
+              else parentSlotTaken = false;
+            } else {
+              if (nNxt >= maxT) { scratch.overflow = 1; return false; }
+              nxt[nNxt++] = ch;
+            }
+          }
+          if (nChildren == 0) {  // dead end: the trail itself becomes a candidate
+            trail_seed_extend(par, plen, refv, xdrop);
+            if (scratch.overflow) return false;
+            if (!record_edge(par, plen, ref, whichStart, bestLong, bestShort)) return false;
+          }
+          if (!parentSlotTaken) slot_free(par.slot);
+        }
+        ++step;
+        if ((step % kCheckInterval == 0) || (nNxt >= kMaxBorderPaths)) {
+          if (!score_edges(xdrop, k + step, ref, whichStart, bestLong, bestShort)) return false;
+          if (nNxt > 5) {
+            const u32 mkg = scratch.mark();
+            u32* kept = (u32*)scratch.alloc((nNxt + P.max_branches + 1) * 4);
+            if (!kept) return false;
+            u32 nKept = 0;
+            complexRegion |= gardening(kept, nKept);
+            if (scratch.overflow) return false;
+            if (!adopt_kept(kept, nKept, k + step)) return false;
+            scratch.release(mkg);
+          } else
+            adopt_all();
+        } else
+          adopt_all();
+        if (scratch.overflow) return false;
+      }
+    }
+    bool found = false;
+    if (bestLong.have || bestShort.have) {
+      const EdgeBest& W = bestLong.have ? bestLong : bestShort;  // sortOutBestBorder, :310-329
+      const u32 newLen = W.path_keep + (W.ref_len - W.ref_from);
+      const u32 wlen = (newLen > k) ? (newLen - k) : 0;  // cutAnchors HEAD/TAIL
+      const double diff = (double)weakLen - (double)wlen;
+      double minScore;
+      if ((weakLen >= 300) || complexRegion) minScore = (0.75 > P.min_border) ? 0.75 : P.min_border;
+      else minScore = P.min_border;
+      if ((diff < weakLen * 0.05 || ((weakLen < 6) & (wlen < 6))) & (W.idscore >= minScore)) {
+        found = true;
+        if (location == 2) L.end = W.anchor_pos;
+        else R.start = W.anchor_pos;
+        u8* dst = (u8*)keep.alloc(wlen ? wlen : 1);
+        if (!dst) return false;
+        // walk-order sequence: trail prefix, then raw border; minus the first K (the anchor);
+        // TAIL is already in read orientation, HEAD is reversed
+        PathView pv; pv.w = W.seq; pv.len = W.path_keep;
+        for (u32 i = 0; i < wlen; ++i) {
+          const u32 wi = k + i;  // walk index
+          u8 ch;
+          if (wi < W.path_keep) ch = code_char(pv.code(wi));
+          else {
+            const u32 ri = W.ref_from + (wi - W.path_keep);
+            const i32 step = dirRight ? 1 : -1;
+            ch = code_char(base_code(rd.s[W.ref_start + (i32)ri * step]));
+          }
+          dst[dirRight ? i : (wlen - 1 - i)] = ch;
+        }
+        weakOut.off = (u32)(dst - keep.base);
+        weakOut.len = (i32)wlen;
+      }
+    }
+    return found;
+  }
+
+  // ------------------------------------------------------------------ per-read driver (main.cpp:258-296)
+  // Returns the status; on kReadOk the pieces describe the corrected read.
+  TALC_HD u8 run(const ReadJob& job) {
+    rd = job.rd;
+    cov = job.cov;
+    wide = job.wide;
+    dps.cells_nw = dps.cells_lcs = dps.cells_ovl = dps.cells_xdrop = 0;
+    const u32 k = K();
+    if (!((i32)rd.len > (i32)k)) return kReadShort;
+    C = rd.len - k + 1;
+    if (ctr) ctr->lookups_seg += C;
+    const u32 keepBytes = job.arena_bytes / 4;
+    keep.init(job.arena, keepBytes & ~7u);
+    scratch.init(job.arena + (keepBytes & ~7u), job.arena_bytes - (keepBytes & ~7u));
+    // Read::reCoverage gate (Read.cpp:190, Q1: strictly greater)
+    u32 nbIn = 0;
+    for (u32 i = 0; i < C; ++i) nbIn += (cov[i] > P.min_count) ? 1 : 0;
+    if (nbIn == 0) return kReadNoSolid;
+    // Read::defineStructure2 (Read.cpp:260-276)
+    bool checok = find_in_regions();
+    if (keep.overflow) return kReadOverflow;
+    noise = seq_error_threshold();
+    analyze_in_regions(noise);
+    if (keep.overflow) return kReadOverflow;
+    if (nregs > 0) checok &= initial_structure();
+    if (!checok) return kReadNoStructure;
+    headRaw = headPresent ? regs[0].start : 0;
+    tailRaw = tailPresent ? rd.len - (regs[nregs - 1].end + k) : 0;
+    gapPiece = (Piece*)keep.alloc((nregs ? nregs : 1) * sizeof(Piece));
+    if (!gapPiece) return kReadOverflow;
+    for (u32 i = 0; i + 1 < nregs; ++i) gapPiece[i].len = -1;
+    headPiece.len = tailPiece.len = -1;
+    complexRegion = false;
+    // Read::correct2 (Read.cpp:336-386)
+    for (u32 reg = 0; reg + 1 < nregs; ++reg) {
+      if (ctr) ctr->gaps++;
+      bool success = false;
+      for (int attempt = 0; attempt < 2 && !success; ++attempt) {
+        // initializeINNER (Explorer.cpp:228-243)
+        scratch.release(0);
+        location = 1;
+        dirRight = (attempt == 0);
+        L = regs[reg];
+        R = regs[reg + 1];
+        weakLen = R.start - (L.end + k);
+        if (!build_anchors(true) || !build_anchors(false)) return kReadOverflow;
+        Piece w;
+        success = search_bridge(w);
+        if (scratch.overflow || keep.overflow) return kReadOverflow;
+        if (success) gapPiece[reg] = w;
+      }
+      if (success && ctr) ctr->gaps_bridged++;
+      regs[reg] = L;  // updateINNER (Read.cpp:294-303)
+      regs[reg + 1] = R;
+    }
+    const u32 headLen = headRaw;  // region 0's start is untouched by the inner gaps
+    if (headPresent && headLen <= kBorderMaxLen) {
+      if (ctr) ctr->borders++;
+      scratch.release(0);
+      location = 0;
+      dirRight = false;
+      L.start = L.end = 0;
+      R = regs[0];
+      weakLen = R.start;
+      nAncL = 0;
+      if (!build_anchors(false)) return kReadOverflow;
+      Piece w;
+      const bool ok = search_edge(w);
+      if (scratch.overflow || keep.overflow) return kReadOverflow;
+      if (ok) {
+        if (ctr) ctr->borders_corrected++;
+        regs[0] = R;  // updateHEAD (Read.cpp:305-311)
+        headPiece = w;
+      }
+    }
+    const u32 tailLen = tailRaw;
+    if (tailPresent && tailLen <= kBorderMaxLen) {
+      if (ctr) ctr->borders++;
+      scratch.release(0);
+      location = 2;
+      dirRight = true;
+      R.start = R.end = 0;
+      L = regs[nregs - 1];
+      weakLen = rd.len - (L.end + k);
+      nAncR = 0;
+      if (!build_anchors(true)) return kReadOverflow;
+      Piece w;
+      const bool ok = search_edge(w);
+      if (scratch.overflow || keep.overflow) return kReadOverflow;
+      if (ok) {
+        if (ctr) ctr->borders_corrected++;
+        regs[nregs - 1] = L;  // updateTAIL (Read.cpp:313-318)
+        tailPiece = w;
+      }
+    }
+    return kReadOk;
+  }
+
+  // length of the corrected read (Read::updateCorrSeq, Read.cpp:320-326)
+  TALC_HD u32 corrected_length() const {
+    const u32 k = P.K;
+    u32 n = 0;
+    n += (headPiece.len >= 0) ? (u32)headPiece.len : (headPresent ? headRaw : 0);
+    for (u32 i = 0; i < nregs; ++i) {
+      n += regs[i].end + k - regs[i].start;
+      if (i + 1 < nregs) n += (gapPiece[i].len >= 0) ? (u32)gapPiece[i].len : gapRawLen(i);
+    }
+    n += (tailPiece.len >= 0) ? (u32)tailPiece.len : (tailPresent ? tailRaw : 0);
+    return n;
+  }
+  u32 headRaw, tailRaw;  // lengths of the raw head / tail as first defined
+  TALC_HD u32 gapRawLen(u32 i) const {
+    const u32 a = regs[i].end + P.K, b = regs[i + 1].start;
+    return b > a ? b - a : 0;
+  }
+  // write the corrected read as upper-case ASCII
+  TALC_HD void emit(u8* out) const {
+    const u32 k = P.K;
+    u32 o = 0;
+    if (headPiece.len >= 0) { for (i32 i = 0; i < headPiece.len; ++i) out[o++] = keep.base[headPiece.off + i]; }
+    else if (headPresent) { for (u32 i = 0; i < headRaw; ++i) out[o++] = code_char(rd.code(i)); }
+    for (u32 r = 0; r < nregs; ++r) {
+      for (u32 i = regs[r].start; i < regs[r].end + k; ++i) out[o++] = code_char(rd.code(i));
+      if (r + 1 < nregs) {
+        if (gapPiece[r].len >= 0) { for (i32 i = 0; i < gapPiece[r].len; ++i) out[o++] = keep.base[gapPiece[r].off + i]; }
+        else { for (u32 i = regs[r].end + k; i < regs[r + 1].start; ++i) out[o++] = code_char(rd.code(i)); }
+      }
+    }
+    if (tailPiece.len >= 0) { for (i32 i = 0; i < tailPiece.len; ++i) out[o++] = keep.base[tailPiece.off + i]; }
+    else if (tailPresent) { for (u32 i = rd.len - tailRaw; i < rd.len; ++i) out[o++] = code_char(rd.code(i)); }
+  }
+};
+
+}  // namespace talc

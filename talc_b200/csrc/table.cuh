@@ -1,0 +1,112 @@
+// table.cuh -- the k-mer count table in HBM (replaces the reference's
+// std::map<Dna5String, pair<uint,uint>> : Settings.cpp:26,50; queries Jellyfish.cpp:308-321,
+// 383-393,485-496).  Only equality look-ups are ever made, so an open-addressed hash is legal.
+//
+// Layout: power-of-two array of 16-byte slots {u64 key, u32 count, u32 colour}; two slots
+// share one 32-byte DRAM sector and probing walks sector by sector (pair-aligned linear
+// probing), so a hit or a miss in the home sector costs exactly one sector fetch.
+// Load factor <= 0.5.  Empty slots hold key = ~0 (keys use at most 60 bits).
+#pragma once
+#include "defs.cuh"
+
+namespace talc {
+
+struct __attribute__((aligned(16))) Slot {
+  u64 key;
+  u32 count;
+  u32 colour;
+};
+
+static const u64 kEmptyKey = ~0ull;
+
+struct TableView {
+  const Slot* slots;
+  u64 mask;  // capacity - 1 (capacity is a power of two >= 2)
+};
+
+TALC_HD u64 hash_kmer(u64 k) {  // murmur3 fmix64
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ Slot load_slot(const Slot* p) {
+  // one 16-byte read-only load; the two slots of a sector are fetched by two such loads
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  Slot s;
+  s.key = ((u64)v.y << 32) | v.x;
+  s.count = v.z;
+  s.colour = v.w;
+  return s;
+}
+#else
+inline Slot load_slot(const Slot* p) { return *p; }
+#endif
+
+// resolve one key against its already-fetched home sector; returns 1 hit, 0 definite miss, -1 keep probing
+TALC_HD int sector_resolve(const Slot& s0, const Slot& s1, u64 key, u32& count, u32& colour) {
+  if (s0.key == key) { count = s0.count; colour = s0.colour; return 1; }
+  if (s0.key == kEmptyKey) { count = 0; colour = 0; return 0; }
+  if (s1.key == key) { count = s1.count; colour = s1.colour; return 1; }
+  if (s1.key == kEmptyKey) { count = 0; colour = 0; return 0; }
+  return -1;
+}
+
+// continue a probe sequence past sector b
+TALC_HD bool table_probe_from(const TableView& t, u64 b, u64 key, u32& count, u32& colour) {
+  for (;;) {
+    b = (b + 2) & t.mask;
+    const Slot s0 = load_slot(t.slots + b);
+    const Slot s1 = load_slot(t.slots + b + 1);
+    const int r = sector_resolve(s0, s1, key, count, colour);
+    if (r >= 0) return r == 1;
+  }
+}
+
+// point look-up: (count, colour) or (0,0) when absent (Jellyfish.cpp:317-318,492-493)
+TALC_HD bool table_lookup(const TableView& t, u64 key, u32& count, u32& colour) {
+  const u64 b = hash_kmer(key) & t.mask & ~1ull;
+  const Slot s0 = load_slot(t.slots + b);
+  const Slot s1 = load_slot(t.slots + b + 1);
+  const int r = sector_resolve(s0, s1, key, count, colour);
+  if (r >= 0) return r == 1;
+  return table_probe_from(t, b, key, count, colour);
+}
+
+// the four successor counts in A,C,G,T order (Jellyfish.cpp:308-321): the four home sectors are
+// fetched together (8 independent 16-byte loads in flight), stragglers continue probing one by one
+TALC_HD void table_next_counts(const TableView& t, u64 kmer, bool right, u32 K, u32 cnt[4], u32 col[4]) {
+  u64 key[4], b[4];
+  Slot s0[4], s1[4];
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    key[i] = kmer_next(kmer, i, right, K);
+    b[i] = hash_kmer(key[i]) & t.mask & ~1ull;
+  }
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    s0[i] = load_slot(t.slots + b[i]);
+    s1[i] = load_slot(t.slots + b[i] + 1);
+  }
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    const int r = sector_resolve(s0[i], s1[i], key[i], cnt[i], col[i]);
+    if (r < 0) table_probe_from(t, b[i], key[i], cnt[i], col[i]);
+  }
+}
+
+// Jellyfish.cpp:383-393
+TALC_HD int table_out_degree(const TableView& t, u64 kmer, bool right, u32 K, u32 min_count) {
+  u32 cnt[4], col[4];
+  table_next_counts(t, kmer, right, K, cnt, col);
+  int d = 0;
+#pragma unroll
+  for (u32 b = 0; b < 4; ++b) d += (cnt[b] >= min_count) ? 1 : 0;
+  return d;
+}
+
+}  // namespace talc
