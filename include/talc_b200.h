@@ -1,0 +1,141 @@
+/* talc_b200.h -- C ABI of the B200 correction library (libtalc_b200.so).
+ *
+ * TALC (lbroseus/TALC) has no plugin / FFI interface of its own; the drop-in surface is the `talc`
+ * command line and its output files.  This ABI replaces the *internal seam* of the reference, i.e.
+ * exactly the calls main() makes on the hot path (all paths relative to /root/reference/src):
+ *
+ *   talc_table_load_dump / talc_table_load_packed
+ *       <- SR_DBG = buildCDBG(1, dump, jdump); decolourRepeatsFromDBG(SR_DBG, K);   main.cpp:231-232
+ *          (Jellyfish.cpp:236-295, utils.cpp:658-669)
+ *   talc_correct_batch / talc_correct_batch_device
+ *       <- the body of the OpenMP loop over reads                                  main.cpp:247-306
+ *          Read r(id,seq); if len>K: r.reCoverage() -> r.defineStructure2() -> r.correct2(); r.getCorrSeq()
+ *          (Read.cpp:174-386, Explorer.cpp, Trail.cpp, Trajectory.cpp)
+ *   talc_coverage_batch
+ *       <- getLRCountsInSR(seq, K, SR_DBG, ..)                                     Jellyfish.cpp:471-496
+ *   talc_table_lookup
+ *       <- dBG.count(kmer) / dBG.at(kmer)                                          Jellyfish.cpp:317-318,492-493
+ *   per-read `status[]` <- the two throwToLog() messages of main.cpp:290,294 (io.cpp:105-111)
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function returns 0 on success
+ * and a negative code on failure (message via talc_last_error); no exception crosses the boundary.
+ * The caller owns every buffer it passes in; the library owns its device memory inside talc_ctx.
+ * A context is bound to one CUDA device and is not thread-safe.  There is no CPU fallback: without a
+ * usable CUDA device talc_ctx_create fails.
+ *
+ * k-mers are 2-bit packed into uint64_t with the FIRST base in the MOST significant position
+ * (A=0, C=1, G=2, T=3), K <= 31.  Reads are ASCII (ACGTN, either case; anything else reads as N, the
+ * way SeqAn converts char -> Dna5); corrected reads come back as upper-case ACGTN.
+ */
+#ifndef TALC_B200_H
+#define TALC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct talc_ctx talc_ctx;
+
+/* Settings.cpp:33-69 (set by main.cpp:94-195 / Settings.cpp:74-123); defaults via talc_params_default */
+typedef struct talc_params {
+  uint32_t K;                       /* -k, 18..30 (main.cpp:112-116); up to 31 accepted by the library */
+  uint32_t min_count;               /* --MIN_COUNT        gp_MIN_COUNT (2)              */
+  uint32_t window_size;             /* --WINDOW_SIZE      gp_WINDOW_SIZE (9)            */
+  uint32_t max_nb_branches;         /* --MAX_NB_BRANCHES  gp_MAX_NB_COMPETING_PATHS (7) */
+  double alpha;                     /* --ALPHA_FOR_PRED   gp_ALPHA (2.57)               */
+  double sr_error_rate;             /* --SR_ERROR_RATE    gp_SR_ERROR_RATE (0.025)      */
+  double min_inner_score;           /* --MIN_INNER_SCORE  (0.7)                         */
+  double min_border_score;          /* --MIN_BORDER_SCORE (0.7)                         */
+  int32_t cycle_mode;               /* 0: SeqAn2 Horspool over mixed alphabets (default), 1: exact first occurrence */
+  int32_t q11_zero_init;            /* Explorer.cpp:705 uninitialised counter behaves as 0 (default 1) */
+} talc_params;
+
+/* per-read outcome: main.cpp:262 (short), :290 (no structure), :294 (no solid k-mer) */
+enum {
+  TALC_READ_OK = 0,
+  TALC_READ_NO_SOLID = 1,      /* log: "No solid kmer could be found."            */
+  TALC_READ_NO_STRUCTURE = 2,  /* log: "Unable to define convenient structure."   */
+  TALC_READ_SHORT = 3          /* len <= K: passed through, nothing logged        */
+};
+
+/* algorithmic work of a batch (properties of the algorithm on the input) and timings */
+typedef struct talc_counters {
+  uint64_t lookups_seg, lookups_deg, lookups_walk;
+  uint64_t steps_inner, steps_border, frontier_sum;
+  uint64_t cells_nw, cells_lcs, cells_ovl, cells_xdrop;
+  uint64_t gaps, gaps_bridged, gap_attempts, borders, borders_corrected;
+  uint64_t ev_gardening, ev_bridge, ev_edge, ev_cycle;
+  uint64_t bases_out, reads_ok, reads_overflow;
+  /* filled by the host side of the call */
+  uint64_t reads, bases_in, reads_second_tier, kernel_launches;
+  double ms_h2d, ms_coverage, ms_correct, ms_correct_tier2, ms_gather, ms_d2h, ms_total;
+} talc_counters;
+
+enum {
+  TALC_OK = 0,
+  TALC_ERR_ARG = -1,
+  TALC_ERR_CUDA = -2,
+  TALC_ERR_IO = -3,
+  TALC_ERR_NO_TABLE = -4,
+  TALC_ERR_CAPACITY = -5,   /* an output buffer supplied by the caller is too small */
+  TALC_ERR_SCRATCH = -6     /* a read exhausted even the second-tier scratch arena  */
+};
+
+void talc_params_default(talc_params* p, uint32_t K);
+
+int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out);
+void talc_ctx_destroy(talc_ctx* ctx);
+const char* talc_last_error(talc_ctx* ctx);   /* ctx may be NULL: last create error */
+
+/* scratch sizing (optional): bytes per thread for the first and second tier, resident threads per SM */
+int talc_ctx_set_scratch(talc_ctx* ctx, uint32_t tier1_bytes, uint32_t tier2_bytes, uint32_t tier2_threads);
+
+/* ---- k-mer table (main.cpp:231-232) -------------------------------------------------------- */
+/* Jellyfish `dump -c` text (KMER<ws>COUNT per line), optional junction dump (NULL = none).      */
+int talc_table_load_dump(talc_ctx* ctx, const char* dump_path, const char* junction_path, uint64_t* n_lines,
+                         uint64_t* n_kept);
+/* same, from packed k-mers in dump-line order; counts as the dump gives them (int)               */
+int talc_table_load_packed(talc_ctx* ctx, const uint64_t* keys, const int64_t* counts, uint64_t n,
+                           const uint64_t* jkeys, const int64_t* jcounts, uint64_t nj, int use_junctions,
+                           uint64_t* n_kept);
+/* replication across GPUs: rank 0 builds, every rank allocates the same capacity, the raw slot
+ * array is broadcast (NCCL) between the device pointers below, then each rank seals its copy.     */
+int talc_table_info(talc_ctx* ctx, uint64_t* capacity_slots, uint64_t* bytes, uint64_t* n_entries);
+int talc_table_alloc(talc_ctx* ctx, uint64_t capacity_slots);
+int talc_table_device_ptr(talc_ctx* ctx, void** device_ptr);
+int talc_table_seal(talc_ctx* ctx, uint64_t n_entries);
+/* single-process replication: copy src's sealed table to dst's device (peer copy over NVLink)    */
+int talc_table_copy(talc_ctx* dst, talc_ctx* src);
+/* point look-ups from the host (tests, debugging): found[i] in {0,1}                              */
+int talc_table_lookup(talc_ctx* ctx, const uint64_t* keys, uint64_t n, uint32_t* counts, uint32_t* colours,
+                      uint8_t* found);
+
+/* ---- correction (main.cpp:247-306) ----------------------------------------------------------- */
+/* Host buffers.  bases: the reads concatenated; offsets[n_reads+1].  out / out_offsets[n_reads+1] /
+ * status[n_reads] receive the corrected reads in input order; uncorrectable reads come back as
+ * their (Dna5-normalised) input with a non-zero status.  counters may be NULL.                    */
+int talc_correct_batch(talc_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint8_t* out,
+                       uint64_t out_capacity, uint64_t* out_offsets, uint8_t* status, talc_counters* counters);
+/* Same with every buffer already resident on the context's device (no host<->device copies).      */
+int talc_correct_batch_device(talc_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                              uint64_t total_bases, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_out_offsets,
+                              uint8_t* d_status, talc_counters* counters);
+/* Per-read coverage vectors only (Read::reCoverage): counts[sum(max(0,len-K+1))], host buffers.   */
+int talc_coverage_batch(talc_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                        uint32_t* counts, uint64_t counts_capacity);
+
+/* ---- device self-tests of the scoring primitives (used by tests/ on a GPU) ------------------- */
+/* pairs of NUL-free ASCII strings given as (concatenated bytes, offsets[n+1]); op: 0 NW score,
+ * 1 LCS length, 2 overlap score (walk order), 3 seed-and-extension (result[4*i..]: ref_ext,
+ * cand_ext, score, stop; aux = xdrop, aux2 = direction_right, K from the context)                 */
+int talc_test_align(talc_ctx* ctx, int op, const uint8_t* a, const uint64_t* a_off, const uint8_t* b,
+                    const uint64_t* b_off, uint32_t n, int aux, int aux2, int32_t* result);
+/* permutation produced by the device replica of libstdc++ std::sort on keys[n] (operator<)        */
+int talc_test_sort(talc_ctx* ctx, const int64_t* keys, uint32_t n, uint32_t* perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TALC_B200_H */

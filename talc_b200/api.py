@@ -1,0 +1,218 @@
+"""ctypes binding of libtalc_b200.so (include/talc_b200.h).
+
+This is the harness side used by tests and bench.py; the product is the shared library and the `talc`
+command line built on it.  There is no CPU path: creating a context without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import build as _build
+
+
+class TalcParams(C.Structure):
+    _fields_ = [("K", C.c_uint32), ("min_count", C.c_uint32), ("window_size", C.c_uint32),
+                ("max_nb_branches", C.c_uint32), ("alpha", C.c_double), ("sr_error_rate", C.c_double),
+                ("min_inner_score", C.c_double), ("min_border_score", C.c_double), ("cycle_mode", C.c_int32),
+                ("q11_zero_init", C.c_int32)]
+
+
+COUNTER_U64 = ["lookups_seg", "lookups_deg", "lookups_walk", "steps_inner", "steps_border", "frontier_sum", "cells_nw",
+               "cells_lcs", "cells_ovl", "cells_xdrop", "gaps", "gaps_bridged", "gap_attempts", "borders",
+               "borders_corrected", "ev_gardening", "ev_bridge", "ev_edge", "ev_cycle", "bases_out", "reads_ok",
+               "reads_overflow", "reads", "bases_in", "reads_second_tier", "kernel_launches"]
+COUNTER_F64 = ["ms_h2d", "ms_coverage", "ms_correct", "ms_correct_tier2", "ms_gather", "ms_d2h", "ms_total"]
+
+
+class TalcCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in COUNTER_U64] + [(n, C.c_double) for n in COUNTER_F64]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n in COUNTER_U64 + COUNTER_F64}
+
+
+STATUS_MESSAGES = {1: "No solid kmer could be found.", 2: "Unable to define convenient structure."}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.build_library()
+        L = C.CDLL(path)
+        vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+        L.talc_params_default.argtypes = [C.POINTER(TalcParams), C.c_uint32]
+        L.talc_ctx_create.argtypes = [C.POINTER(TalcParams), C.c_int, C.POINTER(vp)]
+        L.talc_ctx_destroy.argtypes = [vp]
+        L.talc_last_error.restype = C.c_char_p
+        L.talc_last_error.argtypes = [vp]
+        L.talc_ctx_set_scratch.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.talc_table_load_dump.argtypes = [vp, C.c_char_p, C.c_char_p, u64p, u64p]
+        L.talc_table_load_packed.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, C.c_int, u64p]
+        L.talc_table_info.argtypes = [vp, u64p, u64p, u64p]
+        L.talc_table_alloc.argtypes = [vp, C.c_uint64]
+        L.talc_table_device_ptr.argtypes = [vp, C.POINTER(vp)]
+        L.talc_table_seal.argtypes = [vp, C.c_uint64]
+        L.talc_table_copy.argtypes = [vp, vp]
+        L.talc_table_lookup.argtypes = [vp, vp, C.c_uint64, vp, vp, vp]
+        L.talc_correct_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint64, vp, vp, C.POINTER(TalcCounters)]
+        L.talc_correct_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint64, vp, vp,
+                                                C.POINTER(TalcCounters)]
+        L.talc_coverage_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint64]
+        L.talc_test_align.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp]
+        L.talc_test_sort.argtypes = [vp, vp, C.c_uint32, vp]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def default_params(k: int, **kw) -> TalcParams:
+    p = TalcParams()
+    lib().talc_params_default(C.byref(p), k)
+    for key, v in kw.items():
+        setattr(p, key, v)
+    return p
+
+
+class TalcError(RuntimeError):
+    pass
+
+
+class Talc:
+    """One context = one GPU = one replica of the k-mer table."""
+
+    def __init__(self, params: TalcParams, device: int = 0):
+        self.params = params
+        self.h = C.c_void_p()
+        rc = lib().talc_ctx_create(C.byref(params), device, C.byref(self.h))
+        if rc != 0:
+            raise TalcError("talc_ctx_create failed (%d): %s" % (rc, lib().talc_last_error(None).decode()))
+
+    def close(self):
+        if self.h:
+            lib().talc_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise TalcError("%s failed (%d): %s" % (what, rc, lib().talc_last_error(self.h).decode()))
+
+    def set_scratch(self, tier1_bytes=0, tier2_bytes=0, tier2_threads=0):
+        self._check(lib().talc_ctx_set_scratch(self.h, tier1_bytes, tier2_bytes, tier2_threads), "talc_ctx_set_scratch")
+
+    # ---- table
+    def load_dump(self, dump: str, junctions: Optional[str] = None):
+        nl, nk = C.c_uint64(0), C.c_uint64(0)
+        self._check(lib().talc_table_load_dump(self.h, dump.encode(), junctions.encode() if junctions else None,
+                                               C.byref(nl), C.byref(nk)), "talc_table_load_dump")
+        return nl.value, nk.value
+
+    def load_packed(self, keys, counts, jkeys=None, jcounts=None) -> int:
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        counts = np.ascontiguousarray(counts, dtype=np.int64)
+        uj = jkeys is not None
+        jk = np.ascontiguousarray(jkeys if uj else [], dtype=np.uint64)
+        jc = np.ascontiguousarray(jcounts if uj else [], dtype=np.int64)
+        nk = C.c_uint64(0)
+        self._check(lib().talc_table_load_packed(self.h, _ptr(keys), _ptr(counts), len(keys), _ptr(jk), _ptr(jc), len(jk),
+                                                 1 if uj else 0, C.byref(nk)), "talc_table_load_packed")
+        return nk.value
+
+    def table_info(self):
+        cap, nbytes, n = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        rc = lib().talc_table_info(self.h, C.byref(cap), C.byref(nbytes), C.byref(n))
+        return dict(ready=(rc == 0), capacity=cap.value, bytes=nbytes.value, entries=n.value)
+
+    def table_alloc(self, capacity: int):
+        self._check(lib().talc_table_alloc(self.h, capacity), "talc_table_alloc")
+
+    def table_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(lib().talc_table_device_ptr(self.h, C.byref(p)), "talc_table_device_ptr")
+        return p.value
+
+    def table_seal(self, n_entries: int):
+        self._check(lib().talc_table_seal(self.h, n_entries), "talc_table_seal")
+
+    def lookup(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = len(keys)
+        cnt = np.zeros(n, dtype=np.uint32)
+        col = np.zeros(n, dtype=np.uint32)
+        found = np.zeros(n, dtype=np.uint8)
+        self._check(lib().talc_table_lookup(self.h, _ptr(keys), n, _ptr(cnt), _ptr(col), _ptr(found)), "talc_table_lookup")
+        return cnt, col, found
+
+    # ---- correction, host buffers
+    def correct(self, reads: np.ndarray, offsets: np.ndarray, out: np.ndarray = None, out_offsets: np.ndarray = None,
+                status: np.ndarray = None):
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        cap = 2 * int(offsets[-1]) + 64 * n + 4096
+        if out is None:
+            out = np.empty(cap, dtype=np.uint8)
+        if out_offsets is None:
+            out_offsets = np.zeros(n + 1, dtype=np.uint64)
+        if status is None:
+            status = np.zeros(max(n, 1), dtype=np.uint8)
+        ctr = TalcCounters()
+        self._check(lib().talc_correct_batch(self.h, _ptr(reads), _ptr(offsets), n, _ptr(out), len(out), _ptr(out_offsets),
+                                             _ptr(status), C.byref(ctr)), "talc_correct_batch")
+        return out[: int(out_offsets[n])], out_offsets, status[:n], ctr.as_dict()
+
+    # ---- correction, device-resident torch tensors
+    def correct_device(self, d_reads, d_offsets, total_bases: int, d_out, d_out_offsets, d_status):
+        n = d_offsets.numel() - 1
+        ctr = TalcCounters()
+        self._check(lib().talc_correct_batch_device(self.h, d_reads.data_ptr(), d_offsets.data_ptr(), n, total_bases,
+                                                    d_out.data_ptr(), d_out.numel(), d_out_offsets.data_ptr(),
+                                                    d_status.data_ptr(), C.byref(ctr)), "talc_correct_batch_device")
+        return ctr.as_dict()
+
+    def coverage(self, reads: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+        k = self.params.K
+        total = int(np.maximum(lens - k + 1, 0).sum())
+        counts = np.zeros(max(total, 1), dtype=np.uint32)
+        self._check(lib().talc_coverage_batch(self.h, _ptr(reads), _ptr(offsets), n, _ptr(counts), len(counts)),
+                    "talc_coverage_batch")
+        return counts[:total]
+
+    # ---- device self-tests
+    def test_align(self, op: int, a_list, b_list, aux: int = 0, aux2: int = 0) -> np.ndarray:
+        def cat(lst):
+            off = np.zeros(len(lst) + 1, dtype=np.uint64)
+            for i, s in enumerate(lst):
+                off[i + 1] = off[i] + len(s)
+            data = np.frombuffer(b"".join(lst) + b"\0", dtype=np.uint8).copy()
+            return data, off
+        a, ao = cat(a_list)
+        b, bo = cat(b_list)
+        n = len(a_list)
+        res = np.zeros(n * (4 if op == 3 else 1), dtype=np.int32)
+        self._check(lib().talc_test_align(self.h, op, _ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, aux, aux2, _ptr(res)),
+                    "talc_test_align")
+        return res.reshape(n, 4) if op == 3 else res
+
+    def test_sort(self, keys) -> np.ndarray:
+        keys = np.ascontiguousarray(keys, dtype=np.int64)
+        perm = np.zeros(len(keys), dtype=np.uint32)
+        self._check(lib().talc_test_sort(self.h, _ptr(keys), len(keys), _ptr(perm)), "talc_test_sort")
+        return perm

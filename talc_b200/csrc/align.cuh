@@ -38,7 +38,7 @@ struct DpStats {  // algorithmic DP cell updates (SURVEY 8d "integer work")
 };
 
 // match masks of pattern rows [64*block, 64*block+64) for the five symbols (N matches N)
-TALC_HD void build_peq(const SeqView& pat, u32 pn, u32 block, u64 peq[5]) {
+TALC_HDN void build_peq(const SeqView& pat, u32 pn, u32 block, u64 peq[5]) {
   peq[0] = peq[1] = peq[2] = peq[3] = peq[4] = 0;
   const u32 r0 = block * 64;
   const u32 r1 = (pn - r0 < 64u) ? pn : r0 + 64;
@@ -54,7 +54,7 @@ TALC_HD void build_peq(const SeqView& pat, u32 pn, u32 block, u64 peq[5]) {
 }
 
 // unit-cost edit distance between a[0..an) and b[0..bn) (both non-empty)
-TALC_HD int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+TALC_HDN int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   // pattern (rows, bit-parallel) = the shorter one, text (columns) = the longer one
   const bool a_is_pat = an <= bn;
   const SeqView& pat = a_is_pat ? a : b;
@@ -101,7 +101,7 @@ TALC_HD int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Aren
 }
 
 // length of the longest common subsequence of a[0..an) and b[0..bn) (both non-empty)
-TALC_HD int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+TALC_HDN int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   const bool a_is_pat = an <= bn;
   const SeqView& pat = a_is_pat ? a : b;
   const SeqView& txt = a_is_pat ? b : a;
@@ -145,7 +145,7 @@ TALC_HD int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena
 
 // Trail::Overlapscore in walk order: match 4 / mismatch -3 / gap -2, leading gaps of both
 // sequences free, trailing gaps charged; score = bottom-right cell.
-TALC_HD int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {
+TALC_HDN int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {
   if (st) st->cells_ovl += (u64)rn * cn;
   const u32 mk = ar.mark();
   i32* row = (i32*)ar.alloc((cn + 1) * 4);
@@ -175,7 +175,7 @@ TALC_HD int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 c
 // and database[doff..doff+dlen) (H, rows), both in walk order.  Outputs how far the seed moved along
 // the database (ext_rows) and the query (ext_cols).  `wide` sizes the three anti-diagonals for the
 // worst case instead of the X-drop band (second-tier launch).
-TALC_HD void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen,
+TALC_HDN void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen,
                           int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide, DpStats* st) {
   ext_rows = 0;
   ext_cols = 0;
@@ -315,7 +315,7 @@ struct SeedExt {
   i32 score;     // NW score of the two extensions (<= 0), or -xdrop when the seed could not extend
   bool stop;
 };
-TALC_HD SeedExt seed_and_extension(const SeqView& refArg, const SeqView& candArg, int xdrop, bool right, u32 K,
+TALC_HDN SeedExt seed_and_extension(const SeqView& refArg, const SeqView& candArg, int xdrop, bool right, u32 K,
                                    Arena& ar, bool wide, DpStats* st) {
   SeedExt r;
   const bool state = !(refArg.len < candArg.len);

@@ -132,7 +132,7 @@ class Corrector {
   TALC_HD u32 K() const { return P.K; }
 
   // ------------------------------------------------------------------ table access with counters
-  TALC_HD int out_degree(u32 pos, bool right) {
+  TALC_HDN int out_degree(u32 pos, bool right) {
     if (ctr) ctr->lookups_deg += 4;
     bool ok;
     const u64 km = rd.kmer_at(pos, K(), ok);
@@ -163,7 +163,7 @@ class Corrector {
   // ------------------------------------------------------------------ Read.cpp:493-518
   // robust mean over the [15%,90%) slice of the sorted in-counts, computed without sorting: the sum
   // of the r smallest values is exact in integers (and in double below 2^53), so order is irrelevant
-  TALC_HD u64 sum_of_smallest(u32 r, u32 maxv) {  // sum of the r smallest values among counts >= MIN
+  TALC_HDN u64 sum_of_smallest(u32 r, u32 maxv) {  // sum of the r smallest values among counts >= MIN
     if (r == 0) return 0;
     int top = 7;
     while (top > 0 && ((maxv >> (4 * top)) & 15u) == 0) --top;  // leading zero nibbles of the maximum
@@ -196,7 +196,7 @@ class Corrector {
     return sumBelow + (u64)remaining * prefix;
   }
 
-  TALC_HD double seq_error_threshold() {
+  TALC_HDN double seq_error_threshold() {
     u32 n = 0, maxv = 0;
     for (u32 i = 0; i < C; ++i) {
       n += (cov[i] >= P.min_count) ? 1 : 0;
@@ -218,7 +218,7 @@ class Corrector {
   }
 
   // ------------------------------------------------------------------ Read.cpp:440-489
-  TALC_HD bool find_in_regions() {
+  TALC_HDN bool find_in_regions() {
     // first pass counts, second pass fills
     u32 n = 0;
     bool state = false;
@@ -247,7 +247,7 @@ class Corrector {
   }
 
   // ------------------------------------------------------------------ Read.cpp:524-600
-  TALC_HD void analyze_in_regions(double thr) {
+  TALC_HDN void analyze_in_regions(double thr) {
     // kept regions overwrite the front of a second array; the input list is mutated in place (Q5)
     Region* kept = (Region*)keep.alloc((nregs ? nregs : 1) * sizeof(Region));
     if (!kept) return;
@@ -303,7 +303,7 @@ class Corrector {
   }
 
   // ------------------------------------------------------------------ Read.cpp:214-258
-  TALC_HD bool initial_structure() {
+  TALC_HDN bool initial_structure() {
     const u32 Lr = rd.len;
     u64 len = 0;
     headPresent = tailPresent = false;
@@ -320,7 +320,7 @@ class Corrector {
   }
 
   // ------------------------------------------------------------------ Explorer.cpp:402-411
-  TALC_HD void sort_anchors(AnchorRec* a, u32 n) {
+  TALC_HDN void sort_anchors(AnchorRec* a, u32 n) {
     const int cc = (int)(noise / P.sr_error);
     std_sort(a, a + n, [cc](const AnchorRec& l, const AnchorRec& r) {
       int dl = cc - (int)l.count;
@@ -338,7 +338,7 @@ class Corrector {
 
   // Explorer.cpp:413-478 (LEFT region: scan from its last k-mer down) and :480-543 (RIGHT region:
   // scan from its first k-mer up).  `left` selects which.
-  TALC_HD bool build_anchors(bool left) {
+  TALC_HDN bool build_anchors(bool left) {
     const Region& rg = left ? L : R;
     const u32 nbKmers = rg.end - rg.start + 1;
     const u32 pivot = left ? rg.end : rg.start;
@@ -402,7 +402,7 @@ class Corrector {
   }
 
   // ------------------------------------------------------------------ trail slots
-  TALC_HD bool setup_search(u32 pathMax) {
+  TALC_HDN bool setup_search(u32 pathMax) {
     slotWords = (K() + pathMax + 2 + 31) / 32 + 1;
     maxT = wide ? 208u : 48u;
     cur = (Trail*)scratch.alloc(maxT * sizeof(Trail));
@@ -440,7 +440,7 @@ class Corrector {
   }
 
   // root trail: the anchor k-mer in walk order (Trail.cpp:57-65)
-  TALC_HD bool push_root(const AnchorRec& a) {
+  TALC_HDN bool push_root(const AnchorRec& a) {
     const int s = slot_alloc();
     if (s < 0) return false;
     u64* w = slot_ptr((u32)s);
@@ -466,7 +466,7 @@ class Corrector {
 
   // Trail.cpp:289-302 + SeqAn Finder/Pattern<Horspool>: does the child's last k-mer already occur in
   // the parent's sequence, first occurrence at a position > 0 (Q17)?  parent sequence = slot, plen bases.
-  TALC_HD bool already_got_there(u64 needle, const u64* w, u32 plen) {
+  TALC_HDN bool already_got_there(u64 needle, const u64* w, u32 plen) {
     const u32 k = K();
     if (!(plen > k)) return false;
     const u32 stride = (P.cycle_mode == 0) ? k : 1u;
@@ -485,7 +485,7 @@ class Corrector {
 
   // ------------------------------------------------------------------ gardening, Explorer.cpp:773-865
   // kept[] receives indices into nxt (duplicates possible, Q16); returns isComplex
-  TALC_HD bool gardening(u32* kept, u32& nKept) {
+  TALC_HDN bool gardening(u32* kept, u32& nKept) {
     if (ctr) ctr->ev_gardening++;
     const u32 n = nNxt;
     const u32 MAXP = P.max_branches;
@@ -560,7 +560,7 @@ class Corrector {
   }
 
   // replace cur by nxt[kept[..]]; trails not kept release their slots, duplicates get copies
-  TALC_HD bool adopt_kept(const u32* kept, u32 nKept, u32 plen) {
+  TALC_HDN bool adopt_kept(const u32* kept, u32 nKept, u32 plen) {
     if (nKept > maxT) { scratch.overflow = 1; return false; }
     const u32 mk = scratch.mark();
     u8* used = (u8*)scratch.alloc(nNxt ? nNxt : 1);
@@ -609,7 +609,7 @@ class Corrector {
     return false;
   }
 
-  TALC_HD bool search_bridge(Piece& weakOut) {
+  TALC_HDN bool search_bridge(Piece& weakOut) {
     const u32 k = K();
     const AnchorRec* anchors = dirRight ? ancL : ancR;
     const u32 nAnch = dirRight ? nAncL : nAncR;
@@ -809,7 +809,7 @@ class Corrector {
 
   // ------------------------------------------------------------------ border search
   // Trail::seedAndExtend, Trail.cpp:193-216 (reference string vs this trail)
-  TALC_HD bool trail_seed_extend(Trail& t, u32 tlen, const SeqView& refv, int xdrop) {
+  TALC_HDN bool trail_seed_extend(Trail& t, u32 tlen, const SeqView& refv, int xdrop) {
     const SeqView pv = view_of_path(slot_ptr(t.slot), tlen);
     const SeedExt e = seed_and_extension(refv, pv, xdrop, dirRight, K(), scratch, wide, &dps);
     bool ok = (e.cand_ext == tlen);
@@ -822,7 +822,7 @@ class Corrector {
   }
 
   // Trajectory.cpp:482-503
-  TALC_HD SeedExt find_stop_position(const SeqView& refArg, const SeqView& candArg, int xdrop) {
+  TALC_HDN SeedExt find_stop_position(const SeqView& refArg, const SeqView& candArg, int xdrop) {
     int xdrop1 = xdrop;
     bool goFurther = true;
     SeedExt ext, next;
@@ -837,7 +837,7 @@ class Corrector {
   }
 
   // Explorer::recordEdge, Explorer.cpp:1103-1118, folded straight into the running best of its list
-  TALC_HD bool record_edge(const Trail& t, u32 tlen, const RefView& ref, u32 whichStart, EdgeBest& bestLong,
+  TALC_HDN bool record_edge(const Trail& t, u32 tlen, const RefView& ref, u32 whichStart, EdgeBest& bestLong,
                            EdgeBest& bestShort) {
     if (ctr) ctr->ev_edge++;
     const u32 k = K();
@@ -898,7 +898,7 @@ class Corrector {
   }
 
   // Explorer::scoreEdges, Explorer.cpp:709-740 (operates on nxt)
-  TALC_HD bool score_edges(int& xdrop, u32 tlen, const RefView& ref, u32 whichStart, EdgeBest& bestLong,
+  TALC_HDN bool score_edges(int& xdrop, u32 tlen, const RefView& ref, u32 whichStart, EdgeBest& bestLong,
                            EdgeBest& bestShort) {
     if (nNxt == 0) return true;
     const SeqView refv = view_of(ref);
@@ -938,7 +938,7 @@ class Corrector {
   }
 
   // Explorer::searchEdge, Explorer.cpp:992-1081
-  TALC_HD bool search_edge(Piece& weakOut) {
+  TALC_HDN bool search_edge(Piece& weakOut) {
     const u32 k = K();
     const AnchorRec* anchors = dirRight ? ancL : ancR;
     const u32 nAnch = dirRight ? nAncL : nAncR;
@@ -1084,7 +1084,7 @@ class Corrector {
 
   // ------------------------------------------------------------------ per-read driver (main.cpp:258-296)
   // Returns the status; on kReadOk the pieces describe the corrected read.
-  TALC_HD u8 run(const ReadJob& job) {
+  TALC_HDN u8 run(const ReadJob& job) {
     rd = job.rd;
     cov = job.cov;
     wide = job.wide;
@@ -1181,7 +1181,7 @@ class Corrector {
   }
 
   // length of the corrected read (Read::updateCorrSeq, Read.cpp:320-326)
-  TALC_HD u32 corrected_length() const {
+  TALC_HDN u32 corrected_length() const {
     const u32 k = P.K;
     u32 n = 0;
     n += (headPiece.len >= 0) ? (u32)headPiece.len : (headPresent ? headRaw : 0);
@@ -1198,7 +1198,7 @@ class Corrector {
     return b > a ? b - a : 0;
   }
   // write the corrected read as upper-case ASCII
-  TALC_HD void emit(u8* out) const {
+  TALC_HDN void emit(u8* out) const {
     const u32 k = P.K;
     u32 o = 0;
     if (headPiece.len >= 0) { for (i32 i = 0; i < headPiece.len; ++i) out[o++] = keep.base[headPiece.off + i]; }

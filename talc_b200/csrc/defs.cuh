@@ -8,12 +8,14 @@
 #include <stdint.h>
 #include <string.h>
 
+// TALC_HD: small helpers, always inlined.  TALC_HDN: the big routines; they stay real calls on the device
+// (forcing the whole per-read pipeline into one function body makes the NVVM optimiser run for an hour).
 #if defined(__CUDACC__)
 #define TALC_HD __host__ __device__ __forceinline__
-#define TALC_HD_NOINLINE __host__ __device__ __noinline__
+#define TALC_HDN __host__ __device__ __noinline__
 #else
 #define TALC_HD inline
-#define TALC_HD_NOINLINE
+#define TALC_HDN inline
 #endif
 
 namespace talc {

@@ -33,7 +33,7 @@ TALC_HD bool expected_by_last_node(u32 nextc, u32 cc, double alpha) {
 }
 
 // Explorer.cpp:1226-1298.  Returns the number of tags (0 on a dead end, else 4).
-TALC_HD int tag_next_nodes(const u32 cnt[4], const u32 col[4], u32 count, const Params& P, bool complex_, u8 tag[4],
+TALC_HDN int tag_next_nodes(const u32 cnt[4], const u32 col[4], u32 count, const Params& P, bool complex_, u8 tag[4],
                            double dist[4]) {
   int counter = 0;
   u32 lambda_noise = 0;

@@ -117,7 +117,7 @@ TALC_HD void insertion_sort(T* first, T* last, Less less) {
 }  // namespace stdsort_detail
 
 template <class T, class Less>
-TALC_HD void std_sort(T* first, T* last, Less less) {
+TALC_HDN void std_sort(T* first, T* last, Less less) {
   using namespace stdsort_detail;
   if (first == last) return;
   const i64 n = last - first;

@@ -57,7 +57,7 @@ TALC_HD int sector_resolve(const Slot& s0, const Slot& s1, u64 key, u32& count, 
 }
 
 // continue a probe sequence past sector b
-TALC_HD bool table_probe_from(const TableView& t, u64 b, u64 key, u32& count, u32& colour) {
+TALC_HDN bool table_probe_from(const TableView& t, u64 b, u64 key, u32& count, u32& colour) {
   for (;;) {
     b = (b + 2) & t.mask;
     const Slot s0 = load_slot(t.slots + b);

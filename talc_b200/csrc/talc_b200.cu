@@ -1,0 +1,946 @@
+// talc_b200.cu -- sm_100a kernels and the C ABI (include/talc_b200.h) of the TALC correction path.
+//
+// Kernels (all HBM / integer bound; nothing here is a dense contraction, so no tensor cores):
+//   table_insert_kernel / table_finalize_kernel / table_colour_kernel   k-mer table build in HBM
+//   kmer_count_kernel + coverage_kernel                                 Read::reCoverage, batched
+//   correct_kernel<wide>                                                segmentation + graph search + scoring
+//   gather_kernel                                                       corrected reads back into input order
+// Grid sizes are multiples of the SM count; per-thread scratch lives in HBM (180 GB makes that cheap).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <cub/cub.cuh>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/talc_b200.h"
+#include "correct.cuh"
+#include "dump_parse.hpp"
+
+using namespace talc;
+
+// =====================================================================================
+// table build
+// =====================================================================================
+// Entry i of the dump (file order) claims a slot with CAS, then the (line index, count) pair with the
+// smallest line index wins through a 64-bit atomicMin: that is map::insert's "first line wins"
+// (Jellyfish.cpp:262) independent of the order in which threads arrive.
+__global__ void table_insert_kernel(Slot* slots, u64 mask, const u64* keys, const u32* counts, u64 n) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 key = keys[i];
+    u64 b = hash_kmer(key) & mask & ~1ull;
+    Slot* hit = nullptr;
+    while (!hit) {
+      for (int j = 0; j < 2 && !hit; ++j) {
+        Slot* s = slots + b + j;
+        unsigned long long prev = *(volatile unsigned long long*)&s->key;
+        if (prev == kEmptyKey) prev = atomicCAS((unsigned long long*)&s->key, (unsigned long long)kEmptyKey, (unsigned long long)key);
+        if (prev == kEmptyKey || prev == key) hit = s;
+      }
+      b = (b + 2) & mask;
+    }
+    const unsigned long long v = ((unsigned long long)i << 32) | (unsigned long long)counts[i];
+    atomicMin((unsigned long long*)&hit->count, v);  // {count, colour} viewed as one u64: colour half carries the line index
+  }
+}
+// strip the line index: colour := 0 for every occupied slot, count stays
+__global__ void table_finalize_kernel(Slot* slots, u64 capacity, unsigned long long* n_entries) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  unsigned long long mine = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
+    if (slots[i].key != kEmptyKey) {
+      slots[i].colour = 0;
+      ++mine;
+    } else {
+      slots[i].count = 0;
+      slots[i].colour = 0;
+    }
+  }
+  if (mine) atomicAdd(n_entries, mine);
+}
+__global__ void table_fill_empty_kernel(Slot* slots, u64 capacity) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
+    slots[i].key = kEmptyKey;
+    slots[i].count = 0xFFFFFFFFu;
+    slots[i].colour = 0xFFFFFFFFu;
+  }
+}
+// junction colours: the host has already reduced the junction dump to one final value per k-mer
+// ("last line wins, forward before reverse complement": Jellyfish.cpp:284-286); only existing keys change
+__global__ void table_colour_kernel(Slot* slots, u64 mask, const u64* keys, const u32* colours, u64 n) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 key = keys[i];
+    u64 b = hash_kmer(key) & mask & ~1ull;
+    for (;;) {
+      bool done = false;
+      for (int j = 0; j < 2; ++j) {
+        Slot* s = slots + b + j;
+        if (s->key == key) { s->colour = colours[i]; done = true; break; }
+        if (s->key == kEmptyKey) { done = true; break; }
+      }
+      if (done) break;
+      b = (b + 2) & mask;
+    }
+  }
+}
+__global__ void table_lookup_kernel(TableView tv, const u64* keys, u64 n, u32* counts, u32* colours, u8* found) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u32 c, col;
+    found[i] = table_lookup(tv, keys[i], c, col) ? 1 : 0;
+    counts[i] = c;
+    colours[i] = col;
+  }
+}
+
+// =====================================================================================
+// coverage (Read::reCoverage / getLRCountsInSRFromDBG, Read.cpp:174-195, Jellyfish.cpp:485-496)
+// =====================================================================================
+__global__ void kmer_count_kernel(const u64* offs, u32 n, u32 K, u64* nk, u32* sortKey, u32* sortVal) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 len = offs[i + 1] - offs[i];
+  nk[i] = len >= K ? len - K + 1 : 0;
+  sortKey[i] = 0xFFFFFFFFu - (u32)len;  // ascending key = descending length
+  sortVal[i] = i;
+}
+// One warp per read; each lane rolls a 2-bit k-mer over 4 consecutive positions (K+3 byte loads for 4
+// probes), probes the table (one 32-byte sector per probe), and the warp writes 512 contiguous bytes.
+__global__ void __launch_bounds__(256) coverage_kernel(TableView tv, u32 K, const u8* __restrict__ bases,
+                                                       const u64* __restrict__ offs, const u64* __restrict__ kmerOff,
+                                                       u32 n, u32* __restrict__ cov) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warpsPerBlock = blockDim.x >> 5;
+  const u64 kmask = kmer_mask(K);
+  for (u32 r = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < n; r += gridDim.x * warpsPerBlock) {
+    const u64 o = offs[r];
+    const u32 len = (u32)(offs[r + 1] - o);
+    if (len < K) continue;
+    const u32 C = len - K + 1;
+    const u8* s = bases + o;
+    u32* out = cov + kmerOff[r];
+    for (u32 base = 0; base < C; base += 128) {
+      const u32 p0 = base + lane * 4;
+      if (p0 >= C) continue;
+      u64 km = 0;
+      u32 bad = 0;  // number of bases since the last N, saturating at K
+      for (u32 j = 0; j < K; ++j) {
+        const u32 c = base_code(__ldg(s + p0 + j));
+        bad = (c > 3) ? 0 : (bad + 1);
+        km = ((km << 2) | (c & 3)) & kmask;
+      }
+      u32 cnt[4] = {0, 0, 0, 0};
+      u64 kms[4];
+      u32 okm = 0;
+      kms[0] = km;
+      okm |= (bad >= K) ? 1u : 0u;
+#pragma unroll
+      for (u32 q = 1; q < 4; ++q) {
+        if (p0 + q < C) {
+          const u32 c = base_code(__ldg(s + p0 + q + K - 1));
+          bad = (c > 3) ? 0 : (bad + 1);
+          km = ((km << 2) | (c & 3)) & kmask;
+          okm |= (bad >= K) ? (1u << q) : 0u;
+        }
+        kms[q] = km;
+      }
+      // issue the four home-sector fetches together
+      Slot s0[4], s1[4];
+      u64 b[4];
+#pragma unroll
+      for (u32 q = 0; q < 4; ++q) {
+        b[q] = hash_kmer(kms[q]) & tv.mask & ~1ull;
+        if ((okm >> q) & 1u) {
+          s0[q] = load_slot(tv.slots + b[q]);
+          s1[q] = load_slot(tv.slots + b[q] + 1);
+        }
+      }
+#pragma unroll
+      for (u32 q = 0; q < 4; ++q) {
+        if ((okm >> q) & 1u) {
+          u32 col;
+          const int rr = sector_resolve(s0[q], s1[q], kms[q], cnt[q], col);
+          if (rr < 0) table_probe_from(tv, b[q], kms[q], cnt[q], col);
+        }
+      }
+      if (p0 + 3 < C && ((((size_t)(out + p0)) & 15) == 0)) {
+        *reinterpret_cast<uint4*>(out + p0) = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+      } else {
+        for (u32 q = 0; q < 4 && p0 + q < C; ++q) out[p0 + q] = cnt[q];
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// correction: one thread per read, warps pull 32 reads at a time from a length-sorted queue
+// =====================================================================================
+struct CorrectArgs {
+  TableView tv;
+  Params P;
+  const u8* bases;
+  const u64* offs;
+  const u64* kmerOff;
+  const u32* cov;
+  const u32* order;   // read indices, longest first
+  u32 nOrder;
+  u8* arenas;
+  u32 arenaBytes;
+  u8* outArena;       // corrected reads, allocation order
+  u64 outCap;
+  unsigned long long* outCursor;
+  u64* outPos;
+  u32* outLen;
+  u8* status;
+  unsigned long long* counters;  // kNumCounters
+  u32* workCounter;
+  u32* overflowList;
+  u32* nOverflow;
+  u32* outFull;
+};
+
+template <bool WIDE>
+__global__ void __launch_bounds__(128) correct_kernel(CorrectArgs A) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  u8* myArena = A.arenas + gtid * (u64)A.arenaBytes;
+  Counters mine;
+  for (;;) {
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(A.workCounter, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= A.nOrder) break;
+    const u32 qi = base + lane;
+    if (qi < A.nOrder) {
+      const u32 r = A.order[qi];
+      Corrector cx;
+      cx.T = A.tv;
+      cx.P = A.P;
+#pragma unroll
+      for (int i = 0; i < kNumCounters; ++i) ((u64*)&mine)[i] = 0;
+      cx.ctr = &mine;
+      ReadJob job;
+      job.rd.s = A.bases + A.offs[r];
+      job.rd.len = (u32)(A.offs[r + 1] - A.offs[r]);
+      job.cov = A.cov + A.kmerOff[r];
+      job.arena = myArena;
+      job.arena_bytes = A.arenaBytes;
+      job.wide = WIDE;
+      const u8 st = cx.run(job);
+      if (st == kReadOverflow) {
+        A.status[r] = st;
+        const u32 slot = atomicAdd(A.nOverflow, 1u);
+        A.overflowList[slot] = r;
+      } else {
+        const u32 olen = (st == kReadOk) ? cx.corrected_length() : job.rd.len;
+        const unsigned long long pos = atomicAdd(A.outCursor, (unsigned long long)olen);
+        if (pos + olen <= A.outCap) {
+          u8* dst = A.outArena + pos;
+          if (st == kReadOk) cx.emit(dst);
+          else
+            for (u32 i = 0; i < job.rd.len; ++i) dst[i] = code_char(job.rd.code(i));
+        } else {
+          atomicExch(A.outFull, 1u);
+        }
+        A.outPos[r] = pos;
+        A.outLen[r] = olen;
+        A.status[r] = st;
+        mine.cells_nw += cx.dps.cells_nw;
+        mine.cells_lcs += cx.dps.cells_lcs;
+        mine.cells_ovl += cx.dps.cells_ovl;
+        mine.cells_xdrop += cx.dps.cells_xdrop;
+        mine.bases_out += olen;
+        if (st == kReadOk) mine.reads_ok += 1;
+        for (int i = 0; i < kNumCounters; ++i) {
+          const u64 v = ((const u64*)&mine)[i];
+          if (v) atomicAdd(A.counters + i, (unsigned long long)v);
+        }
+      }
+    }
+  }
+}
+
+// corrected reads from allocation order into input order; one warp per read, 16-byte chunks
+__global__ void gather_kernel(const u8* __restrict__ arena, const u64* __restrict__ pos, const u32* __restrict__ len,
+                              const u64* __restrict__ outOff, u32 n, u8* __restrict__ out) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warpsPerBlock = blockDim.x >> 5;
+  for (u32 r = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < n; r += gridDim.x * warpsPerBlock) {
+    const u8* src = arena + pos[r];
+    u8* dst = out + outOff[r];
+    const u32 L = len[r];
+    for (u32 i = lane; i < L; i += 32) dst[i] = src[i];
+  }
+}
+__global__ void len_to_u64_kernel(const u32* len, u32 n, u64* out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = len[i];
+}
+
+// =====================================================================================
+// device self-tests of the primitives
+// =====================================================================================
+__global__ void test_align_kernel(int op, const u8* a, const u64* aoff, const u8* b, const u64* boff, u32 n, int aux,
+                                  int aux2, u32 K, u8* arenas, u32 arenaBytes, i32* result) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Arena ar;
+  ar.init(arenas + (u64)i * arenaBytes, arenaBytes);
+  SeqView va, vb;
+  va.s = a + aoff[i]; va.start = 0; va.step = 1; va.w = nullptr; va.len = (u32)(aoff[i + 1] - aoff[i]);
+  vb.s = b + boff[i]; vb.start = 0; vb.step = 1; vb.w = nullptr; vb.len = (u32)(boff[i + 1] - boff[i]);
+  // the second string is also exercised as a packed trail when it holds no N
+  u64* packed = (u64*)ar.alloc(((vb.len + 31) / 32 + 2) * 8);
+  bool pure = packed != nullptr;
+  for (u32 j = 0; j < vb.len && pure; ++j) pure = vb.code(j) < 4;
+  if (pure) {
+    for (u32 j = 0; j < (vb.len + 31) / 32 + 2; ++j) packed[j] = 0;
+    for (u32 j = 0; j < vb.len; ++j) path_set(packed, j, vb.code(j));
+    vb = view_of_path(packed, vb.len);
+  }
+  if (op == 0) result[i] = -nw_distance(va, va.len, vb, vb.len, ar, nullptr);
+  else if (op == 1) result[i] = lcs_length(va, va.len, vb, vb.len, ar, nullptr);
+  else if (op == 2) result[i] = overlap_score(va, va.len, vb, vb.len, ar, nullptr);
+  else {
+    const SeedExt e = seed_and_extension(va, vb, aux, aux2 != 0, K, ar, true, nullptr);
+    result[4 * i + 0] = (i32)e.ref_ext;
+    result[4 * i + 1] = (i32)e.cand_ext;
+    result[4 * i + 2] = e.score;
+    result[4 * i + 3] = e.stop ? 1 : 0;
+  }
+  if (ar.overflow) result[(op == 3) ? 4 * i : i] = INT32_MIN;
+}
+__global__ void test_sort_kernel(const i64* keys, u32 n, u32* perm) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (u32 i = 0; i < n; ++i) perm[i] = i;
+  std_sort(perm, perm + n, [keys](const u32& x, const u32& y) { return keys[x] < keys[y]; });
+}
+
+// =====================================================================================
+// host side
+// =====================================================================================
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct talc_ctx {
+  talc_params params;
+  Params P;
+  int device = 0;
+  int sms = 0;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8];
+  // table
+  Slot* slots = nullptr;
+  u64 capacity = 0;
+  u64 nEntries = 0;
+  bool tableOwned = true;
+  bool tableReady = false;
+  // scratch sizing
+  u32 tier1Bytes = 48 * 1024;
+  u32 tier2Bytes = 6u << 20;
+  u32 tier2Threads = 2048;
+  // cached device buffers
+  DevBuf bases, offs, kmerOff, nk, cov, order, sortKey, sortKeyOut, sortVal, cubTmp, arenas, outArena, outPos, outLen,
+      outLen64, status, outOffs, out, misc, overflowList;
+};
+
+static thread_local std::string g_createError;
+
+#define CUDA_TRY(ctx, call)                                                                             \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess) {                                                                           \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                 \
+      return TALC_ERR_CUDA;                                                                             \
+    }                                                                                                   \
+  } while (0)
+
+static Params to_device_params(const talc_params& q) {
+  Params p;
+  p.K = q.K;
+  p.min_count = q.min_count;
+  p.window = q.window_size;
+  p.max_branches = q.max_nb_branches;
+  p.alpha = q.alpha;
+  p.sr_error = q.sr_error_rate;
+  p.min_inner = q.min_inner_score;
+  p.min_border = q.min_border_score;
+  p.cycle_mode = q.cycle_mode;
+  p.q11_zero = q.q11_zero_init;
+  return p;
+}
+
+extern "C" {
+
+void talc_params_default(talc_params* p, uint32_t K) {
+  p->K = K;
+  p->min_count = 2;
+  p->window_size = 9;
+  p->max_nb_branches = 7;
+  p->alpha = 2.57;
+  p->sr_error_rate = 0.025;
+  p->min_inner_score = 0.7;
+  p->min_border_score = 0.7;
+  p->cycle_mode = 0;
+  p->q11_zero_init = 1;
+}
+
+const char* talc_last_error(talc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out) {
+  if (!p || !out) return TALC_ERR_ARG;
+  *out = nullptr;
+  if (p->K < 2 || p->K > 31 || p->min_count < 1 || p->max_nb_branches < 1) {
+    g_createError = "invalid parameters (K must be in [2,31])";
+    return TALC_ERR_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_createError = std::string("no CUDA device: this library has no CPU path (") + cudaGetErrorString(e) + ")";
+    return TALC_ERR_CUDA;
+  }
+  if (cuda_device < 0 || cuda_device >= ndev) {
+    g_createError = "cuda_device out of range";
+    return TALC_ERR_ARG;
+  }
+  if ((e = cudaSetDevice(cuda_device)) != cudaSuccess) {
+    g_createError = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return TALC_ERR_CUDA;
+  }
+  talc_ctx* c = new talc_ctx;
+  c->params = *p;
+  c->P = to_device_params(*p);
+  c->device = cuda_device;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cuda_device);
+  c->sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_createError = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+    delete c;
+    return TALC_ERR_CUDA;
+  }
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&c->ev[i]);
+  *out = c;
+  return TALC_OK;
+}
+
+void talc_ctx_destroy(talc_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->slots && c->tableOwned) cudaFree(c->slots);
+  DevBuf* bufs[] = {&c->bases, &c->offs, &c->kmerOff, &c->nk, &c->cov, &c->order, &c->sortKey, &c->sortKeyOut, &c->sortVal,
+                    &c->cubTmp, &c->arenas, &c->outArena, &c->outPos, &c->outLen, &c->outLen64, &c->status, &c->outOffs,
+                    &c->out, &c->misc, &c->overflowList};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int talc_ctx_set_scratch(talc_ctx* c, uint32_t tier1_bytes, uint32_t tier2_bytes, uint32_t tier2_threads) {
+  if (!c) return TALC_ERR_ARG;
+  if (tier1_bytes) c->tier1Bytes = (tier1_bytes + 255u) & ~255u;
+  if (tier2_bytes) c->tier2Bytes = (tier2_bytes + 255u) & ~255u;
+  if (tier2_threads) c->tier2Threads = (tier2_threads + 127u) & ~127u;
+  return TALC_OK;
+}
+
+// ---------------------------------------------------------------------------------- table
+int talc_table_alloc(talc_ctx* c, uint64_t capacity_slots) {
+  if (!c || capacity_slots < 2 || (capacity_slots & (capacity_slots - 1))) return TALC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (c->slots && c->tableOwned) cudaFree(c->slots);
+  c->slots = nullptr;
+  c->tableReady = false;
+  CUDA_TRY(c, cudaMalloc((void**)&c->slots, capacity_slots * sizeof(Slot)));
+  c->capacity = capacity_slots;
+  c->tableOwned = true;
+  const int blocks = c->sms * 8;
+  table_fill_empty_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, c->capacity);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return TALC_OK;
+}
+int talc_table_device_ptr(talc_ctx* c, void** p) {
+  if (!c || !p || !c->slots) return TALC_ERR_ARG;
+  *p = c->slots;
+  return TALC_OK;
+}
+int talc_table_seal(talc_ctx* c, uint64_t n_entries) {
+  if (!c || !c->slots) return TALC_ERR_ARG;
+  c->nEntries = n_entries;
+  c->tableReady = true;
+  return TALC_OK;
+}
+int talc_table_info(talc_ctx* c, uint64_t* cap, uint64_t* bytes, uint64_t* n) {
+  if (!c) return TALC_ERR_ARG;
+  if (cap) *cap = c->capacity;
+  if (bytes) *bytes = c->capacity * sizeof(Slot);
+  if (n) *n = c->nEntries;
+  return c->tableReady ? TALC_OK : TALC_ERR_NO_TABLE;
+}
+
+extern "C" int talc_table_copy(talc_ctx* dst, talc_ctx* src) {
+  if (!dst || !src || !src->tableReady) return TALC_ERR_ARG;
+  int rc = talc_table_alloc(dst, src->capacity);
+  if (rc) return rc;
+  CUDA_TRY(dst, cudaMemcpyPeer(dst->slots, dst->device, src->slots, src->device, src->capacity * sizeof(Slot)));
+  return talc_table_seal(dst, src->nEntries);
+}
+
+// entries: dump order, already filtered to count >= MIN and valid ACGT k-mers of length K
+static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vector<u32>& counts,
+                       const std::vector<u64>& ckeys, const std::vector<u32>& ccols, uint64_t* n_kept) {
+  const u64 n = keys.size();
+  u64 cap = 2;
+  while (cap < 2 * n + 2) cap <<= 1;
+  int rc = talc_table_alloc(c, cap);
+  if (rc) return rc;
+  const int blocks = c->sms * 8;
+  u64* dKeys = nullptr;
+  u32* dCounts = nullptr;
+  if (n) {
+    CUDA_TRY(c, cudaMalloc((void**)&dKeys, n * 8));
+    CUDA_TRY(c, cudaMalloc((void**)&dCounts, n * 4));
+    CUDA_TRY(c, cudaMemcpyAsync(dKeys, keys.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(dCounts, counts.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    table_insert_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap - 1, dKeys, dCounts, n);
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  unsigned long long* dN = nullptr;
+  CUDA_TRY(c, cudaMalloc((void**)&dN, 8));
+  CUDA_TRY(c, cudaMemsetAsync(dN, 0, 8, c->stream));
+  table_finalize_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap, dN);
+  CUDA_TRY(c, cudaGetLastError());
+  if (!ckeys.empty()) {
+    u64* dCk = nullptr;
+    u32* dCc = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&dCk, ckeys.size() * 8));
+    CUDA_TRY(c, cudaMalloc((void**)&dCc, ckeys.size() * 4));
+    CUDA_TRY(c, cudaMemcpyAsync(dCk, ckeys.data(), ckeys.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(dCc, ccols.data(), ckeys.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    table_colour_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap - 1, dCk, dCc, ckeys.size());
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dCk);
+    cudaFree(dCc);
+  }
+  unsigned long long hN = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&hN, dN, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(dN);
+  if (dKeys) cudaFree(dKeys);
+  if (dCounts) cudaFree(dCounts);
+  c->nEntries = hN;
+  c->tableReady = true;
+  if (n_kept) *n_kept = hN;
+  return TALC_OK;
+}
+
+static u64 revcomp_kmer(u64 k, u32 K) {
+  u64 r = 0;
+  for (u32 i = 0; i < K; ++i) {
+    r = (r << 2) | (3 - (k & 3));
+    k >>= 2;
+  }
+  return r;
+}
+
+// reduce the junction list to final colours (sequential semantics of Jellyfish.cpp:278-289) and append the
+// four homopolymer resets of decolourRepeatsFromDBG (utils.cpp:658-669)
+static void reduce_colours(const talc_params& p, const u64* jkeys, const i64* jcounts, u64 nj, bool use, std::vector<u64>& ck,
+                           std::vector<u32>& cc) {
+  std::unordered_map<u64, u32> last;
+  if (use) {
+    last.reserve(nj * 2 + 8);
+    for (u64 i = 0; i < nj; ++i) {
+      const u32 v = (u32)(int)jcounts[i];
+      if (v < kColouredCountThr) {
+        last[jkeys[i]] = v;
+        last[revcomp_kmer(jkeys[i], p.K)] = v;
+      }
+    }
+  }
+  for (u32 b = 0; b < 4; ++b) {
+    u64 homo = 0;
+    for (u32 i = 0; i < p.K; ++i) homo = (homo << 2) | b;
+    last[homo] = 0;
+  }
+  ck.reserve(last.size());
+  cc.reserve(last.size());
+  for (auto& kv : last) {
+    ck.push_back(kv.first);
+    cc.push_back(kv.second);
+  }
+}
+
+int talc_table_load_packed(talc_ctx* c, const uint64_t* keys, const int64_t* counts, uint64_t n, const uint64_t* jkeys,
+                           const int64_t* jcounts, uint64_t nj, int use_junctions, uint64_t* n_kept) {
+  if (!c || (n && (!keys || !counts))) return TALC_ERR_ARG;
+  std::vector<u64> k;
+  std::vector<u32> v;
+  k.reserve(n);
+  v.reserve(n);
+  const u64 kmask = kmer_mask(c->params.K);
+  for (u64 i = 0; i < n; ++i) {
+    const u32 cnt = (u32)(int)counts[i];  // std::stoi(count) >= gp_MIN_COUNT compares as unsigned (Jellyfish.cpp:260)
+    if (cnt >= c->params.min_count && (keys[i] & ~kmask) == 0) {
+      k.push_back(keys[i]);
+      v.push_back(cnt);
+    }
+  }
+  std::vector<u64> ck;
+  std::vector<u32> cc;
+  reduce_colours(c->params, jkeys, jcounts, nj, use_junctions != 0, ck, cc);
+  return build_table(c, k, v, ck, cc, n_kept);
+}
+
+int talc_table_load_dump(talc_ctx* c, const char* dump_path, const char* junction_path, uint64_t* n_lines, uint64_t* n_kept) {
+  if (!c || !dump_path) return TALC_ERR_ARG;
+  DumpEntries d;
+  std::string err;
+  if (!parse_dump_file(dump_path, c->params.K, c->params.min_count, true, d, err)) {
+    c->err = err;
+    return TALC_ERR_IO;
+  }
+  if (n_lines) *n_lines = d.lines;
+  std::vector<u64> ck;
+  std::vector<u32> cc;
+  if (junction_path) {
+    DumpEntries j;
+    if (!parse_dump_file(junction_path, c->params.K, 0, false, j, err)) {
+      c->err = err;
+      return TALC_ERR_IO;
+    }
+    std::vector<i64> jc(j.counts.begin(), j.counts.end());
+    reduce_colours(c->params, j.keys.data(), jc.data(), j.keys.size(), true, ck, cc);
+  } else {
+    reduce_colours(c->params, nullptr, nullptr, 0, false, ck, cc);
+  }
+  std::vector<u32> v(d.counts.size());
+  for (size_t i = 0; i < v.size(); ++i) v[i] = (u32)(int)d.counts[i];
+  return build_table(c, d.keys, v, ck, cc, n_kept);
+}
+
+int talc_table_lookup(talc_ctx* c, const uint64_t* keys, uint64_t n, uint32_t* counts, uint32_t* colours, uint8_t* found) {
+  if (!c || !c->tableReady) return TALC_ERR_NO_TABLE;
+  if (!n) return TALC_OK;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  u64* dK;
+  u32 *dC, *dL;
+  u8* dF;
+  CUDA_TRY(c, cudaMalloc((void**)&dK, n * 8));
+  CUDA_TRY(c, cudaMalloc((void**)&dC, n * 4));
+  CUDA_TRY(c, cudaMalloc((void**)&dL, n * 4));
+  CUDA_TRY(c, cudaMalloc((void**)&dF, n));
+  CUDA_TRY(c, cudaMemcpyAsync(dK, keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+  TableView tv{c->slots, c->capacity - 1};
+  table_lookup_kernel<<<c->sms * 4, 256, 0, c->stream>>>(tv, dK, n, dC, dL, dF);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaMemcpyAsync(counts, dC, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(colours, dL, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(found, dF, n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(dK); cudaFree(dC); cudaFree(dL); cudaFree(dF);
+  return TALC_OK;
+}
+
+// ---------------------------------------------------------------------------------- correction
+// shared front end: k-mer offsets, length-sorted order, coverage.  d_bases/d_offs on device.
+static int prepare_batch(talc_ctx* c, const u8* dBases, const u64* dOffs, u32 n, u64 totalBases, u64& totalKmers) {
+  const u32 K = c->params.K;
+  CUDA_TRY(c, c->nk.reserve((size_t)(n + 1) * 8));
+  CUDA_TRY(c, c->kmerOff.reserve((size_t)(n + 1) * 8));
+  CUDA_TRY(c, c->sortKey.reserve((size_t)n * 4));
+  CUDA_TRY(c, c->sortKeyOut.reserve((size_t)n * 4));
+  CUDA_TRY(c, c->sortVal.reserve((size_t)n * 4));
+  CUDA_TRY(c, c->order.reserve((size_t)n * 4));
+  kmer_count_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(dOffs, n, K, (u64*)c->nk.p, (u32*)c->sortKey.p, (u32*)c->sortVal.p);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaMemsetAsync((u64*)c->nk.p + n, 0, 8, c->stream));
+  size_t tmp1 = 0, tmp2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp1, (u64*)c->nk.p, (u64*)c->kmerOff.p, n + 1, c->stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (u32*)c->sortKey.p, (u32*)c->sortKeyOut.p, (u32*)c->sortVal.p, (u32*)c->order.p,
+                                  (int)n, 0, 32, c->stream);
+  CUDA_TRY(c, c->cubTmp.reserve(std::max(tmp1, tmp2)));
+  size_t tb = c->cubTmp.cap;
+  CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubTmp.p, tb, (u64*)c->nk.p, (u64*)c->kmerOff.p, n + 1, c->stream));
+  tb = c->cubTmp.cap;
+  CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubTmp.p, tb, (u32*)c->sortKey.p, (u32*)c->sortKeyOut.p, (u32*)c->sortVal.p,
+                                              (u32*)c->order.p, (int)n, 0, 32, c->stream));
+  u64 hk = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&hk, (u64*)c->kmerOff.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  totalKmers = hk;
+  CUDA_TRY(c, c->cov.reserve((size_t)(hk + 4) * 4));
+  TableView tv{c->slots, c->capacity - 1};
+  const int blocks = c->sms * 8;
+  CUDA_TRY(c, cudaEventRecord(c->ev[1], c->stream));
+  coverage_kernel<<<blocks, 256, 0, c->stream>>>(tv, K, dBases, dOffs, (const u64*)c->kmerOff.p, n, (u32*)c->cov.p);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaEventRecord(c->ev[2], c->stream));
+  (void)totalBases;
+  return TALC_OK;
+}
+
+int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t* dOffs, uint32_t n, uint64_t totalBases,
+                              uint8_t* dOut, uint64_t outCapacity, uint64_t* dOutOffs, uint8_t* dStatus,
+                              talc_counters* counters) {
+  if (!c) return TALC_ERR_ARG;
+  if (!c->tableReady) { c->err = "no k-mer table loaded"; return TALC_ERR_NO_TABLE; }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (counters) memset(counters, 0, sizeof(*counters));
+  if (n == 0) {
+    if (dOutOffs) CUDA_TRY(c, cudaMemsetAsync(dOutOffs, 0, 8, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return TALC_OK;
+  }
+  CUDA_TRY(c, cudaEventRecord(c->ev[0], c->stream));
+  u64 totalKmers = 0;
+  int rc = prepare_batch(c, dBases, dOffs, n, totalBases, totalKmers);
+  if (rc) return rc;
+
+  // launch geometry: 128-thread blocks, a multiple of the SM count, no more threads than reads need
+  const u32 threadsWanted = ((n + 31) / 32) * 32;
+  u32 blocksPerSm = 4;
+  u32 blocks = (u32)c->sms * blocksPerSm;
+  while (blocks > (u32)c->sms && (u64)(blocks - c->sms) * 128 >= threadsWanted) blocks -= c->sms;
+  const u64 nThreads = (u64)blocks * 128;
+  const u64 outArenaCap = 2 * totalBases + (u64)n * 64 + 4096;
+  CUDA_TRY(c, c->arenas.reserve(std::max<size_t>((size_t)nThreads * c->tier1Bytes, (size_t)c->tier2Threads * c->tier2Bytes)));
+  CUDA_TRY(c, c->outArena.reserve(outArenaCap));
+  CUDA_TRY(c, c->outPos.reserve((size_t)n * 8));
+  CUDA_TRY(c, c->outLen.reserve((size_t)n * 4));
+  CUDA_TRY(c, c->outLen64.reserve((size_t)(n + 1) * 8));
+  CUDA_TRY(c, c->overflowList.reserve((size_t)n * 4));
+  CUDA_TRY(c, c->misc.reserve(1024));
+  // misc layout (u64 words): [0..kNumCounters) counters | then outCursor | workCounter,nOverflow,outFull (u32)
+  unsigned long long* dCounters = (unsigned long long*)c->misc.p;
+  unsigned long long* dCursor = dCounters + kNumCounters;
+  u32* dWork = (u32*)(dCursor + 1);
+  u32* dNOver = dWork + 1;
+  u32* dOutFull = dWork + 2;
+  CUDA_TRY(c, cudaMemsetAsync(c->misc.p, 0, 1024, c->stream));
+
+  CorrectArgs A;
+  A.tv = TableView{c->slots, c->capacity - 1};
+  A.P = c->P;
+  A.bases = dBases;
+  A.offs = dOffs;
+  A.kmerOff = (const u64*)c->kmerOff.p;
+  A.cov = (const u32*)c->cov.p;
+  A.order = (const u32*)c->order.p;
+  A.nOrder = n;
+  A.arenas = (u8*)c->arenas.p;
+  A.arenaBytes = c->tier1Bytes;
+  A.outArena = (u8*)c->outArena.p;
+  A.outCap = outArenaCap;
+  A.outCursor = dCursor;
+  A.outPos = (u64*)c->outPos.p;
+  A.outLen = (u32*)c->outLen.p;
+  A.status = dStatus;
+  A.counters = dCounters;
+  A.workCounter = dWork;
+  A.overflowList = (u32*)c->overflowList.p;
+  A.nOverflow = dNOver;
+  A.outFull = dOutFull;
+  correct_kernel<false><<<blocks, 128, 0, c->stream>>>(A);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+  u32 hOver = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&hOver, dNOver, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  u64 launches = 4;
+  u32 hOver2 = 0;
+  if (hOver > 0) {
+    // second tier: only the reads whose first-tier slice was too small, worst-case buffer sizing
+    CUDA_TRY(c, cudaMemsetAsync(dWork, 0, 8, c->stream));  // workCounter and nOverflow
+    CorrectArgs B = A;
+    B.order = (const u32*)c->overflowList.p;  // read in place: tier 2 appends to a second list
+    CUDA_TRY(c, c->sortVal.reserve((size_t)n * 4));
+    CUDA_TRY(c, cudaMemcpyAsync(c->sortVal.p, c->overflowList.p, (size_t)hOver * 4, cudaMemcpyDeviceToDevice, c->stream));
+    B.order = (const u32*)c->sortVal.p;
+    B.nOrder = hOver;
+    B.arenaBytes = c->tier2Bytes;
+    u32 b2 = std::max<u32>(1, std::min<u32>(c->tier2Threads / 128, (hOver + 127) / 128));
+    correct_kernel<true><<<b2, 128, 0, c->stream>>>(B);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(&hOver2, dNOver, 4, cudaMemcpyDeviceToHost, c->stream));
+    launches++;
+  }
+  CUDA_TRY(c, cudaEventRecord(c->ev[4], c->stream));
+  // input order: exclusive scan of the lengths, then gather
+  len_to_u64_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>((const u32*)c->outLen.p, n, (u64*)c->outLen64.p);
+  CUDA_TRY(c, cudaMemsetAsync((u64*)c->outLen64.p + n, 0, 8, c->stream));
+  size_t tb = c->cubTmp.cap;
+  CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubTmp.p, tb, (u64*)c->outLen64.p, dOutOffs, n + 1, c->stream));
+  u64 hTotalOut = 0;
+  u32 hOutFull = 0;
+  unsigned long long hCtr[kNumCounters];
+  CUDA_TRY(c, cudaMemcpyAsync(&hTotalOut, dOutOffs + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(&hOutFull, dOutFull, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(hCtr, dCounters, sizeof(hCtr), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (hOver2 > 0) {
+    c->err = "a read exhausted the second-tier scratch arena; raise it with talc_ctx_set_scratch";
+    return TALC_ERR_SCRATCH;
+  }
+  if (hOutFull) { c->err = "internal output arena too small"; return TALC_ERR_CAPACITY; }
+  if (hTotalOut > outCapacity) { c->err = "out_capacity too small for the corrected reads"; return TALC_ERR_CAPACITY; }
+  gather_kernel<<<c->sms * 8, 256, 0, c->stream>>>((const u8*)c->outArena.p, (const u64*)c->outPos.p, (const u32*)c->outLen.p,
+                                                  dOutOffs, n, dOut);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaEventRecord(c->ev[5], c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (counters) {
+    memcpy(counters, hCtr, sizeof(hCtr));
+    counters->reads = n;
+    counters->bases_in = totalBases;
+    counters->reads_second_tier = hOver;
+    counters->reads_overflow = hOver2;
+    counters->kernel_launches = launches + 3;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); counters->ms_coverage = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); counters->ms_correct = ms;
+    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); counters->ms_correct_tier2 = ms;
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); counters->ms_gather = ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]); counters->ms_total = ms;
+  }
+  return TALC_OK;
+}
+
+int talc_correct_batch(talc_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n, uint8_t* out,
+                       uint64_t outCapacity, uint64_t* outOffsets, uint8_t* status, talc_counters* counters) {
+  if (!c || !offsets || !outOffsets || (n && (!bases || !out || !status))) return TALC_ERR_ARG;
+  if (!c->tableReady) { c->err = "no k-mer table loaded"; return TALC_ERR_NO_TABLE; }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const u64 total = offsets[n] - offsets[0];
+  if (offsets[0] != 0) { c->err = "offsets[0] must be 0"; return TALC_ERR_ARG; }
+  CUDA_TRY(c, c->bases.reserve(total + 64));
+  CUDA_TRY(c, c->offs.reserve((size_t)(n + 1) * 8));
+  CUDA_TRY(c, c->status.reserve(n + 1));
+  CUDA_TRY(c, c->outOffs.reserve((size_t)(n + 1) * 8));
+  const u64 dOutCap = 2 * total + (u64)n * 64 + 4096;
+  CUDA_TRY(c, c->out.reserve(dOutCap));
+  CUDA_TRY(c, cudaEventRecord(c->ev[6], c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->bases.p, bases, total, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->offs.p, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaEventRecord(c->ev[7], c->stream));
+  talc_counters local;
+  int rc = talc_correct_batch_device(c, (const u8*)c->bases.p, (const u64*)c->offs.p, n, total, (u8*)c->out.p, dOutCap,
+                                     (u64*)c->outOffs.p, (u8*)c->status.p, &local);
+  if (rc) return rc;
+  float msH2D = 0;
+  cudaEventElapsedTime(&msH2D, c->ev[6], c->ev[7]);
+  CUDA_TRY(c, cudaEventRecord(c->ev[6], c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(outOffsets, c->outOffs.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(status, c->status.p, n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const u64 totalOut = outOffsets[n];
+  if (totalOut > outCapacity) { c->err = "out_capacity too small for the corrected reads"; return TALC_ERR_CAPACITY; }
+  CUDA_TRY(c, cudaMemcpyAsync(out, c->out.p, totalOut, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaEventRecord(c->ev[7], c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  float msD2H = 0;
+  cudaEventElapsedTime(&msD2H, c->ev[6], c->ev[7]);
+  if (counters) {
+    *counters = local;
+    counters->ms_h2d = msH2D;
+    counters->ms_d2h = msD2H;
+    counters->ms_total = local.ms_total + msH2D + msD2H;
+  }
+  return TALC_OK;
+}
+
+int talc_coverage_batch(talc_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n, uint32_t* counts,
+                        uint64_t countsCapacity) {
+  if (!c || !offsets || (n && !bases)) return TALC_ERR_ARG;
+  if (!c->tableReady) return TALC_ERR_NO_TABLE;
+  if (!n) return TALC_OK;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const u64 total = offsets[n];
+  CUDA_TRY(c, c->bases.reserve(total + 64));
+  CUDA_TRY(c, c->offs.reserve((size_t)(n + 1) * 8));
+  CUDA_TRY(c, cudaMemcpyAsync(c->bases.p, bases, total, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->offs.p, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  u64 totalKmers = 0;
+  int rc = prepare_batch(c, (const u8*)c->bases.p, (const u64*)c->offs.p, n, total, totalKmers);
+  if (rc) return rc;
+  if (totalKmers > countsCapacity) { c->err = "counts_capacity too small"; return TALC_ERR_CAPACITY; }
+  CUDA_TRY(c, cudaMemcpyAsync(counts, c->cov.p, totalKmers * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return TALC_OK;
+}
+
+// ---------------------------------------------------------------------------------- self-tests
+int talc_test_align(talc_ctx* c, int op, const uint8_t* a, const uint64_t* aOff, const uint8_t* b, const uint64_t* bOff,
+                    uint32_t n, int aux, int aux2, int32_t* result) {
+  if (!c || !n) return TALC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const u32 arenaBytes = 1u << 20;
+  u8 *dA, *dB, *dAr;
+  u64 *dAo, *dBo;
+  i32* dR;
+  const size_t rn = (size_t)n * (op == 3 ? 4 : 1);
+  CUDA_TRY(c, cudaMalloc((void**)&dA, aOff[n] + 1));
+  CUDA_TRY(c, cudaMalloc((void**)&dB, bOff[n] + 1));
+  CUDA_TRY(c, cudaMalloc((void**)&dAo, (size_t)(n + 1) * 8));
+  CUDA_TRY(c, cudaMalloc((void**)&dBo, (size_t)(n + 1) * 8));
+  CUDA_TRY(c, cudaMalloc((void**)&dAr, (size_t)n * arenaBytes));
+  CUDA_TRY(c, cudaMalloc((void**)&dR, rn * 4));
+  CUDA_TRY(c, cudaMemcpyAsync(dA, a, aOff[n], cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(dB, b, bOff[n], cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(dAo, aOff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(dBo, bOff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  test_align_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(op, dA, dAo, dB, dBo, n, aux, aux2, c->params.K, dAr, arenaBytes, dR);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaMemcpyAsync(result, dR, rn * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(dA); cudaFree(dB); cudaFree(dAo); cudaFree(dBo); cudaFree(dAr); cudaFree(dR);
+  return TALC_OK;
+}
+
+int talc_test_sort(talc_ctx* c, const int64_t* keys, uint32_t n, uint32_t* perm) {
+  if (!c || !n) return TALC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  i64* dK;
+  u32* dP;
+  CUDA_TRY(c, cudaMalloc((void**)&dK, (size_t)n * 8));
+  CUDA_TRY(c, cudaMalloc((void**)&dP, (size_t)n * 4));
+  CUDA_TRY(c, cudaMemcpyAsync(dK, keys, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  test_sort_kernel<<<1, 32, 0, c->stream>>>(dK, n, dP);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaMemcpyAsync(perm, dP, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(dK); cudaFree(dP);
+  return TALC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.  Integer / byte work, so the bar is bit-exact: identical corrected sequences, identical per-read
+status (= identical failed-read log), identical algorithmic counters."""
+import numpy as np
+import pytest
+
+from conftest import have_gpu
+
+pytestmark = pytest.mark.gpu
+
+SHARED = ["lookups_seg", "lookups_deg", "lookups_walk", "steps_inner", "steps_border", "frontier_sum", "cells_nw",
+          "cells_lcs", "cells_ovl", "cells_xdrop", "gaps", "gaps_bridged", "gap_attempts", "borders",
+          "borders_corrected", "ev_gardening", "ev_bridge", "ev_edge", "ev_cycle", "bases_out"]
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not have_gpu():
+        pytest.fail("GPU tests selected but no CUDA device is visible")
+    from talc_b200 import api as _api
+    return _api
+
+
+def _ctx(api, case, **kw):
+    t = api.Talc(api.default_params(case.cfg.k, **kw))
+    t.load_packed(case.keys, case.counts, case.jkeys, case.jcounts)
+    return t
+
+
+def _assert_same(case, out, off, status, ctr=None):
+    assert np.array_equal(status, case.o_status), "per-read status (failed-read log) differs"
+    bad = [r for r in range(len(case.off) - 1)
+           if out[int(off[r]):int(off[r + 1])].tobytes() != case.oracle_read(r)]
+    assert not bad, "corrected sequence differs for reads %s" % bad[:10]
+    if ctr is not None:
+        diff = {k: (case.o_ctr[k], ctr[k]) for k in SHARED if case.o_ctr[k] != ctr[k]}
+        assert not diff, "algorithmic counters differ: %s" % diff
+
+
+def test_table_matches_oracle(api, case_c3):
+    case = case_c3
+    t = _ctx(api, case)
+    info = t.table_info()
+    assert info["entries"] == case.otable.size()
+    from talc_b200 import synth
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, len(case.keys), 4000)
+    probe = np.concatenate([case.keys[idx], rng.integers(0, 1 << 42, 500).astype(np.uint64)])
+    cnt, col, found = t.lookup(probe)
+    for i, key in enumerate(probe):
+        f, c, l = case.otable.lookup(synth.unpack_kmer(int(key), case.cfg.k))
+        assert (bool(found[i]), int(cnt[i]), int(col[i])) == (f, c, l)
+    assert (col > 0).any(), "junction colours must be exercised"
+
+
+def test_coverage_matches_oracle(api, case_c1):
+    case = case_c1
+    t = _ctx(api, case)
+    cov = t.coverage(case.reads, case.off)
+    pos = 0
+    for r in range(40):
+        ocnt, _ = case.otable.coverage(case.read(r))
+        assert np.array_equal(cov[pos:pos + len(ocnt)], ocnt)
+        pos += len(ocnt)
+
+
+def test_correction_config1(api, case_c1):
+    t = _ctx(api, case_c1)
+    out, off, st, ctr = t.correct(case_c1.reads, case_c1.off)
+    _assert_same(case_c1, out, off, st, ctr)
+
+
+def test_correction_junctions_config3(api, case_c3):
+    t = _ctx(api, case_c3)
+    out, off, st, ctr = t.correct(case_c3.reads, case_c3.off)
+    _assert_same(case_c3, out, off, st, ctr)
+
+
+def test_correction_stress_config5(api, case_c5):
+    """k=30, 15% errors, low-complexity inserts: frontier > 50 aborts, gardening with ties, second tier."""
+    assert case_c5.o_ctr["ev_gardening"] > 0 and case_c5.o_ctr["ev_frontier_over50"] > 0
+    t = _ctx(api, case_c5)
+    out, off, st, ctr = t.correct(case_c5.reads, case_c5.off)
+    _assert_same(case_c5, out, off, st, ctr)
+    assert ctr["reads_second_tier"] > 0
+
+
+def test_second_tier_is_result_neutral(api, case_c1):
+    """A tiny first-tier scratch slice pushes most reads through the second tier; bytes must not change."""
+    t = _ctx(api, case_c1)
+    t.set_scratch(tier1_bytes=6 * 1024)
+    out, off, st, ctr = t.correct(case_c1.reads, case_c1.off)
+    assert ctr["reads_second_tier"] > 0
+    _assert_same(case_c1, out, off, st, ctr)
+
+
+def test_batch_is_idempotent_and_order_independent(api, case_c1):
+    case = case_c1
+    t = _ctx(api, case)
+    out1, off1, st1, _ = t.correct(case.reads, case.off)
+    out2, off2, st2, _ = t.correct(case.reads, case.off)
+    assert np.array_equal(out1, out2) and np.array_equal(off1, off2) and np.array_equal(st1, st2)
+    # reversed read order gives the same per-read answers
+    n = len(case.off) - 1
+    parts = [case.reads[int(case.off[r]):int(case.off[r + 1])] for r in range(n)][::-1]
+    roff = np.zeros(n + 1, dtype=np.uint64)
+    roff[1:] = np.cumsum([len(p) for p in parts])
+    out3, off3, st3, _ = t.correct(np.concatenate(parts), roff)
+    for r in range(n):
+        a = out1[int(off1[r]):int(off1[r + 1])].tobytes()
+        b = out3[int(off3[n - 1 - r]):int(off3[n - r])].tobytes()
+        assert a == b
+
+
+def test_edge_cases(api, case_c1):
+    """Empty batch, empty read, reads <= K, reads with N, lower case, all-unknown read."""
+    case = case_c1
+    t = _ctx(api, case)
+    k = case.cfg.k
+    base = case.read(0)
+    reads = [b"", b"ACGT", base[:k], base[:k + 1], base.lower(), base[:200] + b"NNNN" + base[200:], b"N" * 300,
+             base[:90] + b"R" + base[91:]]
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    data = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    out, ooff, st, _ = t.correct(data, off)
+    o_out, o_off, o_st, _, _ = case.otable.correct(data, off, threads=1)
+    assert np.array_equal(st, o_st)
+    assert np.array_equal(out, o_out) and np.array_equal(ooff, o_off)
+    e_out, e_off, e_st, _ = t.correct(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    assert len(e_out) == 0 and len(e_st) == 0
+
+
+def test_alignment_primitives_on_device(api, case_c1):
+    from oracle import pyoracle as po
+    case = case_c1
+    t = _ctx(api, case)
+    rng = np.random.default_rng(7)
+
+    def mutate(s: bytes, rate: float) -> bytes:
+        out = bytearray()
+        for ch in s:
+            u = rng.random()
+            if u < rate * 0.4:
+                out.append(rng.choice(list(b"ACGT")))
+            elif u < rate * 0.7:
+                out.append(ch)
+                out.append(rng.choice(list(b"ACGT")))
+            elif u < rate:
+                continue
+            else:
+                out.append(ch)
+        return bytes(out) or b"A"
+
+    a_list, b_list = [], []
+    for i in range(120):
+        n = int(rng.integers(1, 700))
+        s = bytes(rng.choice(list(b"ACGT"), n).tolist())
+        a = mutate(s, 0.15)
+        if i % 7 == 0:
+            a = a[: len(a) // 2] + b"N" + a[len(a) // 2:]
+        a_list.append(a)
+        b_list.append(s)
+    nw = t.test_align(0, a_list, b_list)
+    lcs = t.test_align(1, a_list, b_list)
+    ovl = t.test_align(2, a_list, b_list)
+    for i, (a, b) in enumerate(zip(a_list, b_list)):
+        assert nw[i] == po.nw(a, b)
+        assert lcs[i] == po.lcs(a, b)
+        assert ovl[i] == po.overlap(a, b, True)
+    # seed-and-extension (X-drop end positions + NW of the extensions), both directions
+    k = case.cfg.k
+    refs, cands = [], []
+    for i in range(80):
+        n = int(rng.integers(k + 5, 400))
+        s = bytes(rng.choice(list(b"ACGT"), n).tolist())
+        c = s[:k] + mutate(s[k:], 0.12)
+        if i % 3 == 0:
+            c = c[: max(k + 1, len(c) // 2)]
+        refs.append(s)
+        cands.append(c if len(c) >= k else s)
+    for x in (-1, 0, 2, 4, 9, 30):
+        res = t.test_align(3, refs, cands, aux=x, aux2=1)
+        for i, (r, c) in enumerate(zip(refs, cands)):
+            re_, ce_, pos, sc, stop = po.seed_extend(r, c, x, True, k)
+            assert tuple(res[i]) == (re_, ce_, int(sc), int(stop)), (i, x)
+        # LEFT: the device works on reversed strings (walk order)
+        res = t.test_align(3, [r[::-1] for r in refs], [c[::-1] for c in cands], aux=x, aux2=0)
+        for i, (r, c) in enumerate(zip(refs, cands)):
+            re_, ce_, pos, sc, stop = po.seed_extend(r, c, x, False, k)
+            assert tuple(res[i]) == (re_, ce_, int(sc), int(stop)), (i, x)
+
+
+def test_std_sort_replica_on_device(api, case_c1):
+    from oracle import pyoracle as po
+    t = _ctx(api, case_c1)
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 5, 16, 17, 33, 64, 100, 207):
+        for hi in (2, 4, 50, 10 ** 9):
+            keys = rng.integers(0, hi, n)
+            assert np.array_equal(t.test_sort(keys), po.std_sort_perm(keys)), (n, hi)
+    keys = np.arange(200)[::-1].copy()
+    assert np.array_equal(t.test_sort(keys), po.std_sort_perm(keys))
