@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- corrected long-read Mbp/s of the TALC correction hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement of the reference, host cores
+
+Workload = BASELINE.json configs[1]: a 200k-transcript synthetic transcriptome (20k genes + isoforms),
+its ~30M-entry k=21 count table, ONT-like long reads (10% error).  A step is one pass of the hot path over
+one batch of `--batch-reads` reads of that set (a different slice every step); the table always has its
+full size, so the probes miss L2 as they would on the full run.  Multi-GPU is weak scaling: every rank holds
+a replica of the table (built on rank 0, one NCCL broadcast) and corrects its own batches; no per-read
+communication.  `value` = bases of all ranks / device time (max over ranks) with inputs resident in HBM;
+`e2e` = the same through the host-buffer C-ABI call, copies included.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "corrected long-read Mbp/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="talc_b200", choices=["talc_b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config index (1-based): 2, 3 (junctions) or 1/5")
+    ap.add_argument("--scale", type=float, default=1.0, help="scales transcripts and reads (1.0 = the named config)")
+    ap.add_argument("--batch-reads", type=int, default=131072, help="reads per step and per rank")
+    ap.add_argument("--cpu-sample-reads", type=int, default=384, help="reads of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_name(args, cfg):
+    return ("config%d: %d transcripts (%d genes + isoforms), k=%d count table, ONT-like reads %.0f%% error; "
+            "step = batch of %d reads per GPU" % (args.config, cfg.n_transcripts, cfg.n_genes, cfg.k,
+                                                   100 * cfg.read_error, args.batch_reads))
+
+
+# ----------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path = the oracle restatement (the real binary needs SeqAn2,
+    absent here), ordered std::map table as in the reference, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from oracle import pyoracle as po
+    from talc_b200 import synth
+    cfg = synth.baseline_config(args.config, args.scale)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    tr = synth.make_transcriptome(cfg, dev)
+    keys, counts, jk, jc = synth.make_counts(cfg, tr, dev)
+    use_j = args.config == 3
+    nsample = args.cpu_sample_reads
+    reads, roff = synth.make_reads(cfg, tr, nsample * (args.steps + args.warmup), dev, seed_offset=3)
+    reads, roff = reads.cpu().numpy(), roff.cpu().numpy().astype(np.uint64)
+    threads = os.cpu_count() or 1
+    t0 = time.time()
+    ot = po.OracleTable(po.make_params(k=cfg.k), ordered=True)
+    ot.build_packed(keys.cpu().numpy().astype(np.uint64), counts.cpu().numpy(),
+                    jk.cpu().numpy().astype(np.uint64) if use_j else None, jc.cpu().numpy() if use_j else None)
+    t_table = time.time() - t0
+    times, bases = [], 0
+    for it in range(args.warmup + args.steps):
+        lo, hi = it * nsample, (it + 1) * nsample
+        sub = reads[int(roff[lo]):int(roff[hi])]
+        so = roff[lo:hi + 1] - roff[lo]
+        _, _, _, _, secs = ot.correct(sub, so, threads=threads)
+        if it >= args.warmup:
+            times.append(secs)
+            bases += int(so[-1])
+    total = sum(times)
+    v = bases / 1e6 / total
+    line = {"metric": METRIC, "value": v, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64/f64 (integer k-mer and DP arithmetic, double decisions)", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": workload_name(args, cfg), "table_entries_kept": ot.size(), "table": "std::map (ordered, as the reference)",
+                       "sample_reads_per_step": nsample, "table_build_s": round(t_table, 1)},
+            "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": threads, "kind": "port",
+                             "sample": "%d reads per step of the same read set (oracle restatement, OpenMP over reads)" % nsample},
+            "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from talc_b200 import api, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the correction path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    cfg = synth.baseline_config(args.config, args.scale)
+    use_j = args.config == 3
+    t0 = time.time()
+    tr = synth.make_transcriptome(cfg, dev)
+    ctx = api.Talc(api.default_params(cfg.k), device=local_rank)
+    keys = counts = jk = jc = None
+    t_build = 0.0
+    if rank == 0:
+        keys, counts, jk, jc = synth.make_counts(cfg, tr, dev)
+        tb = time.time()
+        ctx.load_packed(keys.cpu().numpy().astype(np.uint64), counts.cpu().numpy(),
+                        jk.cpu().numpy().astype(np.uint64) if use_j else None, jc.cpu().numpy() if use_j else None)
+        t_build = time.time() - tb
+    info = ctx.table_info()
+    t_bcast_ms = 0.0
+    if world > 1:
+        # replicate: one NCCL broadcast of the raw slot array over NVLink, then each rank seals its copy
+        meta = torch.tensor([info["capacity"], info["entries"]], dtype=torch.int64, device=dev)
+        dist.broadcast(meta, 0)
+        cap, nent = int(meta[0]), int(meta[1])
+        staging = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            ctx.table_export_device(staging)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(staging, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        t_bcast_ms = e0.elapsed_time(e1)
+        if rank != 0:
+            ctx.table_import_device(staging, cap, nent)
+        del staging
+        info = ctx.table_info()
+    # this rank's reads: batch_reads per step, a different slice every step (and every rank)
+    nsteps = args.warmup + args.steps + 1  # +1 slice for the e2e leg warm-up
+    B = args.batch_reads
+    reads, roff = synth.make_reads(cfg, tr, B * nsteps, dev, seed_offset=3 + 17 * rank)
+    cpu_keys = (keys, counts, jk, jc)
+    del tr
+    t_gen = time.time() - t0
+    roff = roff.to(torch.int64)
+
+    def batch(i):
+        lo, hi = (i % nsteps) * B, (i % nsteps + 1) * B
+        b0, b1 = int(roff[lo]), int(roff[hi])
+        return reads[b0:b1].contiguous(), (roff[lo:hi + 1] - roff[lo]).contiguous(), b1 - b0
+
+    maxb = max(int(roff[(i + 1) * B] - roff[i * B]) for i in range(nsteps))
+    d_out = torch.empty(2 * maxb + 64 * B + 4096, dtype=torch.uint8, device=dev)
+    d_ooff = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+    d_st = torch.zeros(B, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: W warm-up steps, then exactly K timed steps
+    for i in range(args.warmup):
+        r, o, nb = batch(i)
+        ctx.correct_device(r, o, nb, d_out, d_ooff, d_st)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    wall0 = time.time()
+    dev_ms, bases, agg = 0.0, 0, None
+    launches = 0
+    for i in range(args.warmup, args.warmup + args.steps):
+        r, o, nb = batch(i)
+        c = ctx.correct_device(r, o, nb, d_out, d_ooff, d_st)
+        dev_ms += c["ms_total"]
+        bases += nb
+        launches += 5 + (1 if c["reads_second_tier"] else 0)  # kmer_count, coverage, correct(+tier2), len_to_u64, gather
+        if agg is None:
+            agg = dict(c)
+        else:
+            for k2, v2 in c.items():
+                agg[k2] += v2
+    barrier()
+    wall = time.time() - wall0
+    clocks = sampler.stop()
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(bases)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    value = float(tot) / 1e6 / (float(tmax) / 1e3)
+
+    # ---- end-to-end leg: host (pinned) buffers through talc_correct_batch, copies inside the timed region
+    e2e_ms, e2e_bases, h2d, d2h = 0.0, 0, 0, 0
+    host_out = torch.empty(2 * maxb + 64 * B + 4096, dtype=torch.uint8).pin_memory().numpy()
+    host_ooff = np.zeros(B + 1, dtype=np.uint64)
+    host_st = np.zeros(B, dtype=np.uint8)
+    pinned = []
+    for i in range(args.warmup + args.steps - 1, args.warmup + args.steps + 1):
+        r, o, nb = batch(i)
+        pinned.append((r.cpu().pin_memory().numpy(), o.cpu().numpy().astype(np.uint64), nb))
+    ctx.correct(pinned[1][0], pinned[1][1], host_out, host_ooff, host_st)  # warm-up of the host path
+    barrier()
+    e2e_steps = max(1, min(args.steps, 2))
+    for s in range(e2e_steps):
+        hr, ho, nb = pinned[s % 2]
+        out, ooff, st, c = ctx.correct(hr, ho, host_out, host_ooff, host_st)
+        e2e_ms += c["ms_total"]
+        e2e_bases += nb
+        h2d = nb + 8 * (B + 1)
+        d2h = int(ooff[-1]) + 8 * (B + 1) + B
+    barrier()
+    emax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    etot = torch.tensor([float(e2e_bases)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(etot, op=dist.ReduceOp.SUM)
+    e2e_value = float(etot) / 1e6 / (float(emax) / 1e3)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # dominant kernel = correct_kernel.  Algorithmic bytes per launch: one 32-byte sector per
+        # logical k-mer look-up (getOutDegree + whatsNext calls, 4 each) + 2 bits per input base + 1 byte per output base
+        steps = args.steps
+        lookups = agg["lookups_deg"] + agg["lookups_walk"]
+        alg_bytes = (32.0 * lookups + agg["bases_in"] / 4.0 + agg["bases_out"]) / steps
+        k_ms = (agg["ms_correct"] + agg["ms_correct_tier2"]) / steps
+        achieved = alg_bytes / 1e9 / (k_ms / 1e3)
+        cov_bytes = (32.0 * agg["lookups_seg"] + agg["bases_in"] / 4.0 + 4.0 * agg["lookups_seg"]) / steps
+        cov_ms = agg["ms_coverage"] / steps
+        line = {"metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": float(tmax) / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64/f64 (integer k-mer and DP arithmetic, double decisions)",
+                "data": "synthetic", "impl": "talc_b200",
+                "config": {"workload": workload_name(args, cfg), "table_entries_kept": info["entries"],
+                           "table_bytes": info["bytes"], "reads_per_step_per_gpu": B,
+                           "l2": "inputs larger than L2: %.2f GB table + %.0f MB of reads per step" % (info["bytes"] / 1e9, bases / steps / 1e6),
+                           "generate_s": round(t_gen, 1), "table_build_s": round(t_build, 2),
+                           "table_broadcast_ms": round(t_bcast_ms, 2), "wall_s_timed_region": round(wall, 3)},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "correct_kernel", "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": k_ms,
+                             "coverage_kernel": {"achieved": cov_bytes / 1e9 / (cov_ms / 1e3), "ms_per_launch": cov_ms,
+                                                 "algorithmic_bytes_per_launch": cov_bytes,
+                                                 "frac": cov_bytes / 1e9 / (cov_ms / 1e3) / peak}},
+                "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches,
+                "clocks": clocks,
+                "counters": {k2: agg[k2] for k2 in ("lookups_seg", "lookups_deg", "lookups_walk", "steps_inner", "steps_border",
+                                                     "cells_nw", "cells_lcs", "cells_ovl", "cells_xdrop", "gaps", "gaps_bridged",
+                                                     "reads_second_tier", "reads_ok", "reads")},
+                "cpu_baseline": None}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, cfg, cpu_keys, use_j, reads, roff)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, cfg, cpu_keys, use_j, reads, roff):
+    """The oracle port on this box's host cores, on a bounded sample of the same reads (rank 0, N=1 only)."""
+    import numpy as np
+    from oracle import pyoracle as po
+    keys, counts, jk, jc = cpu_keys
+    threads = os.cpu_count() or 1
+    ot = po.OracleTable(po.make_params(k=cfg.k), ordered=False)
+    ot.build_packed(keys.cpu().numpy().astype(np.uint64), counts.cpu().numpy(),
+                    jk.cpu().numpy().astype(np.uint64) if use_j else None, jc.cpu().numpy() if use_j else None)
+    n = args.cpu_sample_reads
+    sub = reads[: int(roff[n])].cpu().numpy()
+    so = roff[: n + 1].cpu().numpy().astype(np.uint64)
+    _, _, _, _, secs = ot.correct(sub, so, threads=threads)
+    return {"value": int(so[-1]) / 1e6 / secs, "unit": "Mbp/s", "cores": threads, "kind": "port",
+            "sample": "first %d reads of the step-0 batch (%.2f Mbp), oracle restatement with a hashed table, %.1f s" % (
+                n, int(so[-1]) / 1e6, secs)}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,7 +89,7 @@ int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out);
 void talc_ctx_destroy(talc_ctx* ctx);
 const char* talc_last_error(talc_ctx* ctx);   /* ctx may be NULL: last create error */
 
-/* scratch sizing (optional): bytes per thread for the first and second tier, resident threads per SM */
+/* scratch sizing (optional): bytes per thread for the first and second tier, warps (= reads in flight) of the second tier */
 int talc_ctx_set_scratch(talc_ctx* ctx, uint32_t tier1_bytes, uint32_t tier2_bytes, uint32_t tier2_threads);
 
 /* ---- k-mer table (main.cpp:231-232) -------------------------------------------------------- */
@@ -106,6 +106,10 @@ int talc_table_info(talc_ctx* ctx, uint64_t* capacity_slots, uint64_t* bytes, ui
 int talc_table_alloc(talc_ctx* ctx, uint64_t capacity_slots);
 int talc_table_device_ptr(talc_ctx* ctx, void** device_ptr);
 int talc_table_seal(talc_ctx* ctx, uint64_t n_entries);
+/* the same two steps with a caller-owned DEVICE staging buffer of `bytes` = capacity*16 (e.g. the
+ * tensor handed to ncclBroadcast): export copies the sealed table out, import allocates+copies+seals */
+int talc_table_export_device(talc_ctx* ctx, void* dst_device, uint64_t bytes);
+int talc_table_import_device(talc_ctx* ctx, const void* src_device, uint64_t capacity_slots, uint64_t n_entries);
 /* single-process replication: copy src's sealed table to dst's device (peer copy over NVLink)    */
 int talc_table_copy(talc_ctx* dst, talc_ctx* src);
 /* point look-ups from the host (tests, debugging): found[i] in {0,1}                              */

@@ -42,7 +42,8 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        path = _build.build_library()
+        import os
+        path = os.environ.get("TALC_LIB") or _build.build_library()  # TALC_LIB: tuning builds only
         L = C.CDLL(path)
         vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
         L.talc_params_default.argtypes = [C.POINTER(TalcParams), C.c_uint32]
@@ -58,6 +59,8 @@ def lib():
         L.talc_table_device_ptr.argtypes = [vp, C.POINTER(vp)]
         L.talc_table_seal.argtypes = [vp, C.c_uint64]
         L.talc_table_copy.argtypes = [vp, vp]
+        L.talc_table_export_device.argtypes = [vp, vp, C.c_uint64]
+        L.talc_table_import_device.argtypes = [vp, vp, C.c_uint64, C.c_uint64]
         L.talc_table_lookup.argtypes = [vp, vp, C.c_uint64, vp, vp, vp]
         L.talc_correct_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint64, vp, vp, C.POINTER(TalcCounters)]
         L.talc_correct_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint64, vp, vp,
@@ -146,6 +149,14 @@ class Talc:
 
     def table_seal(self, n_entries: int):
         self._check(lib().talc_table_seal(self.h, n_entries), "talc_table_seal")
+
+    def table_export_device(self, tensor):
+        self._check(lib().talc_table_export_device(self.h, tensor.data_ptr(), tensor.numel() * tensor.element_size()),
+                    "talc_table_export_device")
+
+    def table_import_device(self, tensor, capacity: int, n_entries: int):
+        self._check(lib().talc_table_import_device(self.h, tensor.data_ptr(), capacity, n_entries),
+                    "talc_table_import_device")
 
     def lookup(self, keys):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)

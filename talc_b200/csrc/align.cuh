@@ -54,7 +54,7 @@ TALC_HDN void build_peq(const SeqView& pat, u32 pn, u32 block, u64 peq[5]) {
 }
 
 // unit-cost edit distance between a[0..an) and b[0..bn) (both non-empty)
-TALC_HDN int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+TALC_HDN int nw_distance_scalar(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   // pattern (rows, bit-parallel) = the shorter one, text (columns) = the longer one
   const bool a_is_pat = an <= bn;
   const SeqView& pat = a_is_pat ? a : b;
@@ -101,7 +101,7 @@ TALC_HDN int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Are
 }
 
 // length of the longest common subsequence of a[0..an) and b[0..bn) (both non-empty)
-TALC_HDN int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+TALC_HDN int lcs_length_scalar(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   const bool a_is_pat = an <= bn;
   const SeqView& pat = a_is_pat ? a : b;
   const SeqView& txt = a_is_pat ? b : a;
@@ -143,9 +143,149 @@ TALC_HDN int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Aren
   return lcs;
 }
 
+#if defined(__CUDA_ARCH__)
+// Device forms: the 64-row blocks of the pattern are spread over the lanes and the text streams through them
+// as a systolic pipeline -- lane L works on text column t-L at time t and hands its horizontal delta (Myers)
+// or its addition carry (LCS) to lane L+1 with one shuffle.  More than 32 blocks are processed in stripes with
+// the boundary deltas parked in the scratch arena, exactly like the scalar form does for every block.
+__device__ __noinline__ int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+  const bool a_is_pat = an <= bn;
+  const u32 pn = a_is_pat ? an : bn;
+  if (pn <= 64) return nw_distance_scalar(a, an, b, bn, ar, st);
+  const SeqView& pat = a_is_pat ? a : b;
+  const SeqView& txt = a_is_pat ? b : a;
+  const u32 tn = a_is_pat ? bn : an;
+  if (st) st->cells_nw += (u64)an * bn;
+  const u32 lane = threadIdx.x & 31u;
+  const u32 nblocks = (pn + 63) / 64;
+  const u32 mk = ar.mark();
+  signed char* h = nullptr;
+  if (nblocks > 32) {
+    h = (signed char*)ar.alloc(tn);
+    if (!h) return 0;
+  }
+  int score = 0;
+  for (u32 s0 = 0; s0 < nblocks; s0 += 32) {
+    const u32 blk = s0 + lane;
+    const bool haveBlk = blk < nblocks;
+    const u32 nb = (nblocks - s0 < 32u) ? (nblocks - s0) : 32u;  // blocks in this stripe
+    u64 peq[5] = {0, 0, 0, 0, 0};
+    if (haveBlk) build_peq(pat, pn, blk, peq);
+    const bool last = haveBlk && (blk + 1 == nblocks);
+    const u32 top = last ? (pn - blk * 64 - 1) : 63;
+    u64 Pv = ~0ull, Mv = 0;
+    int houtPrev = 0;
+    u32 cPrev = 4;
+    int acc = 0;
+    __syncwarp();
+    for (u32 t = 0; t < tn + nb - 1; ++t) {
+      int hin = __shfl_up_sync(0xffffffffu, houtPrev, 1);
+      u32 c = __shfl_up_sync(0xffffffffu, cPrev, 1);
+      if (lane == 0) {
+        c = (t < tn) ? txt.code(t) : 4u;
+        hin = (s0 == 0) ? 1 : ((t < tn) ? (int)h[t] : 0);
+      }
+      const bool valid = haveBlk && (t >= lane) && (t - lane < tn);
+      int hout = 0;
+      if (valid) {
+        u64 Eq = peq[c];
+        const u64 hneg = (hin < 0) ? 1ull : 0ull;
+        const u64 Xv = Eq | Mv;
+        Eq |= hneg;
+        const u64 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        u64 Ph = Mv | ~(Xh | Pv);
+        u64 Mh = Pv & Xh;
+        hout = (int)((Ph >> top) & 1ull) - (int)((Mh >> top) & 1ull);
+        Ph <<= 1;
+        Mh <<= 1;
+        Mh |= hneg;
+        Ph |= (hin > 0) ? 1ull : 0ull;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+        if (last) acc += hout;
+        else if (lane == 31) h[t - lane] = (signed char)hout;  // stripe boundary
+      }
+      houtPrev = hout;
+      cPrev = c;
+    }
+    // the lane that owns the last block carries the score
+    const int lastLane = (int)((nblocks - 1) - s0);
+    if (lastLane >= 0 && lastLane < 32) score = (int)pn + __shfl_sync(0xffffffffu, acc, lastLane);
+    __syncwarp();
+  }
+  ar.release(mk);
+  return score;
+}
+
+__device__ __noinline__ int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+  const bool a_is_pat = an <= bn;
+  const u32 pn = a_is_pat ? an : bn;
+  if (pn <= 64) return lcs_length_scalar(a, an, b, bn, ar, st);
+  const SeqView& pat = a_is_pat ? a : b;
+  const SeqView& txt = a_is_pat ? b : a;
+  const u32 tn = a_is_pat ? bn : an;
+  if (st) st->cells_lcs += (u64)an * bn;
+  const u32 lane = threadIdx.x & 31u;
+  const u32 nblocks = (pn + 63) / 64;
+  const u32 mk = ar.mark();
+  u8* carry = nullptr;
+  if (nblocks > 32) {
+    carry = (u8*)ar.alloc(tn);
+    if (!carry) return 0;
+  }
+  int lcs = 0;
+  for (u32 s0 = 0; s0 < nblocks; s0 += 32) {
+    const u32 blk = s0 + lane;
+    const bool haveBlk = blk < nblocks;
+    const u32 nb = (nblocks - s0 < 32u) ? (nblocks - s0) : 32u;
+    u64 peq[5] = {0, 0, 0, 0, 0};
+    if (haveBlk) build_peq(pat, pn, blk, peq);
+    const bool last = haveBlk && (blk + 1 == nblocks);
+    const u32 rows = last ? (pn - blk * 64) : 64;
+    u64 V = ~0ull;
+    u32 coutPrev = 0, cPrev = 4;
+    __syncwarp();
+    for (u32 t = 0; t < tn + nb - 1; ++t) {
+      u32 cin = __shfl_up_sync(0xffffffffu, coutPrev, 1);
+      u32 c = __shfl_up_sync(0xffffffffu, cPrev, 1);
+      if (lane == 0) {
+        c = (t < tn) ? txt.code(t) : 4u;
+        cin = (s0 == 0) ? 0u : ((t < tn) ? (u32)carry[t] : 0u);
+      }
+      const bool valid = haveBlk && (t >= lane) && (t - lane < tn);
+      u32 cout = 0;
+      if (valid) {
+        const u64 M = peq[c];
+        const u64 U = V & M;
+        const u64 tt = V + U;
+        const u64 sum = tt + (u64)cin;
+        cout = (u32)(tt < V) | (u32)(sum < tt);
+        V = sum | (V & ~M);
+        if (!last && lane == 31) carry[t - lane] = (u8)cout;
+      }
+      coutPrev = cout;
+      cPrev = c;
+    }
+    int z = 0;
+    if (haveBlk) z = __popcll(~V & ((rows == 64) ? ~0ull : ((1ull << rows) - 1ull)));
+    lcs += (int)__reduce_add_sync(0xffffffffu, (unsigned)z);
+    __syncwarp();
+  }
+  ar.release(mk);
+  return lcs;
+}
+#else
+inline int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+  return nw_distance_scalar(a, an, b, bn, ar, st);
+}
+inline int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+  return lcs_length_scalar(a, an, b, bn, ar, st);
+}
+#endif
+
 // Trail::Overlapscore in walk order: match 4 / mismatch -3 / gap -2, leading gaps of both
 // sequences free, trailing gaps charged; score = bottom-right cell.
-TALC_HDN int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {
+TALC_HDN int overlap_score_scalar(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {
   if (st) st->cells_ovl += (u64)rn * cn;
   const u32 mk = ar.mark();
   i32* row = (i32*)ar.alloc((cn + 1) * 4);
@@ -171,11 +311,65 @@ TALC_HDN int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 
   return res;
 }
 
+#if defined(__CUDA_ARCH__)
+// Device form: one DP row at a time, 32 columns per pass.  The vertical and diagonal terms of a cell only need
+// the previous row; the horizontal term v[j] = max(t[j], v[j-1] - 2) unrolls to max_{l<=j}(t[l] + 2l) - 2j,
+// a prefix maximum, i.e. one five-step warp scan per pass.  Integer arithmetic, identical to the scalar form.
+__device__ __noinline__ int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {
+  if (st) st->cells_ovl += (u64)rn * cn;
+  const u32 lane = threadIdx.x & 31u;
+  const u32 mk = ar.mark();
+  i32* row = (i32*)ar.alloc((cn + 1) * 4);
+  if (!row) return 0;
+  for (u32 j = lane; j <= cn; j += 32) row[j] = 0;
+  __syncwarp();
+  const i32 NEG = -(1 << 28);
+  for (u32 i = 0; i < rn; ++i) {
+    const u32 rc = ref.code(i);
+    i32 leftNew = 0;  // S[i][0]
+    i32 leftOld = 0;  // S[i-1][0]
+    for (u32 j0 = 1; j0 <= cn; j0 += 32) {
+      const u32 j = j0 + lane;
+      const bool act = j <= cn;
+      const i32 up = act ? row[j] : NEG;
+      i32 diag = __shfl_up_sync(0xffffffffu, up, 1);
+      if (lane == 0) diag = leftOld;
+      i32 t = NEG;
+      if (act) {
+        const i32 d = diag + ((rc == cand.code(j - 1)) ? 4 : -3);
+        const i32 u = up - 2;
+        t = d > u ? d : u;
+      }
+      i32 a = t + 2 * (i32)j;  // prefix maximum of t[l] + 2l
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const i32 other = __shfl_up_sync(0xffffffffu, a, o);
+        if ((int)lane >= o) a = a > other ? a : other;
+      }
+      const i32 fromLeft = leftNew + 2 * (i32)(j0 - 1);
+      i32 v = (a > fromLeft ? a : fromLeft) - 2 * (i32)j;
+      if (act) row[j] = v;
+      leftOld = __shfl_sync(0xffffffffu, up, 31);
+      leftNew = __shfl_sync(0xffffffffu, v, 31);
+    }
+    __syncwarp();
+  }
+  const int res = row[cn];
+  __syncwarp();
+  ar.release(mk);
+  return res;
+}
+#else
+inline int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {
+  return overlap_score_scalar(ref, rn, cand, cn, ar, st);
+}
+#endif
+
 // SeqAn 2.x _extendSeedGappedXDropOneDirection for Score(0,-1,-1) on query[qoff..qoff+qlen) (V, columns)
 // and database[doff..doff+dlen) (H, rows), both in walk order.  Outputs how far the seed moved along
 // the database (ext_rows) and the query (ext_cols).  `wide` sizes the three anti-diagonals for the
 // worst case instead of the X-drop band (second-tier launch).
-TALC_HDN void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen,
+TALC_HDN void xdrop_extend_scalar(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen,
                           int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide, DpStats* st) {
   ext_rows = 0;
   ext_cols = 0;
@@ -305,6 +499,165 @@ TALC_HDN void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqVi
   }
   ar.release(mk);
 }
+
+
+#if defined(__CUDA_ARCH__)
+// Device form of the same routine: the 32 lanes of the warp that owns the read each take every 32nd cell
+// of an anti-diagonal, and the three live anti-diagonals sit in shared memory while the band fits
+// (it nearly always does: with match = 0 a cell survives only within X of the main diagonal).  The
+// arithmetic, the window updates and the end-position rules are the scalar routine's, line for line.
+// Must be called by all 32 lanes with identical arguments.
+__device__ __noinline__ void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff,
+                                          u32 dlen, int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide,
+                                          DpStats* st) {
+  __shared__ i32 xdShared[TALC_WARPS_PER_BLOCK][3 * TALC_XD_CAP];
+  const u32 lane = threadIdx.x & 31;
+  const u32 warp = (threadIdx.x >> 5) % TALC_WARPS_PER_BLOCK;
+  ext_rows = 0;
+  ext_cols = 0;
+  const i64 cols = (i64)qlen + 1;
+  const i64 rows = (i64)dlen + 1;
+  if (rows == 1 || cols == 1) return;
+  const int gapCost = -1;
+  const int undefined = INT32_MIN + 1;
+  const u32 mk = ar.mark();
+  bool useShared = true;
+  i64 capW = TALC_XD_CAP;
+  i32* buf = xdShared[warp];
+  for (;;) {  // at most two rounds: shared-memory band first, full-width global arrays if the band outgrows it
+    i32* antiDiag1 = buf;
+    i32* antiDiag2 = buf + capW;
+    i32* antiDiag3 = buf + 2 * capW;
+    i64 len1 = 0, len2 = 1, len3 = 2;
+    i64 minCol = 1, maxCol = 2;
+    i64 offset1 = 0, offset2 = 0, offset3 = 0;
+    __syncwarp();
+    if (lane == 0) {
+      antiDiag2[0] = 0;
+      const int v = (-gapCost > scoreDropOff) ? undefined : gapCost;
+      antiDiag3[0] = v;
+      antiDiag3[1] = v;
+    }
+    __syncwarp();
+    i64 antiDiagNo = 1;
+    int best = 0;
+    u64 cells = 0;
+    bool outgrown = false;
+    while (minCol < maxCol) {
+      ++antiDiagNo;
+      {
+        i32* t = antiDiag1;
+        antiDiag1 = antiDiag2;
+        antiDiag2 = antiDiag3;
+        antiDiag3 = t;
+        len1 = len2;
+        len2 = len3;
+      }
+      offset1 = offset2;
+      offset2 = offset3;
+      offset3 = minCol - 1;
+      len3 = maxCol + 1 - offset3;
+      if (len3 > capW) { outgrown = true; break; }
+      if (lane == 0) {
+        const int minScore = best - scoreDropOff;
+        int e0 = undefined, e1 = undefined;
+        if ((int)antiDiagNo * gapCost > minScore) {
+          if (offset3 == 0) e0 = (int)antiDiagNo * gapCost;
+          if (antiDiagNo - maxCol == 0) e1 = (int)antiDiagNo * gapCost;
+        }
+        antiDiag3[0] = e0;
+        antiDiag3[maxCol - offset3] = e1;  // maxCol - offset3 >= 2: never the same cell as [0]
+      }
+      int antiDiagBest = (int)antiDiagNo * gapCost;
+      for (i64 col = minCol + lane; col < maxCol; col += 32) {
+        const i64 i3 = col - offset3, i2 = col - offset2, i1 = col - offset1;
+        const u32 queryPos = (u32)(col - 1);
+        const u32 dbPos = (u32)(antiDiagNo - col - 1);
+        const int d2a = antiDiag2[i2 - 1], d2b = antiDiag2[i2];
+        int tmp = (d2a > d2b ? d2a : d2b) + gapCost;
+        const int sub = antiDiag1[i1 - 1] + ((query.code(qoff + queryPos) == database.code(doff + dbPos)) ? 0 : -1);
+        tmp = tmp > sub ? tmp : sub;
+        if (tmp < best - scoreDropOff) {
+          antiDiag3[i3] = undefined;
+        } else {
+          antiDiag3[i3] = tmp;
+          antiDiagBest = antiDiagBest > tmp ? antiDiagBest : tmp;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, antiDiagBest, o);
+        antiDiagBest = antiDiagBest > other ? antiDiagBest : other;
+      }
+      __syncwarp();
+      cells += (u64)(maxCol - minCol);
+      best = best > antiDiagBest ? best : antiDiagBest;
+      while (minCol - offset3 < len3 && antiDiag3[minCol - offset3] == undefined && minCol - offset2 - 1 < len2 &&
+             antiDiag2[minCol - offset2 - 1] == undefined) {
+        ++minCol;
+      }
+      while (maxCol - offset3 > 0 && (antiDiag3[maxCol - offset3 - 1] == undefined) &&
+             (antiDiag2[maxCol - offset2 - 1] == undefined)) {
+        --maxCol;
+      }
+      ++maxCol;
+      {
+        const i64 lo = antiDiagNo + 2 - rows;
+        if (lo > minCol) minCol = lo;
+        if (cols < maxCol) maxCol = cols;
+      }
+    }
+    if (outgrown) {
+      if (!useShared) {  // even the full-width arrays were too small: cannot happen (capW = cols + 1)
+        ar.overflow = 1;
+        ar.release(mk);
+        return;
+      }
+      useShared = false;
+      capW = cols + 1;
+      buf = (i32*)ar.alloc((u32)(3 * capW * 4));
+      if (!buf) return;
+      continue;
+    }
+    if (st) st->cells_xdrop += cells;
+    i64 longestExtensionCol = len3 + offset3 - 2;
+    i64 longestExtensionRow = antiDiagNo - longestExtensionCol;
+    int longestExtensionScore = antiDiag3[longestExtensionCol - offset3];
+    if (longestExtensionScore == undefined) {
+      if (antiDiag2[len2 - 2] != undefined) {
+        longestExtensionCol = len2 + offset2 - 2;
+        longestExtensionRow = antiDiagNo - 1 - longestExtensionCol;
+        longestExtensionScore = antiDiag2[longestExtensionCol - offset2];
+      } else if (len2 > 2 && antiDiag2[len2 - 3] != undefined) {
+        longestExtensionCol = len2 + offset2 - 3;
+        longestExtensionRow = antiDiagNo - 1 - longestExtensionCol;
+        longestExtensionScore = antiDiag2[longestExtensionCol - offset2];
+      }
+    }
+    if (longestExtensionScore == undefined) {
+      for (i64 i = 0; i < len1; ++i) {
+        if (antiDiag1[i] > longestExtensionScore) {
+          longestExtensionScore = antiDiag1[i];
+          longestExtensionCol = i + offset1;
+          longestExtensionRow = antiDiagNo - 2 - longestExtensionCol;
+        }
+      }
+    }
+    if (longestExtensionScore != undefined) {
+      ext_rows = (u32)longestExtensionRow;
+      ext_cols = (u32)longestExtensionCol;
+    }
+    __syncwarp();
+    ar.release(mk);
+    return;
+  }
+}
+#else
+inline void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen,
+                         int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide, DpStats* st) {
+  xdrop_extend_scalar(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, ar, wide, st);
+}
+#endif
 
 // Trail.cpp:341-437 getSeedAndExtension in walk order.  refArg / candArg are the two arguments in the
 // reference's order; `right` is the search direction.  Extensions are returned as walk-order prefix

@@ -93,6 +93,7 @@ class Corrector {
  public:
   TableView T;
   Params P;
+  ModelTabs tabs;  // n == 0: no tables (host emulation)
   ReadView rd;
   const u32* cov;
   u32 C;  // number of k-mers
@@ -169,26 +170,30 @@ class Corrector {
     while (top > 0 && ((maxv >> (4 * top)) & 15u) == 0) --top;  // leading zero nibbles of the maximum
     u32 prefix = 0, remaining = r;
     u64 sumBelow = 0;
+    const u32 lane = lane_id(), nl = lane_count();
     for (int nib = top; nib >= 0; --nib) {  // radix select, most significant nibble first
       u32 hist[16];
       u64 hsum[16];
-#pragma unroll
       for (int i = 0; i < 16; ++i) { hist[i] = 0; hsum[i] = 0; }
       const u32 shift = 4 * nib;
       const u32 himask = (nib == 7) ? 0u : (~0u << (shift + 4));
-      for (u32 i = 0; i < C; ++i) {
+      for (u32 i = lane; i < C; i += nl) {  // each lane bins every nl-th count
         const u32 v = cov[i];
         if (v < P.min_count) continue;
         if ((v & himask) != (prefix & himask)) continue;
         const u32 d = (v >> shift) & 15u;
-        hist[d]++;
-        hsum[d] += v;
+        hist[d] += 1u;
+        hsum[d] += (u64)v;
       }
-      u32 d = 0;
-      for (; d < 15; ++d) {
-        if (hist[d] >= remaining) break;
-        remaining -= hist[d];
-        sumBelow += hsum[d];
+      u32 d = 15;
+      bool found = false;
+      for (int q = 0; q < 16; ++q) {
+        const u32 h = warp_sum(hist[q]);
+        const u64 hs = warp_sum64(hsum[q]);
+        if (!found) {
+          if (h >= remaining || q == 15) { d = (u32)q; found = true; }
+          else { remaining -= h; sumBelow += hs; }
+        }
       }
       prefix |= d << shift;
     }
@@ -198,10 +203,12 @@ class Corrector {
 
   TALC_HDN double seq_error_threshold() {
     u32 n = 0, maxv = 0;
-    for (u32 i = 0; i < C; ++i) {
+    for (u32 i = lane_id(); i < C; i += lane_count()) {
       n += (cov[i] >= P.min_count) ? 1 : 0;
       maxv = cov[i] > maxv ? cov[i] : maxv;
     }
+    n = warp_sum(n);
+    maxv = warp_max(maxv);
     u32 first, last;
     if (n > 10) {
       first = (u32)(0.15 * (double)n);
@@ -321,14 +328,21 @@ class Corrector {
 
   // ------------------------------------------------------------------ Explorer.cpp:402-411
   TALC_HDN void sort_anchors(AnchorRec* a, u32 n) {
+    if (n < 2) return;
     const int cc = (int)(noise / P.sr_error);
-    std_sort(a, a + n, [cc](const AnchorRec& l, const AnchorRec& r) {
-      int dl = cc - (int)l.count;
-      int dr = cc - (int)r.count;
-      dl = dl < 0 ? -dl : dl;
-      dr = dr < 0 ? -dr : dr;
-      return dl < dr;
-    });
+    const u32 mk = scratch.mark();
+    SortKey* keys = (SortKey*)scratch.alloc(n * sizeof(SortKey));
+    AnchorRec* tmp = (AnchorRec*)scratch.alloc(n * sizeof(AnchorRec));
+    if (!keys || !tmp) return;
+    for (u32 i = 0; i < n; ++i) {
+      int d = cc - (int)a[i].count;
+      keys[i].key = d < 0 ? -(i64)d : (i64)d;
+      keys[i].idx = i;
+      tmp[i] = a[i];
+    }
+    std_sort_keys(keys, n);
+    for (u32 i = 0; i < n; ++i) a[i] = tmp[keys[i].idx];
+    scratch.release(mk);
   }
 
   TALC_HD u64 read_kmer(u32 pos) {  // anchors sit on k-mers with count >= MIN, hence without N
@@ -483,6 +497,230 @@ class Corrector {
     return false;
   }
 
+
+  // ------------------------------------------------------------------ single-trail fast path
+  // The frontier holds one trail for ~96% of all steps (oracle counters).  While it does, and the step
+  // is an ordinary one -- exactly one admissible successor, no aim reached, no cycle, no pruning point --
+  // the step only touches registers, the table and the trail's packed sequence.  Anything else ends the
+  // run *before* the step, and the general code below redoes that step in full; the two are therefore
+  // interchangeable step by step and the result cannot depend on which one ran.
+  // border == false: oneMoreStep (Explorer.cpp:546-612); border == true: oneMoreStepInTheDark (:615-687).
+  TALC_HDN void fast_walk_scalar(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border) {
+    if (nCur != 1) return;
+    const u32 k = P.K;
+    const bool right = dirRight;
+    Trail tr = cur[0];
+    u64* w = slot_ptr(tr.slot);
+    u64 kmer = tr.kmer;
+    u32 count = tr.count;
+    double dsum = tr.dist;
+    u32 st = step;
+    u32 nSteps = 0;
+    const u32 stride = (P.cycle_mode == 0) ? k : 1u;
+    const u64 kmask = kmer_mask(k);
+    u64 rkmer = 0;  // the last k-mer with its bases in reverse order
+    for (u32 i = 0; i < k; ++i) rkmer |= ((kmer >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
+    // the word of the packed sequence that is being filled lives in a register
+    u32 cwIdx = (k + st) >> 5;
+    u64 cw = w[cwIdx];
+    while (st < pathMax) {
+      if (border && ((st + 1) % kCheckInterval == 0)) break;  // scoreEdges is due after this step
+      const u32 plen = k + st;
+      u32 cnt[4], col[4];
+      NextProbe probe;
+      table_next_issue(T, kmer, right, k, probe);          // 8 loads in flight ...
+      const StepBounds sb = step_bounds_tab(count, P, tabs);  // ... while the interval bounds are looked up
+      table_next_resolve(T, probe, cnt, col);
+      u8 tag[4];
+      const int nt = tag_next_nodes(cnt, col, sb, P, false, tag);
+      if (nt == 0) break;  // dead end
+      int child = -1, nChildren = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (tag[i] != kUnexpected) { child = i; ++nChildren; }
+      if (nChildren != 1) break;
+      const u64 ck = kmer_next(kmer, (u32)child, right, k);
+      if (!border) {
+        bool aim = false;
+        for (u32 a = 0; a < nAims; ++a) aim |= (aims[a].kmer == ck);
+        if (aim) break;
+      }
+      // cycle test against the parent's sequence (plen bases), current word taken from the register
+      if (plen > k) {
+        bool hit = false, cyc = false;
+        // LEFT walks compare in walk order, i.e. against the reversed k-mer, which is maintained incrementally
+        const u64 needle = right ? ck : (((rkmer << 2) | (u64)child) & kmask);
+        for (u32 p = 0; p + k <= plen && !hit; p += stride) {
+          const u32 wi0 = right ? p : (plen - k - p);
+          const u32 wi = wi0 >> 5, off = 2 * (wi0 & 31);
+          const u64 a0 = (wi == cwIdx) ? cw : w[wi];
+          u64 hi = a0 << off;
+          if (off && (off + 2 * k > 64)) {
+            const u64 a1 = (wi + 1 == cwIdx) ? cw : w[wi + 1];
+            hi |= a1 >> (64 - off);
+          }
+          if ((hi >> (64 - 2 * k)) == needle) { hit = true; cyc = p > 0; }
+        }
+        if (cyc) break;
+      }
+      // commit the step
+      {
+        const u32 idx = plen >> 5;
+        if (idx != cwIdx) { w[cwIdx] = cw; cwIdx = idx; cw = w[idx]; }
+        const u32 sh = 62 - 2 * (plen & 31);
+        cw = (cw & ~(3ull << sh)) | ((u64)child << sh);
+        w[cwIdx] = cw;
+      }
+      dsum = dsum + step_dist(count, cnt[child], sb);
+      if (!right) rkmer = ((rkmer << 2) | (u64)child) & kmask;  // reverse(b + x[..K-2]) = reverse(x)[1..] + b
+      kmer = ck;
+      count = cnt[child];
+      ++st;
+      ++nSteps;
+    }
+    if (nSteps) {
+      w[cwIdx] = cw;
+      tr.kmer = kmer;
+      tr.count = count;
+      tr.dist = dsum;
+      cur[0] = tr;
+      step = st;
+      if (ctr) {
+        if (border) ctr->steps_border += nSteps;
+        else ctr->steps_inner += nSteps;
+        ctr->frontier_sum += nSteps;
+        ctr->lookups_walk += 4ull * nSteps;
+      }
+    }
+  }
+
+
+#if defined(__CUDA_ARCH__)
+  // The same fast path with the warp's lanes put to work: lanes 0-3 probe the four successors (A,C,G,T) side
+  // by side and a ballot picks the branch; one lane per aim k-mer and one lane per cycle-test window.
+  // When exactly one successor reaches MIN_COUNT it is EXPECTED by the `counter == 1` rule of tagNextNodes
+  // (Explorer.cpp:1251) and no interval bound is needed; otherwise the scalar tagger decides.
+  __device__ __noinline__ void fast_walk(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border) {
+    if (nCur != 1) return;
+    if (nAims > 32) { fast_walk_scalar(step, pathMax, aims, nAims, border); return; }
+    const u32 lane = threadIdx.x & 31u;
+    const u32 k = P.K;
+    const bool right = dirRight;
+    const TableView tv = T;
+    const Params prm = P;
+    const ModelTabs mt = tabs;
+    Trail tr = cur[0];
+    u64* w = slot_ptr(tr.slot);
+    u64 kmer = tr.kmer;
+    u32 count = tr.count;
+    double dsum = tr.dist;
+    u32 st = step;
+    u32 nSteps = 0;
+    const u32 stride = (prm.cycle_mode == 0) ? k : 1u;
+    const u64 kmask = kmer_mask(k);
+    u64 rkmer = 0;
+    for (u32 i = 0; i < k; ++i) rkmer |= ((kmer >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
+    const u64 myAim = (!border && lane < nAims) ? aims[lane].kmer : ~0ull;  // ~0 is not a k-mer (<= 60 bits)
+    u32 cwIdx = (k + st) >> 5;
+    u64 cw = w[cwIdx];
+    const u32 b = lane & 3u;
+#pragma unroll 1
+    while (st < pathMax) {
+      if (border && ((st + 1) % kCheckInterval == 0)) break;
+      const u32 plen = k + st;
+      // ---- the four successors, one per lane (lanes 4..31 mirror lanes 0..3)
+      const u64 key = kmer_next(kmer, b, right, k);
+      const u64 bucket = hash_kmer(key) & tv.mask & ~1ull;
+      const Slot s0 = load_slot(tv.slots + bucket);
+      const Slot s1 = load_slot(tv.slots + bucket + 1);
+      u32 cnt, col;
+      if (sector_resolve(s0, s1, key, cnt, col) < 0) table_probe_from(tv, bucket, key, cnt, col);
+      const u32 m = __ballot_sync(0xffffffffu, cnt >= prm.min_count) & 0xFu;
+      if (m == 0) break;  // dead end
+      int child;
+      if ((m & (m - 1)) == 0) {
+        child = __ffs((int)m) - 1;
+      } else {
+        u32 cnt4[4], col4[4];
+        for (int i = 0; i < 4; ++i) {
+          cnt4[i] = __shfl_sync(0xffffffffu, cnt, i);
+          col4[i] = __shfl_sync(0xffffffffu, col, i);
+        }
+        const StepBounds sb = step_bounds_tab(count, prm, mt);
+        u8 tag[4];
+        tag_next_nodes(cnt4, col4, sb, prm, false, tag);
+        int nChildren = 0;
+        child = -1;
+        for (int i = 0; i < 4; ++i)
+          if (tag[i] != kUnexpected) { child = i; ++nChildren; }
+        if (nChildren != 1) break;
+      }
+      const u32 childCnt = __shfl_sync(0xffffffffu, cnt, child);
+      const u64 ck = kmer_next(kmer, (u32)child, right, k);
+      if (__ballot_sync(0xffffffffu, myAim == ck)) break;  // aim reached: the general step records the bridge
+      // ---- cycle test, one window per lane
+      if (plen > k) {
+        const u64 needle = right ? ck : (((rkmer << 2) | (u64)child) & kmask);
+        bool cyc = false;
+        for (u32 base = 0; (u64)base * stride + k <= plen; base += 32) {
+          const u32 p = (base + lane) * stride;
+          bool match = false;
+          if (p + k <= plen) {
+            const u32 wi0 = right ? p : (plen - k - p);
+            const u32 wi = wi0 >> 5, off = 2 * (wi0 & 31);
+            const u64 a0 = (wi == cwIdx) ? cw : w[wi];
+            u64 hi = a0 << off;
+            if (off && (off + 2 * k > 64)) {
+              const u64 a1 = (wi + 1 == cwIdx) ? cw : w[wi + 1];
+              hi |= a1 >> (64 - off);
+            }
+            match = (hi >> (64 - 2 * k)) == needle;
+          }
+          const u32 mm = __ballot_sync(0xffffffffu, match);
+          if (mm) {  // first occurrence = lowest lane of the first batch that matches
+            cyc = ((base + (u32)__ffs((int)mm) - 1) * stride) > 0;
+            break;
+          }
+        }
+        if (cyc) break;
+      }
+      // ---- commit the step
+      {
+        const u32 idx = plen >> 5;
+        if (idx != cwIdx) { cwIdx = idx; cw = 0; }
+        const u32 sh = 62 - 2 * (plen & 31);
+        cw = (cw & ~(3ull << sh)) | ((u64)child << sh);
+        w[cwIdx] = cw;  // every lane stores the same word: each later reads back its own store
+      }
+      const double sq = (count < mt.n) ? mt.sq[count] : sqrt((double)count);
+      dsum = dsum + fabs((double)count - (double)childCnt) / sq;
+      if (!right) rkmer = ((rkmer << 2) | (u64)child) & kmask;
+      kmer = ck;
+      count = childCnt;
+      ++st;
+      ++nSteps;
+    }
+    __syncwarp();
+    if (nSteps) {
+      tr.kmer = kmer;
+      tr.count = count;
+      tr.dist = dsum;
+      cur[0] = tr;
+      step = st;
+      if (ctr) {
+        if (border) ctr->steps_border += nSteps;
+        else ctr->steps_inner += nSteps;
+        ctr->frontier_sum += nSteps;
+        ctr->lookups_walk += 4ull * nSteps;
+      }
+    }
+  }
+#else
+  inline void fast_walk(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border) {
+    fast_walk_scalar(step, pathMax, aims, nAims, border);
+  }
+#endif
+
   // ------------------------------------------------------------------ gardening, Explorer.cpp:773-865
   // kept[] receives indices into nxt (duplicates possible, Q16); returns isComplex
   TALC_HDN bool gardening(u32* kept, u32& nKept) {
@@ -491,34 +729,39 @@ class Corrector {
     const u32 MAXP = P.max_branches;
     nKept = 0;
     const u32 mk = scratch.mark();
-    GardenKey* t1 = (GardenKey*)scratch.alloc(n * sizeof(GardenKey));
+    SortKey* sk = (SortKey*)scratch.alloc((n + 1) * sizeof(SortKey));
     GardenRank* rankings = (GardenRank*)scratch.alloc(n * sizeof(GardenRank));
     GardenRank* newr = (GardenRank*)scratch.alloc((n + 1) * sizeof(GardenRank));
-    if (!t1 || !rankings || !newr) return false;
+    GardenRank* tmpr = (GardenRank*)scratch.alloc((n + 1) * sizeof(GardenRank));
+    if (!sk || !rankings || !newr || !tmpr) return false;
     u32 nNew = 0;
     bool isComplex = false;
     u32 nb = n < MAXP ? n : MAXP;
     for (u32 t = 0; t < n; ++t) {
       rankings[t].idx = t; rankings[t].r1 = 0; rankings[t].r2 = 0; rankings[t].sum = 0;
-      t1[t].idx = t; t1[t].score = nxt[t].score; t1[t].dist = nxt[t].dist;
+      sk[t].key = -(i64)nxt[t].score;  // sortByScore: descending score
+      sk[t].idx = t;
     }
-    std_sort(t1, t1 + n, [](const GardenKey& l, const GardenKey& r) { return l.score > r.score; });
+    std_sort_keys(sk, n);
     {
       u32 rk = 0;
-      rankings[t1[0].idx].r1 = 0;
+      rankings[sk[0].idx].r1 = 0;
       for (u32 t = 1; t < n; ++t) {
-        if (!(t1[t].score == t1[t - 1].score)) rk++;
-        rankings[t1[t].idx].r1 = rk;
+        if (!(sk[t].key == sk[t - 1].key)) rk++;
+        rankings[sk[t].idx].r1 = rk;
       }
     }
-    for (u32 t = 0; t < n; ++t) { t1[t].idx = t; t1[t].score = nxt[t].score; t1[t].dist = nxt[t].dist; }
-    std_sort(t1, t1 + n, [](const GardenKey& l, const GardenKey& r) { return l.dist < r.dist; });
+    for (u32 t = 0; t < n; ++t) {
+      sk[t].key = sort_key_of_nonneg_double(nxt[t].dist);  // sortByLikelihood: ascending distance
+      sk[t].idx = t;
+    }
+    std_sort_keys(sk, n);
     {
       u32 rk = 0;
-      rankings[t1[0].idx].r2 = 0;
+      rankings[sk[0].idx].r2 = 0;
       for (u32 t = 1; t < n; ++t) {
-        if (!(t1[t].dist == t1[t - 1].dist)) rk++;
-        rankings[t1[t].idx].r2 = rk;
+        if (!(sk[t].key == sk[t - 1].key)) rk++;
+        rankings[sk[t].idx].r2 = rk;
       }
     }
     for (u32 t = 0; t < n; ++t) {
@@ -526,7 +769,9 @@ class Corrector {
       if ((rankings[t].sum == 0) || (n <= MAXP)) newr[nNew++] = rankings[t];
     }
     if (nNew == 0) {
-      std_sort(rankings, rankings + n, [](const GardenRank& l, const GardenRank& r) { return l.r1 < r.r1; });
+      for (u32 t = 0; t < n; ++t) { sk[t].key = (i64)rankings[t].r1; sk[t].idx = t; tmpr[t] = rankings[t]; }
+      std_sort_keys(sk, n);  // sortByMaxScore
+      for (u32 t = 0; t < n; ++t) rankings[t] = tmpr[sk[t].idx];
       u32 s = 0;
       bool ties = false;
       do {
@@ -547,7 +792,9 @@ class Corrector {
         }
         if ((nNew > MAXP) & (newr[0].r1 == atMax.r1)) {  // Q16
           isComplex = true;
-          std_sort(newr, newr + nNew, [](const GardenRank& l, const GardenRank& r) { return l.r2 < r.r2; });
+          for (u32 t = 0; t < nNew; ++t) { sk[t].key = (i64)newr[t].r2; sk[t].idx = t; tmpr[t] = newr[t]; }
+          std_sort_keys(sk, nNew);  // sortByMinDist
+          for (u32 t = 0; t < nNew; ++t) newr[t] = tmpr[sk[t].idx];
           for (u32 t = 0; t < MAXP; ++t) kept[nKept++] = newr[t].idx;
         }
       }
@@ -633,8 +880,8 @@ class Corrector {
       if (!setup_search(pathMax)) return false;
       if (!push_root(anchors[s])) return false;
       // bridges: metadata for all, sequences only for running-best record setters
-      const u32 maxBridges = wide ? 4096u : 96u;
-      const u32 maxKeep = wide ? 64u : 6u;
+      const u32 maxBridges = wide ? 1024u : 96u;
+      const u32 maxKeep = wide ? 32u : 6u;
       BridgeRec* br = (BridgeRec*)scratch.alloc(maxBridges * sizeof(BridgeRec));
       u64* brSeq = (u64*)scratch.alloc(maxKeep * slotWords * 8);
       if (!br || !brSeq) return false;
@@ -646,6 +893,8 @@ class Corrector {
       u32 step = 0;
       const SeqView refv = view_of(ref);
       while ((nCur > 0) & (nCur <= kMaxInnerPaths) & (step < pathMax)) {
+        fast_walk(step, pathMax, aims, nAims, false);
+        if (!(step < pathMax)) break;
         // ---- oneMoreStep, Explorer.cpp:546-612
         const u32 plen = k + step;  // every trail of the frontier has this length
         if (ctr) { ctr->steps_inner++; ctr->frontier_sum += nCur; }
@@ -657,8 +906,8 @@ class Corrector {
           table_next_counts(T, par.kmer, dirRight, k, cnt, col);
           if (ctr) ctr->lookups_walk += 4;
           u8 tag[4];
-          double dist[4];
-          const int nt = tag_next_nodes(cnt, col, par.count, P, complex_, tag, dist);
+          const StepBounds sb = step_bounds(par.count, P);
+          const int nt = tag_next_nodes(cnt, col, sb, P, complex_, tag);
           u32 nChildren = 0;
           for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
           bool parentSlotTaken = false;
@@ -669,7 +918,7 @@ class Corrector {
             ch.count = cnt[i];
             ch.score = par.score;
             ch.failures = par.failures;
-            ch.dist = par.dist + dist[i];
+            ch.dist = par.dist + step_dist(par.count, cnt[i], sb);
             ch.pad = 0;
             // sequence: a single child extends the parent's slot in place, siblings copy it
             if (nChildren == 1) {
@@ -972,6 +1221,8 @@ class Corrector {
       if (!push_root(anchors[s])) return false;
       u32 step = 0;
       while ((nCur > 0) & (nCur <= kMaxInnerPaths) & (step < pathMax)) {
+        fast_walk(step, pathMax, nullptr, 0, true);
+        if (!(step < pathMax)) break;
         // ---- oneMoreStepInTheDark, Explorer.cpp:615-687
         const u32 plen = k + step;
         if (ctr) { ctr->steps_border++; ctr->frontier_sum += nCur; }
@@ -983,8 +1234,8 @@ class Corrector {
           table_next_counts(T, par.kmer, dirRight, k, cnt, col);
           if (ctr) ctr->lookups_walk += 4;
           u8 tag[4];
-          double dist[4];
-          const int nt = tag_next_nodes(cnt, col, par.count, P, complex_, tag, dist);
+          const StepBounds sb = step_bounds(par.count, P);
+          const int nt = tag_next_nodes(cnt, col, sb, P, complex_, tag);
           u32 nChildren = 0;
           for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
           bool parentSlotTaken = false;
@@ -995,7 +1246,7 @@ class Corrector {
             ch.count = cnt[i];
             ch.score = par.score;
             ch.failures = par.failures;
-            ch.dist = par.dist + dist[i];
+            ch.dist = par.dist + step_dist(par.count, cnt[i], sb);
             ch.pad = 0;
             if (nChildren == 1) {
               ch.slot = par.slot;
@@ -1098,7 +1349,8 @@ class Corrector {
     scratch.init(job.arena + (keepBytes & ~7u), job.arena_bytes - (keepBytes & ~7u));
     // Read::reCoverage gate (Read.cpp:190, Q1: strictly greater)
     u32 nbIn = 0;
-    for (u32 i = 0; i < C; ++i) nbIn += (cov[i] > P.min_count) ? 1 : 0;
+    for (u32 i = lane_id(); i < C; i += lane_count()) nbIn += (cov[i] > P.min_count) ? 1 : 0;
+    nbIn = warp_sum(nbIn);
     if (nbIn == 0) return kReadNoSolid;
     // Read::defineStructure2 (Read.cpp:260-276)
     bool checok = find_in_regions();
@@ -1197,21 +1449,37 @@ class Corrector {
     const u32 a = regs[i].end + P.K, b = regs[i + 1].start;
     return b > a ? b - a : 0;
   }
-  // write the corrected read as upper-case ASCII
-  TALC_HDN void emit(u8* out) const {
+  // write the corrected read as upper-case ASCII; the `nl` cooperating lanes each write every nl-th byte
+  TALC_HDN void emit(u8* out, u32 lane, u32 nl) const {
     const u32 k = P.K;
     u32 o = 0;
-    if (headPiece.len >= 0) { for (i32 i = 0; i < headPiece.len; ++i) out[o++] = keep.base[headPiece.off + i]; }
-    else if (headPresent) { for (u32 i = 0; i < headRaw; ++i) out[o++] = code_char(rd.code(i)); }
+    if (headPiece.len >= 0) {
+      for (u32 i = lane; i < (u32)headPiece.len; i += nl) out[o + i] = keep.base[headPiece.off + i];
+      o += (u32)headPiece.len;
+    } else if (headPresent) {
+      for (u32 i = lane; i < headRaw; i += nl) out[o + i] = code_char(rd.code(i));
+      o += headRaw;
+    }
     for (u32 r = 0; r < nregs; ++r) {
-      for (u32 i = regs[r].start; i < regs[r].end + k; ++i) out[o++] = code_char(rd.code(i));
+      const u32 a = regs[r].start, n = regs[r].end + k - regs[r].start;
+      for (u32 i = lane; i < n; i += nl) out[o + i] = code_char(rd.code(a + i));
+      o += n;
       if (r + 1 < nregs) {
-        if (gapPiece[r].len >= 0) { for (i32 i = 0; i < gapPiece[r].len; ++i) out[o++] = keep.base[gapPiece[r].off + i]; }
-        else { for (u32 i = regs[r].end + k; i < regs[r + 1].start; ++i) out[o++] = code_char(rd.code(i)); }
+        if (gapPiece[r].len >= 0) {
+          for (u32 i = lane; i < (u32)gapPiece[r].len; i += nl) out[o + i] = keep.base[gapPiece[r].off + i];
+          o += (u32)gapPiece[r].len;
+        } else {
+          const u32 g0 = regs[r].end + k, gn = gapRawLen(r);
+          for (u32 i = lane; i < gn; i += nl) out[o + i] = code_char(rd.code(g0 + i));
+          o += gn;
+        }
       }
     }
-    if (tailPiece.len >= 0) { for (i32 i = 0; i < tailPiece.len; ++i) out[o++] = keep.base[tailPiece.off + i]; }
-    else if (tailPresent) { for (u32 i = rd.len - tailRaw; i < rd.len; ++i) out[o++] = code_char(rd.code(i)); }
+    if (tailPiece.len >= 0) {
+      for (u32 i = lane; i < (u32)tailPiece.len; i += nl) out[o + i] = keep.base[tailPiece.off + i];
+    } else if (tailPresent) {
+      for (u32 i = lane; i < tailRaw; i += nl) out[o + i] = code_char(rd.code(rd.len - tailRaw + i));
+    }
   }
 };
 

@@ -18,6 +18,11 @@
 #define TALC_HDN inline
 #endif
 
+// launch shape of the correction kernel: 4 warps (= 4 reads in flight) per 128-thread block; per-warp
+// shared-memory staging for the X-drop anti-diagonals
+#define TALC_WARPS_PER_BLOCK 4
+#define TALC_XD_CAP 192
+
 namespace talc {
 
 typedef uint8_t u8;
@@ -63,16 +68,34 @@ enum ReadStatus : u8 {
   kReadOverflow = 250    // internal: scratch arena too small, re-run with a larger arena
 };
 
-// Dna5 code of an input character (SeqAn char -> Dna5): ACGT either case, U -> T, else N(4)
+// Dna5 code of an input character (SeqAn char -> Dna5): ACGT either case, U -> T, else N(4).
+// Branch-free: bits 1-2 of the ASCII code separate A,C,G,T/U; five compares validate the letter.
 TALC_HD u32 base_code(u8 c) {
-  switch (c) {
-    case 'A': case 'a': return 0;
-    case 'C': case 'c': return 1;
-    case 'G': case 'g': return 2;
-    case 'T': case 't': case 'U': case 'u': return 3;
-    default: return 4;
-  }
+  const u32 idx = ((u32)c | 0x20u) - 0x61u;  // a..u -> 0..20
+  const u32 x = (((u32)c >> 1) & 3u) ^ (((u32)c >> 2) & 1u);
+  const bool ok = (idx < 21u) & (((0x180045u >> (idx & 31u)) & 1u) != 0u);  // bit set for a, c, g, t, u
+  return ok ? x : 4u;
 }
+
+// The 32 lanes of the warp that owns a read cooperate on the linear scans; on the host (tests/hostemu)
+// a "warp" is one lane and the reductions are identities.
+#if defined(__CUDA_ARCH__)
+TALC_HD u32 lane_id() { return threadIdx.x & 31u; }
+TALC_HD u32 lane_count() { return 32u; }
+TALC_HD u32 warp_sum(u32 v) { return __reduce_add_sync(0xffffffffu, v); }
+TALC_HD u32 warp_max(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
+TALC_HD u64 warp_sum64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#else
+inline u32 lane_id() { return 0; }
+inline u32 lane_count() { return 1; }
+inline u32 warp_sum(u32 v) { return v; }
+inline u32 warp_max(u32 v) { return v; }
+inline u64 warp_sum64(u64 v) { return v; }
+#endif
 TALC_HD u8 code_char(u32 code) { return (u8)("ACGTN"[code]); }
 
 TALC_HD u64 kmer_mask(u32 K) { return (K >= 32) ? ~0ull : ((1ull << (2 * K)) - 1ull); }

@@ -117,14 +117,14 @@ TALC_HD void insertion_sort(T* first, T* last, Less less) {
 }  // namespace stdsort_detail
 
 template <class T, class Less>
-TALC_HDN void std_sort(T* first, T* last, Less less) {
+TALC_HD void std_sort(T* first, T* last, Less less) {
   using namespace stdsort_detail;
   if (first == last) return;
   const i64 n = last - first;
   // __introsort_loop with the recursion unrolled onto an explicit stack; the two halves are
   // disjoint, so the order in which they are processed does not change the result
   struct Frame { T* first; T* last; int depth; };
-  Frame stack[64];
+  Frame stack[40];  // depth limit 2*floor(lg n) <= 38 for any n < 2^19
   int sp = 0;
   int lg = 0;
   for (i64 v = n; v > 1; v >>= 1) ++lg;  // std::__lg
@@ -150,6 +150,24 @@ TALC_HDN void std_sort(T* first, T* last, Less less) {
     for (T* i = first + 16; i != last; ++i) unguarded_linear_insert(i, less);
   } else
     insertion_sort(first, last, less);
+}
+
+// The only instantiation the device code uses: every comparator of the reference is `key(l) < key(r)` on a
+// scalar key, so all sorts run through one routine on (key, original index) pairs -- the permutation only
+// depends on the comparator outcomes -- and the callers then gather their records by `idx`.
+struct SortKey {
+  i64 key;
+  u32 idx;
+};
+struct SortKeyLess {
+  TALC_HD bool operator()(const SortKey& a, const SortKey& b) const { return a.key < b.key; }
+};
+TALC_HDN void std_sort_keys(SortKey* first, u32 n) { std_sort(first, first + n, SortKeyLess()); }
+// non-negative doubles order like their bit patterns
+TALC_HD i64 sort_key_of_nonneg_double(double d) {
+  i64 k;
+  memcpy(&k, &d, sizeof k);
+  return k;
 }
 
 }  // namespace talc

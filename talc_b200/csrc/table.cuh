@@ -79,7 +79,7 @@ TALC_HD bool table_lookup(const TableView& t, u64 key, u32& count, u32& colour) 
 
 // the four successor counts in A,C,G,T order (Jellyfish.cpp:308-321): the four home sectors are
 // fetched together (8 independent 16-byte loads in flight), stragglers continue probing one by one
-TALC_HD void table_next_counts(const TableView& t, u64 kmer, bool right, u32 K, u32 cnt[4], u32 col[4]) {
+TALC_HDN void table_next_counts(const TableView& t, u64 kmer, bool right, u32 K, u32 cnt[4], u32 col[4]) {
   u64 key[4], b[4];
   Slot s0[4], s1[4];
 #pragma unroll
@@ -99,8 +99,33 @@ TALC_HD void table_next_counts(const TableView& t, u64 kmer, bool right, u32 K, 
   }
 }
 
+// the same in two halves, so that a caller can do arithmetic while the eight loads are in flight
+struct NextProbe {
+  u64 key[4], b[4];
+  Slot s0[4], s1[4];
+};
+TALC_HD void table_next_issue(const TableView& t, u64 kmer, bool right, u32 K, NextProbe& q) {
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    q.key[i] = kmer_next(kmer, i, right, K);
+    q.b[i] = hash_kmer(q.key[i]) & t.mask & ~1ull;
+  }
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    q.s0[i] = load_slot(t.slots + q.b[i]);
+    q.s1[i] = load_slot(t.slots + q.b[i] + 1);
+  }
+}
+TALC_HD void table_next_resolve(const TableView& t, const NextProbe& q, u32 cnt[4], u32 col[4]) {
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    const int r = sector_resolve(q.s0[i], q.s1[i], q.key[i], cnt[i], col[i]);
+    if (r < 0) table_probe_from(t, q.b[i], q.key[i], cnt[i], col[i]);
+  }
+}
+
 // Jellyfish.cpp:383-393
-TALC_HD int table_out_degree(const TableView& t, u64 kmer, bool right, u32 K, u32 min_count) {
+TALC_HDN int table_out_degree(const TableView& t, u64 kmer, bool right, u32 K, u32 min_count) {
   u32 cnt[4], col[4];
   table_next_counts(t, kmer, right, K, cnt, col);
   int d = 0;

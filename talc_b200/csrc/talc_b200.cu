@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(256) coverage_kernel(TableView tv, u32 K, cons
 struct CorrectArgs {
   TableView tv;
   Params P;
+  ModelTabs tabs;
   const u8* bases;
   const u64* offs;
   const u64* kmerOff;
@@ -204,51 +205,72 @@ struct CorrectArgs {
   u32* overflowList;
   u32* nOverflow;
   u32* outFull;
+  u32* readKcycles;  // optional: per-read elapsed SM cycles / 1024 (tuning aid)
 };
 
+// One warp owns one read.  All 32 lanes run the per-read control flow on the same data, so the warp
+// never diverges (a thread-per-read mapping serialises: the threads of a warp drift onto different code
+// paths and each one then pays its own chain of HBM latencies alone).  Lanes share the warp's scratch
+// slice; identical stores to identical addresses are benign; side effects on global state are lane 0's.
+#ifndef TALC_MIN_BLOCKS
+#define TALC_MIN_BLOCKS 4
+#endif
 template <bool WIDE>
-__global__ void __launch_bounds__(128) correct_kernel(CorrectArgs A) {
+__global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) correct_kernel(CorrectArgs A) {
+  // One copy of the per-read state per warp, in shared memory: with 32 lanes holding identical state, keeping
+  // it in (per-lane) local memory multiplies its cache footprint by 32 and the L1 thrashes.
+  __shared__ Corrector cxs[TALC_WARPS_PER_BLOCK];
+  __shared__ Counters mines[TALC_WARPS_PER_BLOCK];
   const u32 lane = threadIdx.x & 31;
-  const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  u8* myArena = A.arenas + gtid * (u64)A.arenaBytes;
-  Counters mine;
+  const u32 wib = (threadIdx.x >> 5) % TALC_WARPS_PER_BLOCK;
+  Corrector& cx = cxs[wib];
+  Counters& mine = mines[wib];
+  const u64 gwarp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  u8* myArena = A.arenas + gwarp * (u64)A.arenaBytes;
   for (;;) {
-    u32 base = 0;
-    if (lane == 0) base = atomicAdd(A.workCounter, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= A.nOrder) break;
-    const u32 qi = base + lane;
-    if (qi < A.nOrder) {
-      const u32 r = A.order[qi];
-      Corrector cx;
-      cx.T = A.tv;
-      cx.P = A.P;
-#pragma unroll
-      for (int i = 0; i < kNumCounters; ++i) ((u64*)&mine)[i] = 0;
-      cx.ctr = &mine;
-      ReadJob job;
-      job.rd.s = A.bases + A.offs[r];
-      job.rd.len = (u32)(A.offs[r + 1] - A.offs[r]);
-      job.cov = A.cov + A.kmerOff[r];
-      job.arena = myArena;
-      job.arena_bytes = A.arenaBytes;
-      job.wide = WIDE;
-      const u8 st = cx.run(job);
-      if (st == kReadOverflow) {
+    u32 qi = 0;
+    if (lane == 0) qi = atomicAdd(A.workCounter, 1u);
+    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if (qi >= A.nOrder) break;
+    const u32 r = A.order[qi];
+    __syncwarp();
+    cx.T = A.tv;
+    cx.P = A.P;
+    cx.tabs = A.tabs;
+    for (int i = 0; i < kNumCounters; ++i) ((u64*)&mine)[i] = 0;
+    cx.ctr = &mine;
+    ReadJob job;
+    job.rd.s = A.bases + A.offs[r];
+    job.rd.len = (u32)(A.offs[r + 1] - A.offs[r]);
+    job.cov = A.cov + A.kmerOff[r];
+    job.arena = myArena;
+    job.arena_bytes = A.arenaBytes;
+    job.wide = WIDE;
+    __syncwarp();
+    const long long t0 = clock64();
+    const u8 st = cx.run(job);
+    __syncwarp();
+    if (A.readKcycles && lane == 0) A.readKcycles[r] = (u32)((clock64() - t0) >> 10);
+    if (st == kReadOverflow) {
+      if (lane == 0) {
         A.status[r] = st;
         const u32 slot = atomicAdd(A.nOverflow, 1u);
         A.overflowList[slot] = r;
-      } else {
-        const u32 olen = (st == kReadOk) ? cx.corrected_length() : job.rd.len;
-        const unsigned long long pos = atomicAdd(A.outCursor, (unsigned long long)olen);
-        if (pos + olen <= A.outCap) {
-          u8* dst = A.outArena + pos;
-          if (st == kReadOk) cx.emit(dst);
-          else
-            for (u32 i = 0; i < job.rd.len; ++i) dst[i] = code_char(job.rd.code(i));
-        } else {
-          atomicExch(A.outFull, 1u);
-        }
+      }
+    } else {
+      const u32 olen = (st == kReadOk) ? cx.corrected_length() : job.rd.len;
+      unsigned long long pos = 0;
+      if (lane == 0) pos = atomicAdd(A.outCursor, (unsigned long long)olen);
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (pos + olen <= A.outCap) {
+        u8* dst = A.outArena + pos;
+        if (st == kReadOk) cx.emit(dst, lane, 32);
+        else
+          for (u32 i = lane; i < job.rd.len; i += 32) dst[i] = code_char(job.rd.code(i));
+      } else if (lane == 0) {
+        atomicExch(A.outFull, 1u);
+      }
+      if (lane == 0) {
         A.outPos[r] = pos;
         A.outLen[r] = olen;
         A.status[r] = st;
@@ -264,6 +286,7 @@ __global__ void __launch_bounds__(128) correct_kernel(CorrectArgs A) {
         }
       }
     }
+    __syncwarp();
   }
 }
 
@@ -284,12 +307,22 @@ __global__ void len_to_u64_kernel(const u32* len, u32 n, u64* out) {
   if (i < n) out[i] = len[i];
 }
 
+__global__ void model_tabs_kernel(double alpha, u32 n, double* lower, double* upper, double* sq) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  lower[i] = model_lower_bound(i, alpha);
+  upper[i] = model_upper_bound(i, alpha);
+  sq[i] = sqrt((double)i);
+}
+
 // =====================================================================================
 // device self-tests of the primitives
 // =====================================================================================
 __global__ void test_align_kernel(int op, const u8* a, const u64* aoff, const u8* b, const u64* boff, u32 n, int aux,
                                   int aux2, u32 K, u8* arenas, u32 arenaBytes, i32* result) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per pair, all lanes with identical data (the scoring routines are warp-cooperative)
+  const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
   if (i >= n) return;
   Arena ar;
   ar.init(arenas + (u64)i * arenaBytes, arenaBytes);
@@ -305,22 +338,34 @@ __global__ void test_align_kernel(int op, const u8* a, const u64* aoff, const u8
     for (u32 j = 0; j < vb.len; ++j) path_set(packed, j, vb.code(j));
     vb = view_of_path(packed, vb.len);
   }
-  if (op == 0) result[i] = -nw_distance(va, va.len, vb, vb.len, ar, nullptr);
-  else if (op == 1) result[i] = lcs_length(va, va.len, vb, vb.len, ar, nullptr);
-  else if (op == 2) result[i] = overlap_score(va, va.len, vb, vb.len, ar, nullptr);
+  i32 r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  if (op == 0) r0 = -nw_distance(va, va.len, vb, vb.len, ar, nullptr);
+  else if (op == 1) r0 = lcs_length(va, va.len, vb, vb.len, ar, nullptr);
+  else if (op == 2) r0 = overlap_score(va, va.len, vb, vb.len, ar, nullptr);
   else {
     const SeedExt e = seed_and_extension(va, vb, aux, aux2 != 0, K, ar, true, nullptr);
-    result[4 * i + 0] = (i32)e.ref_ext;
-    result[4 * i + 1] = (i32)e.cand_ext;
-    result[4 * i + 2] = e.score;
-    result[4 * i + 3] = e.stop ? 1 : 0;
+    r0 = (i32)e.ref_ext;
+    r1 = (i32)e.cand_ext;
+    r2 = e.score;
+    r3 = e.stop ? 1 : 0;
   }
-  if (ar.overflow) result[(op == 3) ? 4 * i : i] = INT32_MIN;
+  if (ar.overflow) r0 = INT32_MIN;
+  if (lane == 0) {
+    if (op == 3) {
+      result[4 * i + 0] = r0;
+      result[4 * i + 1] = r1;
+      result[4 * i + 2] = r2;
+      result[4 * i + 3] = r3;
+    } else
+      result[i] = r0;
+  }
 }
-__global__ void test_sort_kernel(const i64* keys, u32 n, u32* perm) {
+__global__ void test_sort_kernel(const i64* keys, u32 n, u32* perm, void* scratchKeys) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  for (u32 i = 0; i < n; ++i) perm[i] = i;
-  std_sort(perm, perm + n, [keys](const u32& x, const u32& y) { return keys[x] < keys[y]; });
+  SortKey* sk = (SortKey*)scratchKeys;
+  for (u32 i = 0; i < n; ++i) { sk[i].key = keys[i]; sk[i].idx = i; }
+  std_sort_keys(sk, n);
+  for (u32 i = 0; i < n; ++i) perm[i] = sk[i].idx;
 }
 
 // =====================================================================================
@@ -361,14 +406,17 @@ struct talc_ctx {
   bool tableOwned = true;
   bool tableReady = false;
   // scratch sizing
-  u32 tier1Bytes = 48 * 1024;
-  u32 tier2Bytes = 6u << 20;
-  u32 tier2Threads = 2048;
+  u32 tier1Bytes = 1u << 20;    // per warp (= per read in flight)
+  u32 tier2Bytes = 64u << 20;
+  u32 tier2Warps = 128;
+  u32 blocksPerSm = TALC_MIN_BLOCKS;
+  double* modelTabs = nullptr;  // 3 x kModelTabN doubles
   // cached device buffers
   DevBuf bases, offs, kmerOff, nk, cov, order, sortKey, sortKeyOut, sortVal, cubTmp, arenas, outArena, outPos, outLen,
       outLen64, status, outOffs, out, misc, overflowList;
 };
 
+static const u32 kModelTabN = 16384;
 static thread_local std::string g_createError;
 
 #define CUDA_TRY(ctx, call)                                                                             \
@@ -446,6 +494,15 @@ int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out) {
     return TALC_ERR_CUDA;
   }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&c->ev[i]);
+  if (cudaMalloc((void**)&c->modelTabs, (size_t)3 * kModelTabN * sizeof(double)) != cudaSuccess) {
+    g_createError = "cudaMalloc(model tables) failed";
+    delete c;
+    return TALC_ERR_CUDA;
+  }
+  model_tabs_kernel<<<(kModelTabN + 255) / 256, 256, 0, c->stream>>>(p->alpha, kModelTabN, c->modelTabs, c->modelTabs + kModelTabN,
+                                                                  c->modelTabs + 2 * kModelTabN);
+  cudaStreamSynchronize(c->stream);
+  if (const char* e2 = getenv("TALC_BLOCKS_PER_SM")) c->blocksPerSm = (u32)std::max(1, atoi(e2));
   *out = c;
   return TALC_OK;
 }
@@ -455,6 +512,7 @@ void talc_ctx_destroy(talc_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->slots && c->tableOwned) cudaFree(c->slots);
+  if (c->modelTabs) cudaFree(c->modelTabs);
   DevBuf* bufs[] = {&c->bases, &c->offs, &c->kmerOff, &c->nk, &c->cov, &c->order, &c->sortKey, &c->sortKeyOut, &c->sortVal,
                     &c->cubTmp, &c->arenas, &c->outArena, &c->outPos, &c->outLen, &c->outLen64, &c->status, &c->outOffs,
                     &c->out, &c->misc, &c->overflowList};
@@ -468,7 +526,7 @@ int talc_ctx_set_scratch(talc_ctx* c, uint32_t tier1_bytes, uint32_t tier2_bytes
   if (!c) return TALC_ERR_ARG;
   if (tier1_bytes) c->tier1Bytes = (tier1_bytes + 255u) & ~255u;
   if (tier2_bytes) c->tier2Bytes = (tier2_bytes + 255u) & ~255u;
-  if (tier2_threads) c->tier2Threads = (tier2_threads + 127u) & ~127u;
+  if (tier2_threads) c->tier2Warps = (tier2_threads + 3u) & ~3u;
   return TALC_OK;
 }
 
@@ -507,6 +565,21 @@ int talc_table_info(talc_ctx* c, uint64_t* cap, uint64_t* bytes, uint64_t* n) {
   return c->tableReady ? TALC_OK : TALC_ERR_NO_TABLE;
 }
 
+extern "C" int talc_table_export_device(talc_ctx* c, void* dst, uint64_t bytes) {
+  if (!c || !dst || !c->tableReady || bytes < c->capacity * sizeof(Slot)) return TALC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaMemcpyAsync(dst, c->slots, c->capacity * sizeof(Slot), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return TALC_OK;
+}
+extern "C" int talc_table_import_device(talc_ctx* c, const void* src, uint64_t capacity, uint64_t n_entries) {
+  if (!c || !src) return TALC_ERR_ARG;
+  int rc = talc_table_alloc(c, capacity);
+  if (rc) return rc;
+  CUDA_TRY(c, cudaMemcpyAsync(c->slots, src, capacity * sizeof(Slot), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return talc_table_seal(c, n_entries);
+}
 extern "C" int talc_table_copy(talc_ctx* dst, talc_ctx* src) {
   if (!dst || !src || !src->tableReady) return TALC_ERR_ARG;
   int rc = talc_table_alloc(dst, src->capacity);
@@ -727,14 +800,14 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
   int rc = prepare_batch(c, dBases, dOffs, n, totalBases, totalKmers);
   if (rc) return rc;
 
-  // launch geometry: 128-thread blocks, a multiple of the SM count, no more threads than reads need
-  const u32 threadsWanted = ((n + 31) / 32) * 32;
-  u32 blocksPerSm = 4;
+  // launch geometry: 128-thread blocks (4 warps = 4 reads in flight per block), a multiple of the SM count,
+  // no more warps than there are reads
+  u32 blocksPerSm = c->blocksPerSm;
   u32 blocks = (u32)c->sms * blocksPerSm;
-  while (blocks > (u32)c->sms && (u64)(blocks - c->sms) * 128 >= threadsWanted) blocks -= c->sms;
-  const u64 nThreads = (u64)blocks * 128;
+  while (blocks > (u32)c->sms && (u64)(blocks - c->sms) * 4 >= n) blocks -= c->sms;
+  const u64 nWarps = (u64)blocks * 4;
   const u64 outArenaCap = 2 * totalBases + (u64)n * 64 + 4096;
-  CUDA_TRY(c, c->arenas.reserve(std::max<size_t>((size_t)nThreads * c->tier1Bytes, (size_t)c->tier2Threads * c->tier2Bytes)));
+  CUDA_TRY(c, c->arenas.reserve(std::max<size_t>((size_t)nWarps * c->tier1Bytes, (size_t)c->tier2Warps * c->tier2Bytes)));
   CUDA_TRY(c, c->outArena.reserve(outArenaCap));
   CUDA_TRY(c, c->outPos.reserve((size_t)n * 8));
   CUDA_TRY(c, c->outLen.reserve((size_t)n * 4));
@@ -752,6 +825,10 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
   CorrectArgs A;
   A.tv = TableView{c->slots, c->capacity - 1};
   A.P = c->P;
+  A.tabs.lower = c->modelTabs;
+  A.tabs.upper = c->modelTabs + kModelTabN;
+  A.tabs.sq = c->modelTabs + 2 * kModelTabN;
+  A.tabs.n = kModelTabN;
   A.bases = dBases;
   A.offs = dOffs;
   A.kmerOff = (const u64*)c->kmerOff.p;
@@ -771,7 +848,15 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
   A.overflowList = (u32*)c->overflowList.p;
   A.nOverflow = dNOver;
   A.outFull = dOutFull;
-  correct_kernel<false><<<blocks, 128, 0, c->stream>>>(A);
+  A.readKcycles = nullptr;
+  DevBuf dbgCycles;
+  const bool dbg = getenv("TALC_DEBUG_CYCLES") != nullptr;
+  if (dbg) {
+    CUDA_TRY(c, dbgCycles.reserve((size_t)n * 4));
+    CUDA_TRY(c, cudaMemsetAsync(dbgCycles.p, 0, (size_t)n * 4, c->stream));
+    A.readKcycles = (u32*)dbgCycles.p;
+  }
+  correct_kernel<true><<<blocks, 128, 0, c->stream>>>(A);
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaEventRecord(c->ev[3], c->stream));
   u32 hOver = 0;
@@ -789,7 +874,7 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
     B.order = (const u32*)c->sortVal.p;
     B.nOrder = hOver;
     B.arenaBytes = c->tier2Bytes;
-    u32 b2 = std::max<u32>(1, std::min<u32>(c->tier2Threads / 128, (hOver + 127) / 128));
+    u32 b2 = std::max<u32>(1, std::min<u32>(c->tier2Warps / 4, (hOver + 3) / 4));
     correct_kernel<true><<<b2, 128, 0, c->stream>>>(B);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpyAsync(&hOver2, dNOver, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -819,6 +904,23 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaEventRecord(c->ev[5], c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (dbg) {
+    std::vector<u32> kc(n);
+    std::vector<u64> ho(n + 1);
+    cudaMemcpy(kc.data(), dbgCycles.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ho.data(), dOffs, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost);
+    std::vector<u32> idx(n);
+    for (u32 i = 0; i < n; ++i) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return kc[a] > kc[b]; });
+    double sum = 0;
+    for (u32 i = 0; i < n; ++i) sum += kc[i];
+    fprintf(stderr, "[talc debug] per-read Mcycles: total %.0f  mean %.3f  p50 %.3f  p99 %.3f  max %.3f\n", sum / 1024, sum / 1024 / n,
+            kc[idx[n / 2]] / 1024.0, kc[idx[n / 100]] / 1024.0, kc[idx[0]] / 1024.0);
+    for (u32 i = 0; i < 8 && i < n; ++i)
+      fprintf(stderr, "[talc debug]   slow read %u: %.1f Mcycles, length %llu\n", idx[i], kc[idx[i]] / 1024.0,
+              (unsigned long long)(ho[idx[i] + 1] - ho[idx[i]]));
+    dbgCycles.release();
+  }
   if (counters) {
     memcpy(counters, hCtr, sizeof(hCtr));
     counters->reads = n;
@@ -919,7 +1021,7 @@ int talc_test_align(talc_ctx* c, int op, const uint8_t* a, const uint64_t* aOff,
   CUDA_TRY(c, cudaMemcpyAsync(dB, b, bOff[n], cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(dAo, aOff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(dBo, bOff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  test_align_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(op, dA, dAo, dB, dBo, n, aux, aux2, c->params.K, dAr, arenaBytes, dR);
+  test_align_kernel<<<(n + 3) / 4, 128, 0, c->stream>>>(op, dA, dAo, dB, dBo, n, aux, aux2, c->params.K, dAr, arenaBytes, dR);
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaMemcpyAsync(result, dR, rn * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -935,11 +1037,13 @@ int talc_test_sort(talc_ctx* c, const int64_t* keys, uint32_t n, uint32_t* perm)
   CUDA_TRY(c, cudaMalloc((void**)&dK, (size_t)n * 8));
   CUDA_TRY(c, cudaMalloc((void**)&dP, (size_t)n * 4));
   CUDA_TRY(c, cudaMemcpyAsync(dK, keys, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-  test_sort_kernel<<<1, 32, 0, c->stream>>>(dK, n, dP);
+  void* dS;
+  CUDA_TRY(c, cudaMalloc(&dS, (size_t)n * sizeof(SortKey)));
+  test_sort_kernel<<<1, 32, 0, c->stream>>>(dK, n, dP, dS);
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaMemcpyAsync(perm, dP, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  cudaFree(dK); cudaFree(dP);
+  cudaFree(dK); cudaFree(dP); cudaFree(dS);
   return TALC_OK;
 }
 

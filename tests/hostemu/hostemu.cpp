@@ -122,6 +122,8 @@ int emu_correct_reads(void* tab, const emu_params* q, const uint8_t* bases, cons
     Corrector* cx = new Corrector;
     cx->T = tv;
     cx->P = P;
+    cx->tabs.n = 0;
+    cx->tabs.lower = cx->tabs.upper = cx->tabs.sq = nullptr;
     Counters mine;
     memset(&mine, 0, sizeof(mine));
     cx->ctr = &mine;
@@ -149,7 +151,7 @@ int emu_correct_reads(void* tab, const emu_params* q, const uint8_t* bases, cons
     if (st == kReadOk) olen = cx->corrected_length();
     else olen = rd.len;
     if (pos + olen > out_capacity) { delete cx; return -1; }
-    if (st == kReadOk) cx->emit(out + pos);
+    if (st == kReadOk) cx->emit(out + pos, 0, 1);
     else for (u32 i = 0; i < rd.len; ++i) out[pos + i] = code_char(rd.code(i));
     pos += olen;
     if (st != kReadOverflow) total.bases_out += olen;
@@ -223,9 +225,9 @@ int emu_tag_next_nodes(const emu_params* q, const uint32_t* counts4, const uint3
                        int32_t* tags4, double* dist4) {
   Params P = to_params(q);
   u8 tag[4] = {0, 0, 0, 0};
-  double d[4] = {0, 0, 0, 0};
-  int n = tag_next_nodes(counts4, colours4, count, P, complex_ != 0, tag, d);
-  for (int i = 0; i < n; ++i) { tags4[i] = tag[i] == kExpected ? 0 : tag[i] == kUnexpected ? 1 : 7; dist4[i] = d[i]; }
+  const StepBounds sb = step_bounds(count, P);
+  int n = tag_next_nodes(counts4, colours4, sb, P, complex_ != 0, tag);
+  for (int i = 0; i < n; ++i) { tags4[i] = tag[i] == kExpected ? 0 : tag[i] == kUnexpected ? 1 : 7; dist4[i] = step_dist(count, counts4[i], sb); }
   return n;
 }
 }

@@ -21,8 +21,7 @@ total = w.total_bases()
 d_out = torch.empty(2 * total + 64 * n + 4096, dtype=torch.uint8, device="cuda")
 d_ooff = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
 d_st = torch.zeros(n, dtype=torch.uint8, device="cuda")
-for tier1 in (48 * 1024,):
-    t.set_scratch(tier1_bytes=tier1)
+for tier1 in (1 << 20,):
     for it in range(3):
         t0 = time.time()
         ctr = t.correct_device(d_reads, d_off, total, d_out, d_ooff, d_st)
