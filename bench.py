@@ -4,7 +4,7 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
   python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement of the reference, host cores
 
-Workload = BASELINE.json configs[1]: a 200k-transcript synthetic transcriptome (20k genes + isoforms),
+Workload = BASELINE.json configs[1]: a 200k-transcript synthetic transcriptome (8k genes + isoforms),
 its ~30M-entry k=21 count table, ONT-like long reads (10% error).  A step is one pass of the hot path over
 one batch of `--batch-reads` reads of that set (a different slice every step); the table always has its
 full size, so the probes miss L2 as they would on the full run.  Multi-GPU is weak scaling: every rank holds
@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config index (1-based): 2, 3 (junctions) or 1/5")
     ap.add_argument("--scale", type=float, default=1.0, help="scales transcripts and reads (1.0 = the named config)")
     ap.add_argument("--batch-reads", type=int, default=131072, help="reads per step and per rank")
-    ap.add_argument("--cpu-sample-reads", type=int, default=384, help="reads of the bounded CPU sample")
+    ap.add_argument("--cpu-sample-reads", type=int, default=16384, help="reads of the bounded CPU sample (about 10-30 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -118,7 +118,7 @@ def run_reference(args, rank, world):
     tr = synth.make_transcriptome(cfg, dev)
     keys, counts, jk, jc = synth.make_counts(cfg, tr, dev)
     use_j = args.config == 3
-    nsample = args.cpu_sample_reads
+    nsample = max(64, args.cpu_sample_reads // 4)  # per step; the whole run stays within a few minutes
     reads, roff = synth.make_reads(cfg, tr, nsample * (args.steps + args.warmup), dev, seed_offset=3)
     reads, roff = reads.cpu().numpy(), roff.cpu().numpy().astype(np.uint64)
     threads = os.cpu_count() or 1

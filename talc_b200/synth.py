@@ -55,9 +55,13 @@ def baseline_config(i: int, scale: float = 1.0) -> SynthConfig:
     if i == 1:
         c = SynthConfig(seed=1, k=21, n_genes=700, n_transcripts=1000, n_reads=10000, high_count_kmers=3)
     elif i in (2, 3):
-        c = SynthConfig(seed=2, k=21, n_genes=20000, n_transcripts=200000, n_reads=1000000, high_count_kmers=5)
+        # 8k genes x ~25 isoforms: ~12M gene k-mers + ~16M novel/junction k-mers + ~4M erroneous k-mers with
+        # count >= 2  ->  ~30M kept entries, as BASELINE.json names for the transcriptome-scale configuration
+        c = SynthConfig(seed=2, k=21, n_genes=8000, n_transcripts=200000, n_reads=1000000, high_count_kmers=5,
+                        variant_rate=0.05)
     elif i == 4:
-        c = SynthConfig(seed=2, k=21, n_genes=20000, n_transcripts=200000, n_reads=5000000, high_count_kmers=5)
+        c = SynthConfig(seed=2, k=21, n_genes=8000, n_transcripts=200000, n_reads=5000000, high_count_kmers=5,
+                        variant_rate=0.05)
     elif i == 5:
         c = SynthConfig(seed=5, k=30, n_genes=250, n_transcripts=1000, n_reads=10000, read_error=0.15,
                         lowcomp_frac=0.5, high_count_kmers=3)

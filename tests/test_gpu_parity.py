@@ -204,3 +204,41 @@ def test_std_sort_replica_on_device(api, case_c1):
             assert np.array_equal(t.test_sort(keys), po.std_sort_perm(keys)), (n, hi)
     keys = np.arange(200)[::-1].copy()
     assert np.array_equal(t.test_sort(keys), po.std_sort_perm(keys))
+
+
+def test_cli_is_a_drop_in(api, tmp_path):
+    """The `talc` command line on the GPU writes the same .fa / .log / .config.txt as the oracle's front end
+    (reference order: -t 1), from the same text inputs, junction dump included."""
+    import os
+    import subprocess
+    import torch
+    from oracle import pyoracle as po
+    from talc_b200 import build, synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_case.npz"))
+    k = int(g["c3_k"][0])
+    synth.write_dump(str(tmp_path / "sr.dump"), torch.from_numpy(g["c3_keys"].astype(np.int64)),
+                     torch.from_numpy(g["c3_counts"].astype(np.int64)), k)
+    synth.write_dump(str(tmp_path / "j.dump"), torch.from_numpy(g["c3_jkeys"].astype(np.int64)),
+                     torch.from_numpy(g["c3_jcounts"].astype(np.int64)), k)
+    # reads: wrapped FASTA with one unsolvable read and one short read mixed in, so that the log is exercised
+    reads, off = g["c3_reads"], g["c3_off"]
+    with open(tmp_path / "reads.fa", "wb") as f:
+        for r in range(len(off) - 1):
+            s = reads[int(off[r]):int(off[r + 1])].tobytes()
+            f.write(b">read_%d some description\n" % r)
+            for j in range(0, len(s), 60):
+                f.write(s[j:j + 60] + b"\n")
+            if r == 3:
+                f.write(b">junk\n" + b"ACGT" * 60 + b"\n>tiny\nACGTACGT\n")
+    cli = build.build_cli()
+    args = [str(tmp_path / "reads.fa"), "--SRCounts", str(tmp_path / "sr.dump"), "--junctions", str(tmp_path / "j.dump"),
+            "-k", str(k)]
+    assert subprocess.call([cli] + args + ["-o", "gpu", "-t", "4"], cwd=tmp_path, stdout=subprocess.DEVNULL) == 0
+    assert subprocess.call([po.BIN] + args + ["-o", "cpu", "-t", "1", "--oracle-table", "hash"], cwd=tmp_path,
+                           stdout=subprocess.DEVNULL) == 0
+    for ext in (".fa", ".log", ".stats_basics.txt"):
+        assert open(tmp_path / ("gpu" + ext), "rb").read() == open(tmp_path / ("cpu" + ext), "rb").read(), ext
+    a = open(tmp_path / "gpu.config.txt").read().replace("gpu", "X")
+    b = open(tmp_path / "cpu.config.txt").read().replace("cpu", "X")
+    assert a == b
+    assert b"junk" in open(tmp_path / "gpu.log", "rb").read()
