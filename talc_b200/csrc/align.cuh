@@ -469,6 +469,9 @@ TALC_HDN void xdrop_extend_scalar(const SeqView& query, u32 qoff, u32 qlen, cons
     }
   }
   if (st) st->cells_xdrop += cells;
+#ifdef TALC_XD_STATS
+  fprintf(stderr, "XD %d %u %u %lld %llu\n", scoreDropOff, qlen, dlen, (long long)antiDiagNo, (unsigned long long)cells);
+#endif
 
   i64 longestExtensionCol = len3 + offset3 - 2;
   i64 longestExtensionRow = antiDiagNo - longestExtensionCol;
@@ -532,7 +535,7 @@ __device__ __noinline__ void xdrop_extend(const SeqView& query, u32 qoff, u32 ql
     i64 minCol = 1, maxCol = 2;
     i64 offset1 = 0, offset2 = 0, offset3 = 0;
     __syncwarp();
-    if (lane == 0) {
+    {
       antiDiag2[0] = 0;
       const int v = (-gapCost > scoreDropOff) ? undefined : gapCost;
       antiDiag3[0] = v;
@@ -558,7 +561,7 @@ __device__ __noinline__ void xdrop_extend(const SeqView& query, u32 qoff, u32 ql
       offset3 = minCol - 1;
       len3 = maxCol + 1 - offset3;
       if (len3 > capW) { outgrown = true; break; }
-      if (lane == 0) {
+      {  // _initAntiDiag3: every lane stores the same two values (no divergence, no extra barrier)
         const int minScore = best - scoreDropOff;
         int e0 = undefined, e1 = undefined;
         if ((int)antiDiagNo * gapCost > minScore) {
@@ -584,11 +587,7 @@ __device__ __noinline__ void xdrop_extend(const SeqView& query, u32 qoff, u32 ql
           antiDiagBest = antiDiagBest > tmp ? antiDiagBest : tmp;
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const int other = __shfl_xor_sync(0xffffffffu, antiDiagBest, o);
-        antiDiagBest = antiDiagBest > other ? antiDiagBest : other;
-      }
+      antiDiagBest = __reduce_max_sync(0xffffffffu, antiDiagBest);  // also orders the shared-memory stores above
       __syncwarp();
       cells += (u64)(maxCol - minCol);
       best = best > antiDiagBest ? best : antiDiagBest;
