@@ -217,10 +217,10 @@ class Talc:
         a, ao = cat(a_list)
         b, bo = cat(b_list)
         n = len(a_list)
-        res = np.zeros(n * (4 if op == 3 else 1), dtype=np.int32)
+        res = np.zeros(n * (4 if op >= 3 else 1), dtype=np.int32)
         self._check(lib().talc_test_align(self.h, op, _ptr(a), _ptr(ao), _ptr(b), _ptr(bo), n, aux, aux2, _ptr(res)),
                     "talc_test_align")
-        return res.reshape(n, 4) if op == 3 else res
+        return res.reshape(n, 4) if op >= 3 else res
 
     def test_sort(self, keys) -> np.ndarray:
         keys = np.ascontiguousarray(keys, dtype=np.int64)

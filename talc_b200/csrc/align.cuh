@@ -17,19 +17,21 @@
 
 namespace talc {
 
-// either a slice of the raw read (walk order) or a packed trail
+// a slice of the read in walk order (packed when the read holds no N, else raw bytes) or a packed trail:
+// element i is base (start + i*step) of w (2-bit packed) when w != nullptr, else of s (ASCII)
 struct SeqView {
-  const u8* s;    // raw read bytes (when w == nullptr)
+  const u8* s;
   i32 start;
   i32 step;
-  const u64* w;   // packed trail (when non-null)
+  const u64* w;
   u32 len;
   TALC_HD u32 code(u32 i) const {
-    if (w) return (u32)((w[i >> 5] >> (62 - 2 * (i & 31))) & 3ull);
-    return base_code(s[start + (i32)i * step]);
+    const u32 idx = (u32)(start + (i32)i * step);
+    if (w) return (u32)((w[idx >> 5] >> (62 - 2 * (idx & 31))) & 3ull);
+    return base_code(s[idx]);
   }
 };
-TALC_HD SeqView view_of(const RefView& r) { SeqView v; v.s = r.s; v.start = r.start; v.step = r.step; v.w = nullptr; v.len = r.len; return v; }
+TALC_HD SeqView view_of(const RefView& r) { SeqView v; v.s = r.s; v.start = r.start; v.step = r.step; v.w = r.w; v.len = r.len; return v; }
 TALC_HD SeqView view_of(const PathView& p) { SeqView v; v.s = nullptr; v.start = 0; v.step = 1; v.w = p.w; v.len = p.len; return v; }
 TALC_HD SeqView view_of_path(const u64* w, u32 len) { SeqView v; v.s = nullptr; v.start = 0; v.step = 1; v.w = w; v.len = len; return v; }
 
@@ -42,15 +44,7 @@ TALC_HDN void build_peq(const SeqView& pat, u32 pn, u32 block, u64 peq[5]) {
   peq[0] = peq[1] = peq[2] = peq[3] = peq[4] = 0;
   const u32 r0 = block * 64;
   const u32 r1 = (pn - r0 < 64u) ? pn : r0 + 64;
-  if (pat.w && pat.step == 1) {
-    // packed trail: two words hold the 64 rows
-    for (u32 r = r0; r < r1; ++r) {
-      const u32 c = (u32)((pat.w[r >> 5] >> (62 - 2 * (r & 31))) & 3ull);
-      peq[c] |= 1ull << (r - r0);
-    }
-  } else {
-    for (u32 r = r0; r < r1; ++r) peq[pat.code(r)] |= 1ull << (r - r0);
-  }
+  for (u32 r = r0; r < r1; ++r) peq[pat.code(r)] |= 1ull << (r - r0);
 }
 
 // unit-cost edit distance between a[0..an) and b[0..bn) (both non-empty)
@@ -469,9 +463,6 @@ TALC_HDN void xdrop_extend_scalar(const SeqView& query, u32 qoff, u32 qlen, cons
     }
   }
   if (st) st->cells_xdrop += cells;
-#ifdef TALC_XD_STATS
-  fprintf(stderr, "XD %d %u %u %lld %llu\n", scoreDropOff, qlen, dlen, (long long)antiDiagNo, (unsigned long long)cells);
-#endif
 
   i64 longestExtensionCol = len3 + offset3 - 2;
   i64 longestExtensionRow = antiDiagNo - longestExtensionCol;
@@ -504,152 +495,22 @@ TALC_HDN void xdrop_extend_scalar(const SeqView& query, u32 qoff, u32 qlen, cons
 }
 
 
+}  // namespace talc
+#include "xdrop.cuh"
+namespace talc {
+
 #if defined(__CUDA_ARCH__)
-// Device form of the same routine: the 32 lanes of the warp that owns the read each take every 32nd cell
-// of an anti-diagonal, and the three live anti-diagonals sit in shared memory while the band fits
-// (it nearly always does: with match = 0 a cell survives only within X of the main diagonal).  The
-// arithmetic, the window updates and the end-position rules are the scalar routine's, line for line.
-// Must be called by all 32 lanes with identical arguments.
-__device__ __noinline__ void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff,
-                                          u32 dlen, int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide,
-                                          DpStats* st) {
-  __shared__ i32 xdShared[TALC_WARPS_PER_BLOCK][3 * TALC_XD_CAP];
-  const u32 lane = threadIdx.x & 31;
-  const u32 warp = (threadIdx.x >> 5) % TALC_WARPS_PER_BLOCK;
-  ext_rows = 0;
-  ext_cols = 0;
-  const i64 cols = (i64)qlen + 1;
-  const i64 rows = (i64)dlen + 1;
-  if (rows == 1 || cols == 1) return;
-  const int gapCost = -1;
-  const int undefined = INT32_MIN + 1;
-  const u32 mk = ar.mark();
-  bool useShared = true;
-  i64 capW = TALC_XD_CAP;
-  i32* buf = xdShared[warp];
-  for (;;) {  // at most two rounds: shared-memory band first, full-width global arrays if the band outgrows it
-    i32* antiDiag1 = buf;
-    i32* antiDiag2 = buf + capW;
-    i32* antiDiag3 = buf + 2 * capW;
-    i64 len1 = 0, len2 = 1, len3 = 2;
-    i64 minCol = 1, maxCol = 2;
-    i64 offset1 = 0, offset2 = 0, offset3 = 0;
-    __syncwarp();
-    {
-      antiDiag2[0] = 0;
-      const int v = (-gapCost > scoreDropOff) ? undefined : gapCost;
-      antiDiag3[0] = v;
-      antiDiag3[1] = v;
-    }
-    __syncwarp();
-    i64 antiDiagNo = 1;
-    int best = 0;
-    u64 cells = 0;
-    bool outgrown = false;
-    while (minCol < maxCol) {
-      ++antiDiagNo;
-      {
-        i32* t = antiDiag1;
-        antiDiag1 = antiDiag2;
-        antiDiag2 = antiDiag3;
-        antiDiag3 = t;
-        len1 = len2;
-        len2 = len3;
-      }
-      offset1 = offset2;
-      offset2 = offset3;
-      offset3 = minCol - 1;
-      len3 = maxCol + 1 - offset3;
-      if (len3 > capW) { outgrown = true; break; }
-      {  // _initAntiDiag3: every lane stores the same two values (no divergence, no extra barrier)
-        const int minScore = best - scoreDropOff;
-        int e0 = undefined, e1 = undefined;
-        if ((int)antiDiagNo * gapCost > minScore) {
-          if (offset3 == 0) e0 = (int)antiDiagNo * gapCost;
-          if (antiDiagNo - maxCol == 0) e1 = (int)antiDiagNo * gapCost;
-        }
-        antiDiag3[0] = e0;
-        antiDiag3[maxCol - offset3] = e1;  // maxCol - offset3 >= 2: never the same cell as [0]
-      }
-      int antiDiagBest = (int)antiDiagNo * gapCost;
-      for (i64 col = minCol + lane; col < maxCol; col += 32) {
-        const i64 i3 = col - offset3, i2 = col - offset2, i1 = col - offset1;
-        const u32 queryPos = (u32)(col - 1);
-        const u32 dbPos = (u32)(antiDiagNo - col - 1);
-        const int d2a = antiDiag2[i2 - 1], d2b = antiDiag2[i2];
-        int tmp = (d2a > d2b ? d2a : d2b) + gapCost;
-        const int sub = antiDiag1[i1 - 1] + ((query.code(qoff + queryPos) == database.code(doff + dbPos)) ? 0 : -1);
-        tmp = tmp > sub ? tmp : sub;
-        if (tmp < best - scoreDropOff) {
-          antiDiag3[i3] = undefined;
-        } else {
-          antiDiag3[i3] = tmp;
-          antiDiagBest = antiDiagBest > tmp ? antiDiagBest : tmp;
-        }
-      }
-      antiDiagBest = __reduce_max_sync(0xffffffffu, antiDiagBest);  // also orders the shared-memory stores above
-      __syncwarp();
-      cells += (u64)(maxCol - minCol);
-      best = best > antiDiagBest ? best : antiDiagBest;
-      while (minCol - offset3 < len3 && antiDiag3[minCol - offset3] == undefined && minCol - offset2 - 1 < len2 &&
-             antiDiag2[minCol - offset2 - 1] == undefined) {
-        ++minCol;
-      }
-      while (maxCol - offset3 > 0 && (antiDiag3[maxCol - offset3 - 1] == undefined) &&
-             (antiDiag2[maxCol - offset2 - 1] == undefined)) {
-        --maxCol;
-      }
-      ++maxCol;
-      {
-        const i64 lo = antiDiagNo + 2 - rows;
-        if (lo > minCol) minCol = lo;
-        if (cols < maxCol) maxCol = cols;
-      }
-    }
-    if (outgrown) {
-      if (!useShared) {  // even the full-width arrays were too small: cannot happen (capW = cols + 1)
-        ar.overflow = 1;
-        ar.release(mk);
-        return;
-      }
-      useShared = false;
-      capW = cols + 1;
-      buf = (i32*)ar.alloc((u32)(3 * capW * 4));
-      if (!buf) return;
-      continue;
-    }
-    if (st) st->cells_xdrop += cells;
-    i64 longestExtensionCol = len3 + offset3 - 2;
-    i64 longestExtensionRow = antiDiagNo - longestExtensionCol;
-    int longestExtensionScore = antiDiag3[longestExtensionCol - offset3];
-    if (longestExtensionScore == undefined) {
-      if (antiDiag2[len2 - 2] != undefined) {
-        longestExtensionCol = len2 + offset2 - 2;
-        longestExtensionRow = antiDiagNo - 1 - longestExtensionCol;
-        longestExtensionScore = antiDiag2[longestExtensionCol - offset2];
-      } else if (len2 > 2 && antiDiag2[len2 - 3] != undefined) {
-        longestExtensionCol = len2 + offset2 - 3;
-        longestExtensionRow = antiDiagNo - 1 - longestExtensionCol;
-        longestExtensionScore = antiDiag2[longestExtensionCol - offset2];
-      }
-    }
-    if (longestExtensionScore == undefined) {
-      for (i64 i = 0; i < len1; ++i) {
-        if (antiDiag1[i] > longestExtensionScore) {
-          longestExtensionScore = antiDiag1[i];
-          longestExtensionCol = i + offset1;
-          longestExtensionRow = antiDiagNo - 2 - longestExtensionCol;
-        }
-      }
-    }
-    if (longestExtensionScore != undefined) {
-      ext_rows = (u32)longestExtensionRow;
-      ext_cols = (u32)longestExtensionCol;
-    }
-    __syncwarp();
-    ar.release(mk);
-    return;
-  }
+// Device form: the anti-diagonals live in registers (xdrop.cuh) while the band |diagonal| <= X fits 32*S
+// diagonals; beyond that (never seen on the benchmark workloads) every lane runs the scalar routine on the
+// warp's arena.  Must be called by all 32 lanes with identical arguments.
+__device__ __forceinline__ void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff,
+                                             u32 dlen, int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide,
+                                             DpStats* st) {
+  if (scoreDropOff <= 31) xdrop_extend_reg<1>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, st);
+  else if (scoreDropOff <= 63) xdrop_extend_reg<2>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, st);
+  else if (scoreDropOff <= 127) xdrop_extend_reg<4>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, st);
+  else if (scoreDropOff <= 255) xdrop_extend_reg<8>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, st);
+  else xdrop_extend_scalar(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, ar, true, st);
 }
 #else
 inline void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen,

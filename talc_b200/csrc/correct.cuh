@@ -95,6 +95,7 @@ class Corrector {
   Params P;
   ModelTabs tabs;  // n == 0: no tables (host emulation)
   ReadView rd;
+  const u64* rdw;  // the read 2-bit packed (keep arena), nullptr when it holds an N
   const u32* cov;
   u32 C;  // number of k-mers
   Arena keep;     // persistent per-read data: regions, pieces
@@ -171,6 +172,9 @@ class Corrector {
     u32 prefix = 0, remaining = r;
     u64 sumBelow = 0;
     const u32 lane = lane_id(), nl = lane_count();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int nib = top; nib >= 0; --nib) {  // radix select, most significant nibble first
       u32 hist[16];
       u64 hsum[16];
@@ -450,7 +454,8 @@ class Corrector {
     const u32 nw = (nbases + 31) / 32;
     u64* d = slot_ptr(dst);
     const u64* s = slot_ptr(src);
-    for (u32 i = 0; i < nw; ++i) d[i] = s[i];
+    for (u32 i = lane_id(); i < nw; i += lane_count()) d[i] = s[i];  // the warp's lanes share the copy
+    warp_sync();
   }
 
   // root trail: the anchor k-mer in walk order (Trail.cpp:57-65)
@@ -484,6 +489,24 @@ class Corrector {
     const u32 k = K();
     if (!(plen > k)) return false;
     const u32 stride = (P.cycle_mode == 0) ? k : 1u;
+#if defined(__CUDA_ARCH__)
+    {  // one window per lane; the first occurrence is the lowest lane of the first batch that matches
+      u64 nd = needle;
+      if (!dirRight) {
+        nd = 0;
+        for (u32 i = 0; i < k; ++i) nd |= ((needle >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
+      }
+      const u32 lane = threadIdx.x & 31u;
+      for (u32 base = 0; (u64)base * stride + k <= plen; base += 32) {
+        const u32 p = (base + lane) * stride;
+        bool match = false;
+        if (p + k <= plen) match = path_kmer_fwd(w, dirRight ? p : (plen - k - p), k) == nd;
+        const u32 mm = __ballot_sync(0xffffffffu, match);
+        if (mm) return ((base + (u32)__ffs((int)mm) - 1) * stride) > 0;
+      }
+      return false;
+    }
+#endif
     if (dirRight) {
       for (u32 p = 0; p + k <= plen; p += stride)
         if (path_kmer_fwd(w, p, k) == needle) return p > 0;
@@ -596,105 +619,107 @@ class Corrector {
 
 
 #if defined(__CUDA_ARCH__)
-  // The same fast path with the warp's lanes put to work: lanes 0-3 probe the four successors (A,C,G,T) side
-  // by side and a ballot picks the branch; one lane per aim k-mer and one lane per cycle-test window.
-  // When exactly one successor reaches MIN_COUNT it is EXPECTED by the `counter == 1` rule of tagNextNodes
-  // (Explorer.cpp:1251) and no interval bound is needed; otherwise the scalar tagger decides.
+  // The fast path on the device, for a frontier of 1..7 trails (two or three trails walking side by side
+  // through a variant or an isoform bubble is the common multi-trail case: ~30% of all inner steps).
+  // Lane l serves trail l/4 and successor base l%4: all successors of all trails are probed side by side, a
+  // ballot per group of four lanes picks the branch, the aim k-mers are split over the four lanes of a group,
+  // and the cycle test of each trail runs one window per lane.  A step is taken here only if EVERY trail has
+  // exactly one admissible successor, reaches no aim and closes no cycle -- then the frontier keeps its size and
+  // order (child t of trail t), nothing is scored or pruned (frontier <= MAX_NB_COMPETING_PATHS and <= 7, so
+  // `complex` is false and gardening cannot trigger), and the step only appends one base per trail.  Any other
+  // kind of step ends the run *before* the step; the general code then takes that step in full.
   __device__ __noinline__ void fast_walk(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border) {
-    if (nCur != 1) return;
-    if (nAims > 32) { fast_walk_scalar(step, pathMax, aims, nAims, border); return; }
+    const u32 nT = nCur;
+    if (nT == 0 || nT > 7 || nT > P.max_branches) return;
     const u32 lane = threadIdx.x & 31u;
+    const u32 t = lane >> 2, b = lane & 3u;
+    const bool act = t < nT;
     const u32 k = P.K;
     const bool right = dirRight;
     const TableView tv = T;
     const Params prm = P;
     const ModelTabs mt = tabs;
-    Trail tr = cur[0];
-    u64* w = slot_ptr(tr.slot);
+    const u64 kmask = kmer_mask(k);
+    const u32 stride = (prm.cycle_mode == 0) ? k : 1u;
+    const Trail tr = cur[act ? t : 0];
+    u64* const w = slot_ptr(tr.slot);
     u64 kmer = tr.kmer;
     u32 count = tr.count;
     double dsum = tr.dist;
-    u32 st = step;
-    u32 nSteps = 0;
-    const u32 stride = (prm.cycle_mode == 0) ? k : 1u;
-    const u64 kmask = kmer_mask(k);
-    u64 rkmer = 0;
+    u64 rkmer = 0;  // the last k-mer with its bases in reverse order (LEFT walks compare in walk order)
     for (u32 i = 0; i < k; ++i) rkmer |= ((kmer >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
-    const u64 myAim = (!border && lane < nAims) ? aims[lane].kmer : ~0ull;  // ~0 is not a k-mer (<= 60 bits)
-    u32 cwIdx = (k + st) >> 5;
-    u64 cw = w[cwIdx];
-    const u32 b = lane & 3u;
+    u32 st = step, nSteps = 0;
+    const u32 grp = lane & ~3u;
 #pragma unroll 1
     while (st < pathMax) {
-      if (border && ((st + 1) % kCheckInterval == 0)) break;
+      if (border && ((st + 1) % kCheckInterval == 0)) break;  // scoreEdges is due after this step
       const u32 plen = k + st;
-      // ---- the four successors, one per lane (lanes 4..31 mirror lanes 0..3)
-      const u64 key = kmer_next(kmer, b, right, k);
-      const u64 bucket = hash_kmer(key) & tv.mask & ~1ull;
-      const Slot s0 = load_slot(tv.slots + bucket);
-      const Slot s1 = load_slot(tv.slots + bucket + 1);
-      u32 cnt, col;
-      if (sector_resolve(s0, s1, key, cnt, col) < 0) table_probe_from(tv, bucket, key, cnt, col);
-      const u32 m = __ballot_sync(0xffffffffu, cnt >= prm.min_count) & 0xFu;
-      if (m == 0) break;  // dead end
-      int child;
-      if ((m & (m - 1)) == 0) {
-        child = __ffs((int)m) - 1;
-      } else {
-        u32 cnt4[4], col4[4];
-        for (int i = 0; i < 4; ++i) {
-          cnt4[i] = __shfl_sync(0xffffffffu, cnt, i);
-          col4[i] = __shfl_sync(0xffffffffu, col, i);
-        }
-        const StepBounds sb = step_bounds_tab(count, prm, mt);
-        u8 tag[4];
-        tag_next_nodes(cnt4, col4, sb, prm, false, tag);
-        int nChildren = 0;
-        child = -1;
-        for (int i = 0; i < 4; ++i)
-          if (tag[i] != kUnexpected) { child = i; ++nChildren; }
-        if (nChildren != 1) break;
+      // ---- every successor of every trail, one per lane
+      u32 cnt = 0, col = 0;
+      if (act) {
+        const u64 key = kmer_next(kmer, b, right, k);
+        const u64 bucket = hash_kmer(key) & tv.mask & ~1ull;
+        const Slot s0 = load_slot(tv.slots + bucket);
+        const Slot s1 = load_slot(tv.slots + bucket + 1);
+        if (sector_resolve(s0, s1, key, cnt, col) < 0) table_probe_from(tv, bucket, key, cnt, col);
       }
-      const u32 childCnt = __shfl_sync(0xffffffffu, cnt, child);
-      const u64 ck = kmer_next(kmer, (u32)child, right, k);
-      if (__ballot_sync(0xffffffffu, myAim == ck)) break;  // aim reached: the general step records the bridge
-      // ---- cycle test, one window per lane
-      if (plen > k) {
-        const u64 needle = right ? ck : (((rkmer << 2) | (u64)child) & kmask);
-        bool cyc = false;
-        for (u32 base = 0; (u64)base * stride + k <= plen; base += 32) {
-          const u32 p = (base + lane) * stride;
-          bool match = false;
-          if (p + k <= plen) {
-            const u32 wi0 = right ? p : (plen - k - p);
-            const u32 wi = wi0 >> 5, off = 2 * (wi0 & 31);
-            const u64 a0 = (wi == cwIdx) ? cw : w[wi];
-            u64 hi = a0 << off;
-            if (off && (off + 2 * k > 64)) {
-              const u64 a1 = (wi + 1 == cwIdx) ? cw : w[wi + 1];
-              hi |= a1 >> (64 - off);
-            }
-            match = (hi >> (64 - 2 * k)) == needle;
+      const u32 mAll = __ballot_sync(0xffffffffu, cnt >= prm.min_count);
+      const u32 m = (mAll >> grp) & 0xFu;
+      int child = -1;
+      if (act) {
+        if (m != 0 && (m & (m - 1)) == 0) {
+          child = __ffs((int)m) - 1;  // the only successor in the graph: EXPECTED by the counter == 1 rule
+        } else if (m != 0) {
+          u32 cnt4[4], col4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            cnt4[i] = __shfl_sync(0xFu << grp, cnt, grp + i);  // the four lanes of a group branch together
+            col4[i] = __shfl_sync(0xFu << grp, col, grp + i);
           }
-          const u32 mm = __ballot_sync(0xffffffffu, match);
-          if (mm) {  // first occurrence = lowest lane of the first batch that matches
-            cyc = ((base + (u32)__ffs((int)mm) - 1) * stride) > 0;
-            break;
+          const StepBounds sb = step_bounds_tab(count, prm, mt);
+          u8 tag[4];
+          tag_next_nodes(cnt4, col4, sb, prm, false, tag);
+          int nChildren = 0;
+          for (int i = 0; i < 4; ++i)
+            if (tag[i] != kUnexpected) { child = i; ++nChildren; }
+          if (nChildren != 1) child = -1;
+        }
+      }
+      if (__ballot_sync(0xffffffffu, act && child < 0)) break;  // dead end or branching somewhere: general step
+      const u32 childCnt = __shfl_sync(0xffffffffu, cnt, grp + (u32)(child < 0 ? 0 : child));
+      const u64 ck = kmer_next(kmer, (u32)(child < 0 ? 0 : child), right, k);
+      if (!border) {  // aim reached by any trail: the general step records the bridge
+        bool aim = false;
+        if (act)
+          for (u32 a = b; a < nAims; a += 4) aim |= (aims[a].kmer == ck);
+        if (__ballot_sync(0xffffffffu, aim)) break;
+      }
+      // ---- cycle test of every trail against its own sequence, one window per lane
+      if (plen > k) {
+        const u64 myNeedle = right ? ck : (((rkmer << 2) | (u64)(child < 0 ? 0 : child)) & kmask);
+        bool cyc = false;
+        for (u32 q = 0; q < nT && !cyc; ++q) {
+          const u64 needle = __shfl_sync(0xffffffffu, myNeedle, 4 * q);
+          const u64* wq = (const u64*)__shfl_sync(0xffffffffu, (unsigned long long)w, 4 * q);
+          for (u32 base = 0; (u64)base * stride + k <= plen; base += 32) {
+            const u32 p = (base + lane) * stride;
+            bool match = false;
+            if (p + k <= plen) match = path_kmer_fwd(wq, right ? p : (plen - k - p), k) == needle;
+            const u32 mm = __ballot_sync(0xffffffffu, match);
+            if (mm) {  // first occurrence = lowest lane of the first batch that matches
+              cyc = ((base + (u32)__ffs((int)mm) - 1) * stride) > 0;
+              break;
+            }
           }
         }
         if (cyc) break;
       }
-      // ---- commit the step
-      {
-        const u32 idx = plen >> 5;
-        if (idx != cwIdx) { cwIdx = idx; cw = 0; }
-        const u32 sh = 62 - 2 * (plen & 31);
-        cw = (cw & ~(3ull << sh)) | ((u64)child << sh);
-        w[cwIdx] = cw;  // every lane stores the same word: each later reads back its own store
-      }
+      // ---- commit the step: one base per trail
+      if (act && b == 0) path_set(w, plen, (u32)child);
+      __syncwarp();
       const double sq = (count < mt.n) ? mt.sq[count] : sqrt((double)count);
       dsum = dsum + fabs((double)count - (double)childCnt) / sq;
-      if (!right) rkmer = ((rkmer << 2) | (u64)child) & kmask;
+      if (!right) rkmer = ((rkmer << 2) | (u64)(child < 0 ? 0 : child)) & kmask;
       kmer = ck;
       count = childCnt;
       ++st;
@@ -702,16 +727,18 @@ class Corrector {
     }
     __syncwarp();
     if (nSteps) {
-      tr.kmer = kmer;
-      tr.count = count;
-      tr.dist = dsum;
-      cur[0] = tr;
+      if (act && b == 0) {
+        cur[t].kmer = kmer;
+        cur[t].count = count;
+        cur[t].dist = dsum;
+      }
+      __syncwarp();
       step = st;
       if (ctr) {
         if (border) ctr->steps_border += nSteps;
         else ctr->steps_inner += nSteps;
-        ctr->frontier_sum += nSteps;
-        ctr->lookups_walk += 4ull * nSteps;
+        ctr->frontier_sum += (u64)nSteps * nT;
+        ctr->lookups_walk += 4ull * nSteps * nT;
       }
     }
   }
@@ -875,6 +902,7 @@ class Corrector {
       const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(3 * k));
       RefView ref;
       ref.s = rd.s;
+      ref.w = rdw;
       if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = R.end + k - whichStart; }
       else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k - L.start; }
       if (!setup_search(pathMax)) return false;
@@ -906,7 +934,7 @@ class Corrector {
           table_next_counts(T, par.kmer, dirRight, k, cnt, col);
           if (ctr) ctr->lookups_walk += 4;
           u8 tag[4];
-          const StepBounds sb = step_bounds(par.count, P);
+          const StepBounds sb = step_bounds_tab(par.count, P, tabs);
           const int nt = tag_next_nodes(cnt, col, sb, P, complex_, tag);
           u32 nChildren = 0;
           for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
@@ -1214,6 +1242,7 @@ class Corrector {
       const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(2 * k));
       RefView ref;
       ref.s = rd.s;
+      ref.w = rdw;
       if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = rd.len - whichStart; }
       else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k; }
       const SeqView refv = view_of(ref);
@@ -1234,7 +1263,7 @@ class Corrector {
           table_next_counts(T, par.kmer, dirRight, k, cnt, col);
           if (ctr) ctr->lookups_walk += 4;
           u8 tag[4];
-          const StepBounds sb = step_bounds(par.count, P);
+          const StepBounds sb = step_bounds_tab(par.count, P, tabs);
           const int nt = tag_next_nodes(cnt, col, sb, P, complex_, tag);
           u32 nChildren = 0;
           for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
@@ -1347,6 +1376,25 @@ class Corrector {
     const u32 keepBytes = job.arena_bytes / 4;
     keep.init(job.arena, keepBytes & ~7u);
     scratch.init(job.arena + (keepBytes & ~7u), job.arena_bytes - (keepBytes & ~7u));
+    {  // 2-bit copy of the read for the scoring loops (N-free reads only)
+      const u32 nw = (rd.len + 31) / 32 + 1;
+      u64* pw = (u64*)keep.alloc(nw * 8);
+      if (!pw) return kReadOverflow;
+      bool hasN = false;
+      for (u32 wi = lane_id(); wi < nw; wi += lane_count()) {
+        u64 x = 0;
+        for (u32 j = 0; j < 32; ++j) {
+          const u32 idx = wi * 32 + j;
+          u32 c = (idx < rd.len) ? rd.code(idx) : 0u;
+          if (c > 3) { hasN = true; c = 0; }
+          x = (x << 2) | c;
+        }
+        pw[wi] = x;
+      }
+      hasN = warp_any(hasN);
+      warp_sync();
+      rdw = hasN ? nullptr : pw;
+    }
     // Read::reCoverage gate (Read.cpp:190, Q1: strictly greater)
     u32 nbIn = 0;
     for (u32 i = lane_id(); i < C; i += lane_count()) nbIn += (cov[i] > P.min_count) ? 1 : 0;

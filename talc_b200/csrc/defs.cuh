@@ -84,6 +84,8 @@ TALC_HD u32 lane_id() { return threadIdx.x & 31u; }
 TALC_HD u32 lane_count() { return 32u; }
 TALC_HD u32 warp_sum(u32 v) { return __reduce_add_sync(0xffffffffu, v); }
 TALC_HD u32 warp_max(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
+TALC_HD void warp_sync() { __syncwarp(); }
+TALC_HD bool warp_any(bool v) { return __any_sync(0xffffffffu, v) != 0; }
 TALC_HD u64 warp_sum64(u64 v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -95,6 +97,8 @@ inline u32 lane_count() { return 1; }
 inline u32 warp_sum(u32 v) { return v; }
 inline u32 warp_max(u32 v) { return v; }
 inline u64 warp_sum64(u64 v) { return v; }
+inline void warp_sync() {}
+inline bool warp_any(bool v) { return v; }
 #endif
 TALC_HD u8 code_char(u32 code) { return (u8)("ACGTN"[code]); }
 
@@ -146,12 +150,19 @@ struct ReadView {
 // RIGHT-ward walk and read[start - i] for a LEFT-ward walk.  Every reference string the
 // reference builds (anchor+gap+target, target+gap+anchor, anchor+border, border+anchor:
 // Explorer.cpp:925-938,1042-1053) is a contiguous slice of the raw read, so no copy is made.
+// When the read holds no N it is also available 2-bit packed (w != nullptr, same indexing as s): the scoring
+// loops then fetch a base with a shift and a mask instead of decoding ASCII.
 struct RefView {
   const u8* s;
+  const u64* w;
   i32 start;
   i32 step;  // +1 or -1
   u32 len;
-  TALC_HD u32 code(u32 i) const { return base_code(s[start + (i32)i * step]); }
+  TALC_HD u32 code(u32 i) const {
+    const u32 idx = (u32)(start + (i32)i * step);
+    if (w) return (u32)((w[idx >> 5] >> (62 - 2 * (idx & 31))) & 3ull);
+    return base_code(s[idx]);
+  }
 };
 
 // A trail's sequence in walk order, 2-bit packed (32 bases per u64, first base most significant).

@@ -342,7 +342,15 @@ __global__ void test_align_kernel(int op, const u8* a, const u64* aoff, const u8
   if (op == 0) r0 = -nw_distance(va, va.len, vb, vb.len, ar, nullptr);
   else if (op == 1) r0 = lcs_length(va, va.len, vb, vb.len, ar, nullptr);
   else if (op == 2) r0 = overlap_score(va, va.len, vb, vb.len, ar, nullptr);
-  else {
+  else if (op == 4) {  // raw X-drop: a = query segment, b = database segment, aux = score drop-off
+    DpStats ds;
+    ds.cells_xdrop = 0;
+    u32 er = 0, ec = 0;
+    xdrop_extend(va, 0, va.len, vb, 0, vb.len, aux, er, ec, ar, true, &ds);
+    r0 = (i32)er;
+    r1 = (i32)ec;
+    r2 = (i32)ds.cells_xdrop;
+  } else {
     const SeedExt e = seed_and_extension(va, vb, aux, aux2 != 0, K, ar, true, nullptr);
     r0 = (i32)e.ref_ext;
     r1 = (i32)e.cand_ext;
@@ -351,7 +359,7 @@ __global__ void test_align_kernel(int op, const u8* a, const u64* aoff, const u8
   }
   if (ar.overflow) r0 = INT32_MIN;
   if (lane == 0) {
-    if (op == 3) {
+    if (op >= 3) {
       result[4 * i + 0] = r0;
       result[4 * i + 1] = r1;
       result[4 * i + 2] = r2;
@@ -1006,11 +1014,11 @@ int talc_test_align(talc_ctx* c, int op, const uint8_t* a, const uint64_t* aOff,
                     uint32_t n, int aux, int aux2, int32_t* result) {
   if (!c || !n) return TALC_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
-  const u32 arenaBytes = 1u << 20;
+  const u32 arenaBytes = (op == 4) ? (256u << 10) : (1u << 20);
   u8 *dA, *dB, *dAr;
   u64 *dAo, *dBo;
   i32* dR;
-  const size_t rn = (size_t)n * (op == 3 ? 4 : 1);
+  const size_t rn = (size_t)n * (op >= 3 ? 4 : 1);
   CUDA_TRY(c, cudaMalloc((void**)&dA, aOff[n] + 1));
   CUDA_TRY(c, cudaMalloc((void**)&dB, bOff[n] + 1));
   CUDA_TRY(c, cudaMalloc((void**)&dAo, (size_t)(n + 1) * 8));

@@ -2,9 +2,11 @@
 // diffed against the oracle on a machine without a GPU.  TEST AID ONLY: nothing in the shipped
 // library links this file, and the product has no CPU path.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <string>
 #include <vector>
 
 #include "../../talc_b200/csrc/correct.cuh"
@@ -207,6 +209,151 @@ void emu_xdrop(const char* query_seg, const char* database_seg, int xdrop, int w
   u32 er = 0, ec = 0;
   xdrop_extend(bytes_view(query_seg, qn), 0, qn, bytes_view(database_seg, dn), 0, dn, xdrop, er, ec, A, wide != 0, nullptr);
   *ext_rows = er; *ext_cols = ec; *overflow = (int)A.overflow;
+}
+// Mirror of xdrop_extend_reg<S> (talc_b200/csrc/xdrop.cuh) with the warp's registers laid out as flat arrays
+// indexed by g = S*lane + i; shuffles become neighbour reads, warp reductions become loops.  It shares
+// xd_cell / xd_next_window / xd_finish with the device code, so fuzzing it against xdrop_extend_scalar
+// validates the band layout, the window updates and the end-position rules without a GPU.
+static void xdrop_reg_mirror(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen, int X,
+                             int S, u32& ext_rows, u32& ext_cols, u64* cells_out) {
+  const i32 cols = (i32)qlen + 1, rows = (i32)dlen + 1;
+  ext_rows = 0;
+  ext_cols = 0;
+  if (cells_out) *cells_out = 0;
+  if (rows == 1 || cols == 1) return;
+  const int G = 32 * S;
+  std::vector<i32> vE(G), vO(G), vOld(G, kXdU), nv(G);
+  std::vector<u32> qc(G), tc(G);
+  for (int g = 0; g < G; ++g) {
+    vE[g] = (g == 16 * S) ? 0 : kXdU;
+    vO[g] = ((g == 16 * S - 1) | (g == 16 * S)) ? (X >= 1 ? -1 : kXdU) : kXdU;
+    const i32 col = 1 - 16 * S + g, row = 1 + 16 * S - g;
+    qc[g] = (col >= 1 && col <= (i32)qlen) ? query.code(qoff + (u32)(col - 1)) : 6u;
+    tc[g] = (row >= 1 && row <= (i32)dlen) ? database.code(doff + (u32)(row - 1)) : 7u;
+  }
+  i32 minCol = 1, maxCol = 2, d = 1;
+  XdHist h = xd_hist_init();
+  u64 cells = 0;
+  bool lastOdd;
+  for (;;) {
+    ++d;
+    const i32 m = d >> 1;
+    h.push(minCol, maxCol);
+    {
+      const i32 cb = m - 16 * S;
+      const u32 qi = (u32)(m + 16 * S - 1);
+      const u32 nq = (qi < qlen) ? query.code(qoff + qi) : 6u;
+      i32 loC = INT32_MAX, hiC = INT32_MIN;
+      for (int g = 0; g < G; ++g) {
+        const i32 a = g ? vO[g - 1] : kXdU, b = vO[g], dg = vE[g];
+        vOld[g] = dg;
+        nv[g] = xd_cell(a, b, dg, qc[g] == tc[g], cb + g, d, X, minCol, maxCol, loC, hiC);
+      }
+      vE = nv;
+      cells += (u64)(maxCol - minCol);
+      xd_next_window(d, rows, cols, loC, hiC, minCol, maxCol);
+      for (int g = 0; g + 1 < G; ++g) qc[g] = qc[g + 1];
+      qc[G - 1] = nq;
+    }
+    if (!(minCol < maxCol)) { lastOdd = false; break; }
+    ++d;
+    h.push(minCol, maxCol);
+    {
+      const i32 cb = m + 1 - 16 * S;
+      const u32 ti = (u32)(m + 16 * S);
+      const u32 nt = (ti < dlen) ? database.code(doff + ti) : 7u;
+      i32 loC = INT32_MAX, hiC = INT32_MIN;
+      for (int g = 0; g < G; ++g) {
+        const i32 a = vE[g], b = (g + 1 < G) ? vE[g + 1] : kXdU, dg = vO[g];
+        vOld[g] = dg;
+        nv[g] = xd_cell(a, b, dg, qc[g] == tc[g], cb + g, d, X, minCol, maxCol, loC, hiC);
+      }
+      vO = nv;
+      cells += (u64)(maxCol - minCol);
+      xd_next_window(d, rows, cols, loC, hiC, minCol, maxCol);
+      for (int g = G - 1; g > 0; --g) tc[g] = tc[g - 1];
+      tc[0] = nt;
+    }
+    if (!(minCol < maxCol)) { lastOdd = true; break; }
+  }
+  if (cells_out) *cells_out = cells;
+  const i32 cb3 = xd_col_base(d, S), cb2 = xd_col_base(d - 1, S), cb1 = xd_col_base(d - 2, S);
+  auto pick = [&](const std::vector<i32>& v, i32 cb, i32 col) -> i32 {
+    const i32 g = col - cb;
+    return (g >= 0 && g < G) ? v[g] : kXdU;
+  };
+  auto at = [&](int which, i32 col) -> i32 {
+    if (which == 3) return lastOdd ? pick(vO, cb3, col) : pick(vE, cb3, col);
+    return lastOdd ? pick(vE, cb2, col) : pick(vO, cb2, col);
+  };
+  auto argmax1 = [&](i32 lo, i32 hi, i32& col) -> i32 {
+    i32 bv = kXdU;
+    col = INT32_MAX;
+    for (int g = 0; g < G; ++g) {
+      const i32 c = cb1 + g;
+      if (c >= lo && c <= hi && vOld[g] > bv) { bv = vOld[g]; col = c; }
+    }
+    return bv;
+  };
+  xd_finish(d, h, at, argmax1, ext_rows, ext_cols);
+}
+void emu_xdrop_reg(const char* query_seg, const char* database_seg, int xdrop, int S, uint64_t* ext_rows, uint64_t* ext_cols,
+                   uint64_t* cells) {
+  u32 qn = strlen(query_seg), dn = strlen(database_seg);
+  u32 er = 0, ec = 0;
+  u64 c = 0;
+  xdrop_reg_mirror(bytes_view(query_seg, qn), 0, qn, bytes_view(database_seg, dn), 0, dn, xdrop, S, er, ec, &c);
+  *ext_rows = er; *ext_cols = ec; *cells = c;
+}
+// built-in fuzzer: random related pairs, every admissible S; returns the number of disagreements with the scalar form
+int emu_xdrop_reg_fuzz(uint64_t seed, int n_cases, int max_len) {
+  u64 s = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  std::vector<u8> ar(1 << 24);
+  int bad = 0;
+  for (int t = 0; t < n_cases; ++t) {
+    const u32 an = 1 + rnd() % max_len;
+    std::string a(an, 'A'), b;
+    const int alpha = (rnd() % 4 == 0) ? 2 : 4;  // low-complexity pairs make long ties
+    for (u32 i = 0; i < an; ++i) a[i] = "ACGT"[rnd() % alpha];
+    const u32 errPermille = (u32)(rnd() % 300);
+    for (u32 i = 0; i < an; ++i) {
+      const u32 r = rnd() % 1000;
+      if (r < errPermille / 3) continue;                                  // deletion
+      if (r < 2 * errPermille / 3) { b.push_back("ACGT"[rnd() % alpha]); }  // substitution
+      else b.push_back(a[i]);
+      if (rnd() % 1000 < errPermille / 3) b.push_back("ACGT"[rnd() % alpha]);  // insertion
+    }
+    if (rnd() % 5 == 0) b.resize(rnd() % (b.size() + 1));
+    if (rnd() % 7 == 0) b += std::string(rnd() % 40, 'A');
+    if (rnd() % 50 == 0 && !a.empty()) a[rnd() % a.size()] = 'N';
+    if (b.empty()) b = "A";
+    const int X = (int)(rnd() % 12 == 0 ? rnd() % 270 : rnd() % 40) - 1;
+    const bool swap = rnd() & 1;
+    const std::string& q = swap ? b : a;
+    const std::string& db = swap ? a : b;
+    const u32 qoff = rnd() % 3, doff = rnd() % 3;
+    if (qoff >= q.size() || doff >= db.size()) continue;
+    Arena A; A.init(ar.data(), (u32)ar.size());
+    DpStats st; st.cells_xdrop = 0;
+    u32 er0 = 0, ec0 = 0;
+    const SeqView qv = bytes_view(q.data(), (u32)q.size()), dv = bytes_view(db.data(), (u32)db.size());
+    xdrop_extend_scalar(qv, qoff, (u32)q.size() - qoff, dv, doff, (u32)db.size() - doff, X, er0, ec0, A, true, &st);
+    for (int S : {1, 2, 4, 8}) {
+      if (X > 32 * S - 1) continue;
+      u32 er = 0, ec = 0;
+      u64 cells = 0;
+      xdrop_reg_mirror(qv, qoff, (u32)q.size() - qoff, dv, doff, (u32)db.size() - doff, X, S, er, ec, &cells);
+      if (er != er0 || ec != ec0 || cells != st.cells_xdrop) {
+        if (bad < 5)
+          fprintf(stderr, "xdrop mismatch S=%d X=%d q=%s db=%s qoff=%u doff=%u scalar=(%u,%u,%llu) reg=(%u,%u,%llu)\n", S, X,
+                  q.c_str(), db.c_str(), qoff, doff, er0, ec0, (unsigned long long)st.cells_xdrop, er, ec,
+                  (unsigned long long)cells);
+        ++bad;
+      }
+    }
+  }
+  return bad;
 }
 // getSeedAndExtension on walk-order strings (RIGHT as is; for LEFT pass reversed strings and right=0)
 void emu_seed_extend(const char* reference, const char* candidate, int xdrop, int right, uint32_t K, int32_t* ref_ext,

@@ -194,6 +194,43 @@ def test_alignment_primitives_on_device(api, case_c1):
             assert tuple(res[i]) == (re_, ce_, int(sc), int(stop)), (i, x)
 
 
+def test_xdrop_register_band_on_device(api, case_c1):
+    """The register-resident X-drop (csrc/xdrop.cuh, S = 1, 2, 4, 8 diagonals per lane, scalar beyond 255) against the
+    oracle's cell-by-cell restatement: end positions for every drop-off, sequence ends reached, N, low complexity."""
+    from oracle import pyoracle as po
+    t = _ctx(api, case_c1)
+    rng = np.random.default_rng(17)
+    qs, ds = [], []
+    for i in range(1500):
+        n = int(rng.integers(1, 30 if i % 3 == 0 else 400))
+        alpha = list(b"AC") if i % 5 == 0 else list(b"ACGT")
+        s = bytes(rng.choice(alpha, n).tolist())
+        rate = float(rng.random()) * 0.3
+        b = bytearray()
+        for ch in s:
+            u = rng.random()
+            if u < rate / 3:
+                continue
+            b.append(int(rng.choice(alpha)) if u < 2 * rate / 3 else ch)
+            if rng.random() < rate / 3:
+                b.append(int(rng.choice(alpha)))
+        b = bytes(b) or b"A"
+        if i % 4 == 0:
+            b = b[: int(rng.integers(1, len(b) + 1))]
+        if i % 11 == 0:
+            b += b"A" * int(rng.integers(0, 40))
+        if i % 37 == 0:
+            s = s[: n // 2] + b"N" + s[n // 2:]
+        if i % 2:
+            s, b = b, s
+        qs.append(s)
+        ds.append(b)
+    for x in (-1, 0, 1, 2, 3, 5, 8, 13, 21, 31, 32, 47, 63, 64, 100, 127, 128, 200, 255, 256, 300):
+        res = t.test_align(4, qs, ds, aux=x)
+        for i, (q, d) in enumerate(zip(qs, ds)):
+            assert (int(res[i][0]), int(res[i][1])) == po.xdrop(q, d, False, x), (i, x, q, d)
+
+
 def test_std_sort_replica_on_device(api, case_c1):
     from oracle import pyoracle as po
     t = _ctx(api, case_c1)

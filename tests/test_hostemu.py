@@ -101,6 +101,15 @@ def test_primitives_random():
             assert (er.value, ec.value) == po.xdrop(b, a, False, x) and ov.value == 0
 
 
+def test_xdrop_register_band_mirror_matches_scalar():
+    """csrc/xdrop.cuh keeps the X-drop band in registers, S diagonals per lane.  Its host mirror (same cell,
+    window-update and end-position helpers, registers as flat arrays) must reproduce the cell-by-cell routine --
+    end position AND number of cells visited -- for every S that admits the drop-off."""
+    L = pyemu.lib()
+    for seed, (n, max_len) in enumerate([(40000, 12), (40000, 60), (8000, 400)]):
+        assert L.emu_xdrop_reg_fuzz(1000 + seed, n, max_len) == 0
+
+
 def test_std_sort_replica_matches_libstdcxx():
     L = pyemu.lib()
     rng = np.random.default_rng(5)
