@@ -39,11 +39,67 @@ struct DpStats {  // algorithmic DP cell updates (SURVEY 8d "integer work")
   u64 cells_nw, cells_lcs, cells_ovl, cells_xdrop;
 };
 
+// ---- match masks from 2-bit packed sequences without a per-row loop
+// even-position bits of x (0, 2, .., 62) gathered into the low 32 bits
+TALC_HD u32 compress_even(u64 x) {
+  x &= 0x5555555555555555ull;
+  x = (x | (x >> 1)) & 0x3333333333333333ull;
+  x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0full;
+  x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull;
+  x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
+  x = (x | (x >> 16));
+  return (u32)x;
+}
+TALC_HD u64 bit_reverse64(u64 x) {
+#if defined(__CUDA_ARCH__)
+  return __brevll(x);
+#else
+  x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+  x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+  x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+  return __builtin_bswap64(x);
+#endif
+}
+// 32 packed bases starting at base index i, first base most significant; words beyond lastWord are not touched
+TALC_HD u64 packed_chunk32(const u64* w, u32 i, u32 lastWord) {
+  const u32 wi = i >> 5, off = 2 * (i & 31);
+  if (wi > lastWord) return 0;
+  u64 v = w[wi] << off;
+  if (off && wi + 1 <= lastWord) v |= w[wi + 1] >> (64 - off);
+  return v;
+}
+
 // match masks of pattern rows [64*block, 64*block+64) for the five symbols (N matches N)
 TALC_HDN void build_peq(const SeqView& pat, u32 pn, u32 block, u64 peq[5]) {
   peq[0] = peq[1] = peq[2] = peq[3] = peq[4] = 0;
   const u32 r0 = block * 64;
   const u32 r1 = (pn - r0 < 64u) ? pn : r0 + 64;
+  if (pat.w) {
+    // the n rows are n consecutive packed bases, ascending (step +1) or descending (step -1): split the low and
+    // the high bit of every base into two n-bit masks, then the four symbols are the four AND combinations
+    const u32 n = r1 - r0;
+    const u32 first = (u32)(pat.start + (i32)r0 * pat.step), last = (u32)(pat.start + (i32)(r1 - 1) * pat.step);
+    const u32 lowIdx = first < last ? first : last, highIdx = first < last ? last : first;
+    const u32 lastWord = highIdx >> 5;
+    const u64 c0 = packed_chunk32(pat.w, lowIdx, lastWord);
+    const u64 c1 = (n > 32) ? packed_chunk32(pat.w, lowIdx + 32, lastWord) : 0ull;
+    // bit 63-j of lo/hi <-> base lowIdx + j
+    u64 lo = ((u64)compress_even(c0) << 32) | (u64)compress_even(c1);
+    u64 hi = ((u64)compress_even(c0 >> 1) << 32) | (u64)compress_even(c1 >> 1);
+    if (pat.step > 0) {  // row r0+j <-> base lowIdx+j
+      lo = bit_reverse64(lo);
+      hi = bit_reverse64(hi);
+    } else {             // row r0+t <-> base lowIdx + (n-1-t)
+      lo >>= (64 - n);
+      hi >>= (64 - n);
+    }
+    const u64 rowmask = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
+    peq[0] = ~hi & ~lo & rowmask;
+    peq[1] = ~hi & lo & rowmask;
+    peq[2] = hi & ~lo & rowmask;
+    peq[3] = hi & lo & rowmask;
+    return;
+  }
   for (u32 r = r0; r < r1; ++r) peq[pat.code(r)] |= 1ull << (r - r0);
 }
 
@@ -51,8 +107,8 @@ TALC_HDN void build_peq(const SeqView& pat, u32 pn, u32 block, u64 peq[5]) {
 TALC_HDN int nw_distance_scalar(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   // pattern (rows, bit-parallel) = the shorter one, text (columns) = the longer one
   const bool a_is_pat = an <= bn;
-  const SeqView& pat = a_is_pat ? a : b;
-  const SeqView& txt = a_is_pat ? b : a;
+  const SeqView pat = a_is_pat ? a : b;
+  const SeqView txt = a_is_pat ? b : a;
   const u32 pn = a_is_pat ? an : bn;
   const u32 tn = a_is_pat ? bn : an;
   if (st) st->cells_nw += (u64)an * bn;
@@ -97,8 +153,8 @@ TALC_HDN int nw_distance_scalar(const SeqView& a, u32 an, const SeqView& b, u32 
 // length of the longest common subsequence of a[0..an) and b[0..bn) (both non-empty)
 TALC_HDN int lcs_length_scalar(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   const bool a_is_pat = an <= bn;
-  const SeqView& pat = a_is_pat ? a : b;
-  const SeqView& txt = a_is_pat ? b : a;
+  const SeqView pat = a_is_pat ? a : b;
+  const SeqView txt = a_is_pat ? b : a;
   const u32 pn = a_is_pat ? an : bn;
   const u32 tn = a_is_pat ? bn : an;
   if (st) st->cells_lcs += (u64)an * bn;
@@ -143,11 +199,14 @@ TALC_HDN int lcs_length_scalar(const SeqView& a, u32 an, const SeqView& b, u32 b
 // or its addition carry (LCS) to lane L+1 with one shuffle.  More than 32 blocks are processed in stripes with
 // the boundary deltas parked in the scratch arena, exactly like the scalar form does for every block.
 __device__ __noinline__ int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
-  const bool a_is_pat = an <= bn;
+  // rows (bit-parallel, 64 per lane) = the LONGER sequence while it fits one stripe of 32 lanes: the systolic
+  // pipeline then runs for shorter + blocks steps instead of longer + blocks; beyond 2048 the shorter one again
+  const u32 longer = an >= bn ? an : bn;
+  if (longer <= 64) return nw_distance_scalar(a, an, b, bn, ar, st);
+  const bool a_is_pat = (longer <= 2048) ? (an >= bn) : (an <= bn);
   const u32 pn = a_is_pat ? an : bn;
-  if (pn <= 64) return nw_distance_scalar(a, an, b, bn, ar, st);
-  const SeqView& pat = a_is_pat ? a : b;
-  const SeqView& txt = a_is_pat ? b : a;
+  const SeqView pat = a_is_pat ? a : b;  // by value: the fields stay in registers
+  const SeqView txt = a_is_pat ? b : a;
   const u32 tn = a_is_pat ? bn : an;
   if (st) st->cells_nw += (u64)an * bn;
   const u32 lane = threadIdx.x & 31u;
@@ -212,11 +271,12 @@ __device__ __noinline__ int nw_distance(const SeqView& a, u32 an, const SeqView&
 }
 
 __device__ __noinline__ int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
-  const bool a_is_pat = an <= bn;
+  const u32 longer = an >= bn ? an : bn;
+  if (longer <= 64) return lcs_length_scalar(a, an, b, bn, ar, st);
+  const bool a_is_pat = (longer <= 2048) ? (an >= bn) : (an <= bn);  // see nw_distance
   const u32 pn = a_is_pat ? an : bn;
-  if (pn <= 64) return lcs_length_scalar(a, an, b, bn, ar, st);
-  const SeqView& pat = a_is_pat ? a : b;
-  const SeqView& txt = a_is_pat ? b : a;
+  const SeqView pat = a_is_pat ? a : b;
+  const SeqView txt = a_is_pat ? b : a;
   const u32 tn = a_is_pat ? bn : an;
   if (st) st->cells_lcs += (u64)an * bn;
   const u32 lane = threadIdx.x & 31u;
@@ -306,52 +366,59 @@ TALC_HDN int overlap_score_scalar(const SeqView& ref, u32 rn, const SeqView& can
 }
 
 #if defined(__CUDA_ARCH__)
-// Device form: one DP row at a time, 32 columns per pass.  The vertical and diagonal terms of a cell only need
-// the previous row; the horizontal term v[j] = max(t[j], v[j-1] - 2) unrolls to max_{l<=j}(t[l] + 2l) - 2j,
-// a prefix maximum, i.e. one five-step warp scan per pass.  Integer arithmetic, identical to the scalar form.
-__device__ __noinline__ int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {
+// Device form: a skewed wavefront over stripes of 32 columns.  Lane l owns column j0+l of the stripe and works on
+// row t-l at time t, so the cell to its left (lane l-1, same row) was computed one step earlier and arrives by one
+// shuffle; the diagonal term is the left value of the step before, the vertical term the lane's own previous
+// value.  The reference character of a row travels down the lanes with the wavefront.  The last column of a
+// stripe is parked in the arena (one value per row) and feeds lane 0 of the next stripe; lane 0 runs 31 rows
+// ahead of lane 31, so the same buffer is read and overwritten in place.  Same integer recurrence as the scalar
+// form, ~1 warp instruction per cell instead of a prefix-maximum scan per row.
+__device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const SeqView& candArg, u32 cn, Arena& ar,
+                                          DpStats* st) {
+  const SeqView ref = refArg, cand = candArg;  // by value: the fields stay in registers
   if (st) st->cells_ovl += (u64)rn * cn;
   const u32 lane = threadIdx.x & 31u;
   const u32 mk = ar.mark();
-  i32* row = (i32*)ar.alloc((cn + 1) * 4);
-  if (!row) return 0;
-  for (u32 j = lane; j <= cn; j += 32) row[j] = 0;
+  i32* colBuf = (i32*)ar.alloc((rn + 1) * 4);  // S[i][j0-1] for the stripe that starts at column j0
+  if (!colBuf) return 0;
+  for (u32 i = lane; i <= rn; i += 32) colBuf[i] = 0;  // column 0: leading gaps are free
   __syncwarp();
-  const i32 NEG = -(1 << 28);
-  for (u32 i = 0; i < rn; ++i) {
-    const u32 rc = ref.code(i);
-    i32 leftNew = 0;  // S[i][0]
-    i32 leftOld = 0;  // S[i-1][0]
-    for (u32 j0 = 1; j0 <= cn; j0 += 32) {
-      const u32 j = j0 + lane;
-      const bool act = j <= cn;
-      const i32 up = act ? row[j] : NEG;
-      i32 diag = __shfl_up_sync(0xffffffffu, up, 1);
-      if (lane == 0) diag = leftOld;
-      i32 t = NEG;
-      if (act) {
-        const i32 d = diag + ((rc == cand.code(j - 1)) ? 4 : -3);
-        const i32 u = up - 2;
-        t = d > u ? d : u;
+  int result = 0;
+  for (u32 j0 = 1; j0 <= cn; j0 += 32) {
+    const u32 j = j0 + lane;
+    const bool act = j <= cn;
+    const u32 nl = (cn - j0 + 1 < 32u) ? (cn - j0 + 1) : 32u;  // columns in this stripe
+    const bool park = (j0 + 32 <= cn) && (lane == 31);          // a further stripe follows
+    const u32 cc = act ? cand.code(j - 1) : 9u;
+    i32 up = 0, diag = 0, vPrev = 0;  // S[0][j] = S[0][j-1] = 0
+    u32 rcPrev = 8u;
+#pragma unroll 1
+    for (u32 t = 1; t <= rn + nl - 1; ++t) {
+      i32 left = __shfl_up_sync(0xffffffffu, vPrev, 1);
+      u32 rc = __shfl_up_sync(0xffffffffu, rcPrev, 1);
+      if (lane == 0) {
+        const bool in = t <= rn;
+        rc = in ? ref.code(t - 1) : 8u;
+        left = in ? colBuf[t] : 0;
       }
-      i32 a = t + 2 * (i32)j;  // prefix maximum of t[l] + 2l
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const i32 other = __shfl_up_sync(0xffffffffu, a, o);
-        if ((int)lane >= o) a = a > other ? a : other;
+      const u32 i = t - lane;  // wraps for t < lane: fails the range test below
+      i32 v = 0;
+      if (act && i >= 1 && i <= rn) {
+        const i32 d = diag + ((rc == cc) ? 4 : -3);
+        const i32 g = (up > left ? up : left) - 2;
+        v = d > g ? d : g;
+        diag = left;
+        up = v;
+        if (park) colBuf[i] = v;
       }
-      const i32 fromLeft = leftNew + 2 * (i32)(j0 - 1);
-      i32 v = (a > fromLeft ? a : fromLeft) - 2 * (i32)j;
-      if (act) row[j] = v;
-      leftOld = __shfl_sync(0xffffffffu, up, 31);
-      leftNew = __shfl_sync(0xffffffffu, v, 31);
+      vPrev = v;
+      rcPrev = rc;
     }
+    if (j0 + 32 > cn) result = __shfl_sync(0xffffffffu, up, cn - j0);
     __syncwarp();
   }
-  const int res = row[cn];
-  __syncwarp();
   ar.release(mk);
-  return res;
+  return result;
 }
 #else
 inline int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {

@@ -619,6 +619,7 @@ class Corrector {
 
 
 #if defined(__CUDA_ARCH__)
+  static __device__ __noinline__ double sqrt_cold(u32 c) { return sqrt((double)c); }  // counts beyond the table: rare
   // The fast path on the device, for a frontier of 1..7 trails (two or three trails walking side by side
   // through a variant or an isoform bubble is the common multi-trail case: ~30% of all inner steps).
   // Lane l serves trail l/4 and successor base l%4: all successors of all trails are probed side by side, a
@@ -630,8 +631,9 @@ class Corrector {
   // kind of step ends the run *before* the step; the general code then takes that step in full.
   __device__ __noinline__ void fast_walk(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border) {
     const u32 nT = nCur;
-    if (nT == 0 || nT > 7 || nT > P.max_branches) return;
+    if (nT == 0 || nT > 7 || nT > P.max_branches || nAims > 32) return;
     const u32 lane = threadIdx.x & 31u;
+    const u64 myAim = (!border && lane < nAims) ? aims[lane].kmer : ~0ull;  // ~0 is not a k-mer (<= 60 bits)
     const u32 t = lane >> 2, b = lane & 3u;
     const bool act = t < nT;
     const u32 k = P.K;
@@ -688,10 +690,10 @@ class Corrector {
       if (__ballot_sync(0xffffffffu, act && child < 0)) break;  // dead end or branching somewhere: general step
       const u32 childCnt = __shfl_sync(0xffffffffu, cnt, grp + (u32)(child < 0 ? 0 : child));
       const u64 ck = kmer_next(kmer, (u32)(child < 0 ? 0 : child), right, k);
-      if (!border) {  // aim reached by any trail: the general step records the bridge
+      if (!border) {  // aim reached by any trail: the general step records the bridge (one aim k-mer per lane)
         bool aim = false;
-        if (act)
-          for (u32 a = b; a < nAims; a += 4) aim |= (aims[a].kmer == ck);
+#pragma unroll 1
+        for (u32 q = 0; q < nT; ++q) aim |= (myAim == __shfl_sync(0xffffffffu, ck, 4 * q));
         if (__ballot_sync(0xffffffffu, aim)) break;
       }
       // ---- cycle test of every trail against its own sequence, one window per lane
@@ -717,8 +719,10 @@ class Corrector {
       // ---- commit the step: one base per trail
       if (act && b == 0) path_set(w, plen, (u32)child);
       __syncwarp();
-      const double sq = (count < mt.n) ? mt.sq[count] : sqrt((double)count);
-      dsum = dsum + fabs((double)count - (double)childCnt) / sq;
+      if (count != childCnt) {  // a zero numerator adds +0.0 (and would take the slow path of the double division)
+        const double sq = (count < mt.n) ? mt.sq[count] : sqrt_cold(count);
+        dsum = dsum + fabs((double)count - (double)childCnt) / sq;
+      }
       if (!right) rkmer = ((rkmer << 2) | (u64)(child < 0 ? 0 : child)) & kmask;
       kmer = ck;
       count = childCnt;

@@ -109,8 +109,9 @@ TALC_HD i32 xd_cell(i32 a, i32 b, i32 dg, bool match, i32 col, i32 d, i32 X, i32
 
 #if defined(__CUDA_ARCH__)
 template <int S>
-__device__ __noinline__ void xdrop_extend_reg(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff,
-                                              u32 dlen, int X, u32& ext_rows, u32& ext_cols, DpStats* st) {
+__device__ __noinline__ void xdrop_extend_reg(const SeqView& queryArg, u32 qoff, u32 qlen, const SeqView& databaseArg,
+                                              u32 doff, u32 dlen, int X, u32& ext_rows, u32& ext_cols, DpStats* st) {
+  const SeqView query = queryArg, database = databaseArg;  // by value: the fields stay in registers
   const i32 lane = (i32)(threadIdx.x & 31u);
   const i32 cols = (i32)qlen + 1, rows = (i32)dlen + 1;
   ext_rows = 0;
