@@ -328,12 +328,97 @@ __device__ __noinline__ int lcs_length(const SeqView& a, u32 an, const SeqView& 
   ar.release(mk);
   return lcs;
 }
+// Edit distance and LCS length of the same pair in ONE systolic pass (Trajectory::scoreSequence computes both,
+// Trajectory.cpp:239-243): the text stream, the match masks and the pipeline are shared, the two recurrences are
+// independent dependency chains that fill each other's issue slots, and the two hand-over values travel in one
+// shuffle.  Falls back to the two separate routines when a stripe of 32 blocks does not hold the longer sequence.
+__device__ __noinline__ int nw_lcs_fused(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st, int& lcsOut) {
+  const u32 longer = an >= bn ? an : bn;
+  if (longer <= 64 || longer > 2048) {
+    const int d = nw_distance(a, an, b, bn, ar, st);
+    lcsOut = lcs_length(a, an, b, bn, ar, st);
+    return d;
+  }
+  const bool a_is_pat = an >= bn;
+  const u32 pn = a_is_pat ? an : bn;
+  const SeqView pat = a_is_pat ? a : b;
+  const SeqView txt = a_is_pat ? b : a;
+  const u32 tn = a_is_pat ? bn : an;
+  if (st) {
+    st->cells_nw += (u64)an * bn;
+    st->cells_lcs += (u64)an * bn;
+  }
+  const u32 lane = threadIdx.x & 31u;
+  const u32 nblocks = (pn + 63) / 64;  // <= 32
+  const bool haveBlk = lane < nblocks;
+  u64 peq[5] = {0, 0, 0, 0, 0};
+  if (haveBlk) build_peq(pat, pn, lane, peq);
+  const bool last = haveBlk && (lane + 1 == nblocks);
+  const u32 rows = last ? (pn - lane * 64) : 64;
+  const u32 top = rows - 1;
+  u64 Pv = ~0ull, Mv = 0, V = ~0ull;
+  u32 handPrev = 1u;  // (hout + 1) | (cout << 2)
+  u32 cPrev = 4;
+  int acc = 0;
+  __syncwarp();
+#pragma unroll 1
+  for (u32 t = 0; t < tn + nblocks - 1; ++t) {
+    u32 hand = __shfl_up_sync(0xffffffffu, handPrev, 1);
+    u32 c = __shfl_up_sync(0xffffffffu, cPrev, 1);
+    if (lane == 0) {
+      c = (t < tn) ? txt.code(t) : 4u;
+      hand = 2u;  // hin = +1 (first row of the distance matrix), no carry
+    }
+    const bool valid = haveBlk && (t >= lane) && (t - lane < tn);
+    u32 handOut = 1u;
+    if (valid) {
+      const u64 M = peq[c];
+      const int hin = (int)(hand & 3u) - 1;
+      // Myers / Hyyro
+      u64 Eq = M;
+      const u64 hneg = (hin < 0) ? 1ull : 0ull;
+      const u64 Xv = Eq | Mv;
+      Eq |= hneg;
+      const u64 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+      u64 Ph = Mv | ~(Xh | Pv);
+      u64 Mh = Pv & Xh;
+      const int hout = (int)((Ph >> top) & 1ull) - (int)((Mh >> top) & 1ull);
+      Ph <<= 1;
+      Mh <<= 1;
+      Mh |= hneg;
+      Ph |= (hin > 0) ? 1ull : 0ull;
+      Pv = Mh | ~(Xv | Ph);
+      Mv = Ph & Xv;
+      if (last) acc += hout;
+      // bit-parallel LCS
+      const u64 U = V & M;
+      const u64 tt = V + U;
+      const u64 sum = tt + (u64)(hand >> 2);
+      const u32 cout = (u32)(tt < V) | (u32)(sum < tt);
+      V = sum | (V & ~M);
+      handOut = (u32)(hout + 1) | (cout << 2);
+    }
+    handPrev = handOut;
+    cPrev = c;
+  }
+  const int score = (int)pn + __shfl_sync(0xffffffffu, acc, nblocks - 1);
+  int z = 0;
+  if (haveBlk) z = __popcll(~V & ((rows == 64) ? ~0ull : ((1ull << rows) - 1ull)));
+  lcsOut = (int)__reduce_add_sync(0xffffffffu, (unsigned)z);
+  __syncwarp();
+  return score;
+}
 #else
 inline int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   return nw_distance_scalar(a, an, b, bn, ar, st);
 }
 inline int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   return lcs_length_scalar(a, an, b, bn, ar, st);
+}
+inline int nw_lcs_fused(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st, int& lcsOut) {
+  const int d = nw_distance_scalar(a, an, b, bn, ar, st);
+  lcsOut = lcs_length_scalar(a, an, b, bn, ar, st);
+  return d;
 }
 #endif
 
@@ -375,8 +460,12 @@ TALC_HDN int overlap_score_scalar(const SeqView& ref, u32 rn, const SeqView& can
 // form, ~1 warp instruction per cell instead of a prefix-maximum scan per row.
 __device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const SeqView& candArg, u32 cn, Arena& ar,
                                           DpStats* st) {
-  const SeqView ref = refArg, cand = candArg;  // by value: the fields stay in registers
   if (st) st->cells_ovl += (u64)rn * cn;
+  // the recurrence and its all-zero first row and column are symmetric in the two sequences: put on the lanes
+  // the one that wastes fewer of them (stripes x steps per stripe)
+  const bool swap = (u64)((rn + 31) / 32) * (cn + 31) < (u64)((cn + 31) / 32) * (rn + 31);
+  const SeqView ref = swap ? candArg : refArg, cand = swap ? refArg : candArg;  // by value: fields in registers
+  if (swap) { const u32 x = rn; rn = cn; cn = x; }
   const u32 lane = threadIdx.x & 31u;
   const u32 mk = ar.mark();
   i32* colBuf = (i32*)ar.alloc((rn + 1) * 4);  // S[i][j0-1] for the stripe that starts at column j0

@@ -660,10 +660,16 @@ class Corrector {
       u32 cnt = 0, col = 0;
       if (act) {
         const u64 key = kmer_next(kmer, b, right, k);
+        // home sector and the next one of the probe sequence are fetched together: with 3 of 4 successors absent
+        // from the graph a probe usually ends at an empty slot, and ~15% of those lie one sector further on --
+        // a second dependent DRAM round trip on the critical path of the walk unless it is already in flight
         const u64 bucket = hash_kmer(key) & tv.mask & ~1ull;
-        const Slot s0 = load_slot(tv.slots + bucket);
-        const Slot s1 = load_slot(tv.slots + bucket + 1);
-        if (sector_resolve(s0, s1, key, cnt, col) < 0) table_probe_from(tv, bucket, key, cnt, col);
+        const u64 bucket2 = (bucket + 2) & tv.mask;
+        Slot s0, s1, s2, s3;
+        load_sector(tv.slots + bucket, s0, s1);
+        load_sector(tv.slots + bucket2, s2, s3);
+        if (sector_resolve(s0, s1, key, cnt, col) < 0)
+          if (sector_resolve(s2, s3, key, cnt, col) < 0) table_probe_from(tv, bucket2, key, cnt, col);
       }
       const u32 mAll = __ballot_sync(0xffffffffu, cnt >= prm.min_count);
       const u32 m = (mAll >> grp) & 0xFu;
@@ -987,8 +993,8 @@ class Corrector {
               b.leftAnchor = dirRight ? whichStart : aimPos;
               b.rightAnchor = dirRight ? aimPos : whichStart;
               const SeqView pv = view_of_path(slot_ptr(ch.slot), clen);
-              b.score = -nw_distance(refv, ref.len, pv, clen, scratch, &dps);
-              const int lcs = lcs_length(refv, ref.len, pv, clen, scratch, &dps);
+              int lcs = 0;
+              b.score = -nw_lcs_fused(refv, ref.len, pv, clen, scratch, &dps, lcs);
               b.idscore = (double)lcs / (double)(ref.len > clen ? ref.len : clen);
               // cutAnchors INNER (Trajectory.cpp:176-197), limit = RIGHT.end
               b.ok = true;

@@ -43,8 +43,21 @@ __device__ __forceinline__ Slot load_slot(const Slot* p) {
   s.colour = v.w;
   return s;
 }
+// one 32-byte sector = the two slots of a probe step, fetched by ONE 256-bit read-only load (sm_100a);
+// volatile keeps the load where it is written: the callers issue all their sector loads before they look at any
+__device__ __forceinline__ void load_sector(const Slot* p, Slot& a, Slot& b) {
+  u64 x0, x1, x2, x3;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x0), "=l"(x1), "=l"(x2), "=l"(x3) : "l"(p));
+  a.key = x0;
+  a.count = (u32)x1;
+  a.colour = (u32)(x1 >> 32);
+  b.key = x2;
+  b.count = (u32)x3;
+  b.colour = (u32)(x3 >> 32);
+}
 #else
 inline Slot load_slot(const Slot* p) { return *p; }
+inline void load_sector(const Slot* p, Slot& a, Slot& b) { a = p[0]; b = p[1]; }
 #endif
 
 // resolve one key against its already-fetched home sector; returns 1 hit, 0 definite miss, -1 keep probing
@@ -60,8 +73,8 @@ TALC_HD int sector_resolve(const Slot& s0, const Slot& s1, u64 key, u32& count, 
 TALC_HDN bool table_probe_from(const TableView& t, u64 b, u64 key, u32& count, u32& colour) {
   for (;;) {
     b = (b + 2) & t.mask;
-    const Slot s0 = load_slot(t.slots + b);
-    const Slot s1 = load_slot(t.slots + b + 1);
+    Slot s0, s1;
+    load_sector(t.slots + b, s0, s1);
     const int r = sector_resolve(s0, s1, key, count, colour);
     if (r >= 0) return r == 1;
   }
@@ -70,8 +83,8 @@ TALC_HDN bool table_probe_from(const TableView& t, u64 b, u64 key, u32& count, u
 // point look-up: (count, colour) or (0,0) when absent (Jellyfish.cpp:317-318,492-493)
 TALC_HD bool table_lookup(const TableView& t, u64 key, u32& count, u32& colour) {
   const u64 b = hash_kmer(key) & t.mask & ~1ull;
-  const Slot s0 = load_slot(t.slots + b);
-  const Slot s1 = load_slot(t.slots + b + 1);
+  Slot s0, s1;
+  load_sector(t.slots + b, s0, s1);
   const int r = sector_resolve(s0, s1, key, count, colour);
   if (r >= 0) return r == 1;
   return table_probe_from(t, b, key, count, colour);
@@ -88,10 +101,7 @@ TALC_HDN void table_next_counts(const TableView& t, u64 kmer, bool right, u32 K,
     b[i] = hash_kmer(key[i]) & t.mask & ~1ull;
   }
 #pragma unroll
-  for (u32 i = 0; i < 4; ++i) {
-    s0[i] = load_slot(t.slots + b[i]);
-    s1[i] = load_slot(t.slots + b[i] + 1);
-  }
+  for (u32 i = 0; i < 4; ++i) load_sector(t.slots + b[i], s0[i], s1[i]);
 #pragma unroll
   for (u32 i = 0; i < 4; ++i) {
     const int r = sector_resolve(s0[i], s1[i], key[i], cnt[i], col[i]);
@@ -111,10 +121,7 @@ TALC_HD void table_next_issue(const TableView& t, u64 kmer, bool right, u32 K, N
     q.b[i] = hash_kmer(q.key[i]) & t.mask & ~1ull;
   }
 #pragma unroll
-  for (u32 i = 0; i < 4; ++i) {
-    q.s0[i] = load_slot(t.slots + q.b[i]);
-    q.s1[i] = load_slot(t.slots + q.b[i] + 1);
-  }
+  for (u32 i = 0; i < 4; ++i) load_sector(t.slots + q.b[i], q.s0[i], q.s1[i]);
 }
 TALC_HD void table_next_resolve(const TableView& t, const NextProbe& q, u32 cnt[4], u32 col[4]) {
 #pragma unroll

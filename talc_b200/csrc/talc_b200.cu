@@ -157,10 +157,7 @@ __global__ void __launch_bounds__(256) coverage_kernel(TableView tv, u32 K, cons
 #pragma unroll
       for (u32 q = 0; q < 4; ++q) {
         b[q] = hash_kmer(kms[q]) & tv.mask & ~1ull;
-        if ((okm >> q) & 1u) {
-          s0[q] = load_slot(tv.slots + b[q]);
-          s1[q] = load_slot(tv.slots + b[q] + 1);
-        }
+        if ((okm >> q) & 1u) load_sector(tv.slots + b[q], s0[q], s1[q]);
       }
 #pragma unroll
       for (u32 q = 0; q < 4; ++q) {
@@ -212,8 +209,10 @@ struct CorrectArgs {
 // never diverges (a thread-per-read mapping serialises: the threads of a warp drift onto different code
 // paths and each one then pays its own chain of HBM latencies alone).  Lanes share the warp's scratch
 // slice; identical stores to identical addresses are benign; side effects on global state are lane 0's.
+// Residency: the per-read pipeline is ~0.5 MB of SASS and every warp sits in a different part of it, so beyond
+// two warps per SM sub-partition the instruction caches thrash and throughput stops scaling (profiles/r01_icache_*).
 #ifndef TALC_MIN_BLOCKS
-#define TALC_MIN_BLOCKS 4
+#define TALC_MIN_BLOCKS 2
 #endif
 template <bool WIDE>
 __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) correct_kernel(CorrectArgs A) {
@@ -342,7 +341,11 @@ __global__ void test_align_kernel(int op, const u8* a, const u64* aoff, const u8
   if (op == 0) r0 = -nw_distance(va, va.len, vb, vb.len, ar, nullptr);
   else if (op == 1) r0 = lcs_length(va, va.len, vb, vb.len, ar, nullptr);
   else if (op == 2) r0 = overlap_score(va, va.len, vb, vb.len, ar, nullptr);
-  else if (op == 4) {  // raw X-drop: a = query segment, b = database segment, aux = score drop-off
+  else if (op == 5) {  // fused distance + LCS
+    int l = 0;
+    r0 = -nw_lcs_fused(va, va.len, vb, vb.len, ar, nullptr, l);
+    r1 = l;
+  } else if (op == 4) {  // raw X-drop: a = query segment, b = database segment, aux = score drop-off
     DpStats ds;
     ds.cells_xdrop = 0;
     u32 er = 0, ec = 0;

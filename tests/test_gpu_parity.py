@@ -167,10 +167,12 @@ def test_alignment_primitives_on_device(api, case_c1):
     nw = t.test_align(0, a_list, b_list)
     lcs = t.test_align(1, a_list, b_list)
     ovl = t.test_align(2, a_list, b_list)
+    fused = t.test_align(5, a_list, b_list)
     for i, (a, b) in enumerate(zip(a_list, b_list)):
         assert nw[i] == po.nw(a, b)
         assert lcs[i] == po.lcs(a, b)
         assert ovl[i] == po.overlap(a, b, True)
+        assert (int(fused[i][0]), int(fused[i][1])) == (nw[i], lcs[i])
     # seed-and-extension (X-drop end positions + NW of the extensions), both directions
     k = case.cfg.k
     refs, cands = [], []
