@@ -17,23 +17,27 @@
 
 namespace talc {
 
-// a slice of the read in walk order (packed when the read holds no N, else raw bytes) or a packed trail:
-// element i is base (start + i*step) of w (2-bit packed) when w != nullptr, else of s (ASCII)
+// a slice of the packed read in walk order, or a packed trail: element i is base (start + i*step) of w,
+// 2 bits per base (lg = 5) or 4 bits per base (lg = 4, reads that hold an N)
 struct SeqView {
-  const u8* s;
+  const u64* w;
   i32 start;
   i32 step;
-  const u64* w;
   u32 len;
-  TALC_HD u32 code(u32 i) const {
-    const u32 idx = (u32)(start + (i32)i * step);
-    if (w) return (u32)((w[idx >> 5] >> (62 - 2 * (idx & 31))) & 3ull);
-    return base_code(s[idx]);
-  }
+  u32 lg;
+  TALC_HD u32 code(u32 i) const { return packed_code(w, (u32)(start + (i32)i * step), lg); }
 };
-TALC_HD SeqView view_of(const RefView& r) { SeqView v; v.s = r.s; v.start = r.start; v.step = r.step; v.w = r.w; v.len = r.len; return v; }
-TALC_HD SeqView view_of(const PathView& p) { SeqView v; v.s = nullptr; v.start = 0; v.step = 1; v.w = p.w; v.len = p.len; return v; }
-TALC_HD SeqView view_of_path(const u64* w, u32 len) { SeqView v; v.s = nullptr; v.start = 0; v.step = 1; v.w = w; v.len = len; return v; }
+TALC_HD SeqView view_of(const RefView& r) { SeqView v; v.w = r.w; v.start = r.start; v.step = r.step; v.len = r.len; v.lg = r.lg; return v; }
+TALC_HD SeqView view_of(const PathView& p) { SeqView v; v.w = p.w; v.start = 0; v.step = 1; v.len = p.len; v.lg = 5; return v; }
+TALC_HD SeqView view_of_path(const u64* w, u32 len) { SeqView v; v.w = w; v.start = 0; v.step = 1; v.len = len; v.lg = 5; return v; }
+// packs ASCII into the 4-bit layout (test entry points): dst needs (n + 15) / 16 + 1 words
+TALC_HD SeqView pack_ascii4(const u8* s, u32 n, u64* dst) {
+  const u32 nw = (n + 15) / 16 + 1;
+  for (u32 i = 0; i < nw; ++i) dst[i] = 0;
+  for (u32 i = 0; i < n; ++i) dst[i >> 4] |= (u64)base_code(s[i]) << (60 - 4 * (i & 15));
+  SeqView v; v.w = dst; v.start = 0; v.step = 1; v.len = n; v.lg = 4;
+  return v;
+}
 
 struct DpStats {  // algorithmic DP cell updates (SURVEY 8d "integer work")
   u64 cells_nw, cells_lcs, cells_ovl, cells_xdrop;
@@ -74,7 +78,7 @@ TALC_HDN void build_peq(const SeqView& pat, u32 pn, u32 block, u64 peq[5]) {
   peq[0] = peq[1] = peq[2] = peq[3] = peq[4] = 0;
   const u32 r0 = block * 64;
   const u32 r1 = (pn - r0 < 64u) ? pn : r0 + 64;
-  if (pat.w) {
+  if (pat.lg == 5) {
     // the n rows are n consecutive packed bases, ascending (step +1) or descending (step -1): split the low and
     // the high bit of every base into two n-bit masks, then the four symbols are the four AND combinations
     const u32 n = r1 - r0;

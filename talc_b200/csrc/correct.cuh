@@ -95,7 +95,8 @@ class Corrector {
   Params P;
   ModelTabs tabs;  // n == 0: no tables (host emulation)
   ReadView rd;
-  const u64* rdw;  // the read 2-bit packed (keep arena), nullptr when it holds an N
+  const u64* rdw;  // the read packed (keep arena): 2 bits per base, or 4 when it holds an N
+  u32 rdlg;        // 5 or 4
   const u32* cov;
   u32 C;  // number of k-mers
   Arena keep;     // persistent per-read data: regions, pieces
@@ -911,8 +912,8 @@ class Corrector {
       else if (!dirRight & (L.end + k < whichStart)) gapLen = whichStart - (L.end + k);
       const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(3 * k));
       RefView ref;
-      ref.s = rd.s;
       ref.w = rdw;
+      ref.lg = rdlg;
       if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = R.end + k - whichStart; }
       else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k - L.start; }
       if (!setup_search(pathMax)) return false;
@@ -1251,8 +1252,8 @@ class Corrector {
       const u32 gapLen = (location == 0) ? whichStart : (rd.len - (whichStart + k));
       const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(2 * k));
       RefView ref;
-      ref.s = rd.s;
       ref.w = rdw;
+      ref.lg = rdlg;
       if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = rd.len - whichStart; }
       else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k; }
       const SeqView refv = view_of(ref);
@@ -1386,24 +1387,26 @@ class Corrector {
     const u32 keepBytes = job.arena_bytes / 4;
     keep.init(job.arena, keepBytes & ~7u);
     scratch.init(job.arena + (keepBytes & ~7u), job.arena_bytes - (keepBytes & ~7u));
-    {  // 2-bit copy of the read for the scoring loops (N-free reads only)
-      const u32 nw = (rd.len + 31) / 32 + 1;
-      u64* pw = (u64*)keep.alloc(nw * 8);
+    {  // packed copy of the read for the scoring loops: 2 bits per base, 4 when the read holds an N
+      const u32 nw4 = (rd.len + 15) / 16 + 2;
+      u64* pw = (u64*)keep.alloc(nw4 * 8);
       if (!pw) return kReadOverflow;
       bool hasN = false;
+      for (u32 i = lane_id(); i < rd.len; i += lane_count()) hasN |= rd.code(i) > 3;
+      hasN = warp_any(hasN);
+      const u32 per = hasN ? 16u : 32u, bits = hasN ? 4u : 2u;
+      const u32 nw = (rd.len + per - 1) / per + 1;
       for (u32 wi = lane_id(); wi < nw; wi += lane_count()) {
         u64 x = 0;
-        for (u32 j = 0; j < 32; ++j) {
-          const u32 idx = wi * 32 + j;
-          u32 c = (idx < rd.len) ? rd.code(idx) : 0u;
-          if (c > 3) { hasN = true; c = 0; }
-          x = (x << 2) | c;
+        for (u32 j = 0; j < per; ++j) {
+          const u32 idx = wi * per + j;
+          x = (x << bits) | (u64)((idx < rd.len) ? rd.code(idx) : 0u);
         }
         pw[wi] = x;
       }
-      hasN = warp_any(hasN);
       warp_sync();
-      rdw = hasN ? nullptr : pw;
+      rdw = pw;
+      rdlg = hasN ? 4u : 5u;
     }
     // Read::reCoverage gate (Read.cpp:190, Q1: strictly greater)
     u32 nbIn = 0;

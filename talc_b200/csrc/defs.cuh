@@ -150,19 +150,21 @@ struct ReadView {
 // RIGHT-ward walk and read[start - i] for a LEFT-ward walk.  Every reference string the
 // reference builds (anchor+gap+target, target+gap+anchor, anchor+border, border+anchor:
 // Explorer.cpp:925-938,1042-1053) is a contiguous slice of the raw read, so no copy is made.
-// When the read holds no N it is also available 2-bit packed (w != nullptr, same indexing as s): the scoring
-// loops then fetch a base with a shift and a mask instead of decoding ASCII.
+// The scoring loops never see ASCII: the read is packed once per read (Corrector::run), 2 bits per base when it
+// holds no N (lg = 5: 32 bases per word, the same layout as a trail), else 4 bits per base (lg = 4, N = 4).
+// One access path for both: word idx >> lg, field of 64 >> lg bits, first base most significant.
+TALC_HD u32 packed_code(const u64* w, u32 idx, u32 lg) {
+  const u32 bits = 64u >> lg;
+  const u32 pos = idx & ((1u << lg) - 1u);
+  return (u32)(w[idx >> lg] >> (64u - bits * (pos + 1u))) & ((1u << bits) - 1u);
+}
 struct RefView {
-  const u8* s;
-  const u64* w;
+  const u64* w;  // packed read
   i32 start;
   i32 step;  // +1 or -1
   u32 len;
-  TALC_HD u32 code(u32 i) const {
-    const u32 idx = (u32)(start + (i32)i * step);
-    if (w) return (u32)((w[idx >> 5] >> (62 - 2 * (idx & 31))) & 3ull);
-    return base_code(s[idx]);
-  }
+  u32 lg;
+  TALC_HD u32 code(u32 i) const { return packed_code(w, (u32)(start + (i32)i * step), lg); }
 };
 
 // A trail's sequence in walk order, 2-bit packed (32 bases per u64, first base most significant).

@@ -325,18 +325,23 @@ __global__ void test_align_kernel(int op, const u8* a, const u64* aoff, const u8
   if (i >= n) return;
   Arena ar;
   ar.init(arenas + (u64)i * arenaBytes, arenaBytes);
-  SeqView va, vb;
-  va.s = a + aoff[i]; va.start = 0; va.step = 1; va.w = nullptr; va.len = (u32)(aoff[i + 1] - aoff[i]);
-  vb.s = b + boff[i]; vb.start = 0; vb.step = 1; vb.w = nullptr; vb.len = (u32)(boff[i + 1] - boff[i]);
-  // the second string is also exercised as a packed trail when it holds no N
-  u64* packed = (u64*)ar.alloc(((vb.len + 31) / 32 + 2) * 8);
-  bool pure = packed != nullptr;
+  // the sequences reach the scoring routines packed, as in the pipeline: 4 bits per base in general, and the
+  // second string also as a 2-bit trail when it holds no N
+  const u32 an = (u32)(aoff[i + 1] - aoff[i]), bn = (u32)(boff[i + 1] - boff[i]);
+  u64* pa = (u64*)ar.alloc(((an + 15) / 16 + 2) * 8);
+  u64* pb = (u64*)ar.alloc(((bn + 15) / 16 + 2) * 8);
+  u64* packed = (u64*)ar.alloc(((bn + 31) / 32 + 2) * 8);
+  if (!pa || !pb || !packed) return;
+  SeqView va = pack_ascii4(a + aoff[i], an, pa);
+  SeqView vb = pack_ascii4(b + boff[i], bn, pb);
+  bool pure = true;
   for (u32 j = 0; j < vb.len && pure; ++j) pure = vb.code(j) < 4;
   if (pure) {
     for (u32 j = 0; j < (vb.len + 31) / 32 + 2; ++j) packed[j] = 0;
     for (u32 j = 0; j < vb.len; ++j) path_set(packed, j, vb.code(j));
     vb = view_of_path(packed, vb.len);
   }
+  __syncwarp();
   i32 r0 = 0, r1 = 0, r2 = 0, r3 = 0;
   if (op == 0) r0 = -nw_distance(va, va.len, vb, vb.len, ar, nullptr);
   else if (op == 1) r0 = lcs_length(va, va.len, vb, vb.len, ar, nullptr);

@@ -167,10 +167,12 @@ int emu_correct_reads(void* tab, const emu_params* q, const uint8_t* bases, cons
 int emu_num_counters() { return kNumCounters; }
 
 // ---- primitives
+// ASCII -> the 4-bit packed layout the scoring routines read; the words live until the process ends (test aid)
 static SeqView bytes_view(const char* s, u32 n) {
-  SeqView v;
-  v.s = (const u8*)s; v.start = 0; v.step = 1; v.w = nullptr; v.len = n;
-  return v;
+  static thread_local std::vector<std::vector<u64>> keep;
+  if (keep.size() > 64) keep.erase(keep.begin(), keep.begin() + 32);
+  keep.emplace_back((n + 15) / 16 + 2, 0);
+  return pack_ascii4((const u8*)s, n, keep.back().data());
 }
 static std::vector<u64> pack(const char* s, u32 n) {
   std::vector<u64> w((n + 31) / 32 + 2, 0);
