@@ -231,6 +231,45 @@ class Corrector {
 
   // ------------------------------------------------------------------ Read.cpp:440-489
   TALC_HDN bool find_in_regions() {
+#if defined(__CUDA_ARCH__)
+    // 32 k-mers per ballot: a run starts where a set bit follows a clear one (carry = last bit of the previous
+    // word) and ends where a clear bit follows a set one; C <= 1 yields no region (Read.cpp:446)
+    const u32 lane = threadIdx.x & 31u;
+    for (int pass = 0; pass < 2; ++pass) {
+      u32 n = 0, cs = 0, carry = 0;
+      if (C > 1) {
+        for (u32 base = 0; base < C; base += 32) {
+          const u32 pos = base + lane;
+          const u32 m = __ballot_sync(0xffffffffu, pos < C && cov[pos] >= P.min_count);
+          const u32 prev = (m << 1) | carry;
+          u32 starts = m & ~prev, ends = ~m & prev;  // bit i: k-mer base+i opens / is the first one after a run
+          carry = m >> 31;
+          while (starts | ends) {
+            const u32 fs = starts ? (u32)__ffs((int)starts) - 1 : 32u, fe = ends ? (u32)__ffs((int)ends) - 1 : 32u;
+            if (fs < fe) {
+              cs = base + fs;
+              starts &= starts - 1;
+            } else {
+              if (pass) { regs[n].start = cs; regs[n].end = base + fe - 1; }
+              ++n;
+              ends &= ends - 1;
+            }
+          }
+        }
+        if (carry) {  // the last run reaches the end of the read
+          if (pass) { regs[n].start = cs; regs[n].end = C - 1; }
+          ++n;
+        }
+      }
+      if (!pass) {
+        nregs = n;
+        regs = (Region*)keep.alloc((n ? n : 1) * sizeof(Region));
+        if (!regs) return false;
+      }
+    }
+    __syncwarp();
+    return nregs > 0;
+#else
     // first pass counts, second pass fills
     u32 n = 0;
     bool state = false;
@@ -256,6 +295,7 @@ class Corrector {
       if (state) { regs[k].start = cs; regs[k].end = C - 1; ++k; }
     }
     return n > 0;
+#endif
   }
 
   // ------------------------------------------------------------------ Read.cpp:524-600
@@ -441,7 +481,8 @@ class Corrector {
     slotPool = (u64*)scratch.alloc(n * slotWords * 8);
     if (!freeList || !slotPool) return false;
     nFree = n;
-    for (u32 i = 0; i < n; ++i) freeList[i] = (u16)(n - 1 - i);
+    for (u32 i = lane_id(); i < n; i += lane_count()) freeList[i] = (u16)(n - 1 - i);
+    warp_sync();
     nCur = nNxt = 0;
     return true;
   }
@@ -660,17 +701,20 @@ class Corrector {
       // ---- every successor of every trail, one per lane
       u32 cnt = 0, col = 0;
       if (act) {
+        // home sector and the next one of the probe sequence are fetched together and resolved without branches
+        // (3 of 4 successors are absent from the graph, and ~15% of the probes that end at an empty slot end
+        // one sector further on)
         const u64 key = kmer_next(kmer, b, right, k);
-        // home sector and the next one of the probe sequence are fetched together: with 3 of 4 successors absent
-        // from the graph a probe usually ends at an empty slot, and ~15% of those lie one sector further on --
-        // a second dependent DRAM round trip on the critical path of the walk unless it is already in flight
         const u64 bucket = hash_kmer(key) & tv.mask & ~1ull;
         const u64 bucket2 = (bucket + 2) & tv.mask;
         Slot s0, s1, s2, s3;
         load_sector(tv.slots + bucket, s0, s1);
         load_sector(tv.slots + bucket2, s2, s3);
-        if (sector_resolve(s0, s1, key, cnt, col) < 0)
-          if (sector_resolve(s2, s3, key, cnt, col) < 0) table_probe_from(tv, bucket2, key, cnt, col);
+        if (!resolve4(s0, s1, s2, s3, key, cnt, col)) {
+          const u64 v = table_probe_from_v(tv, bucket2, key);
+          cnt = (u32)v;
+          col = (u32)(v >> 32);
+        }
       }
       const u32 mAll = __ballot_sync(0xffffffffu, cnt >= prm.min_count);
       const u32 m = (mAll >> grp) & 0xFu;

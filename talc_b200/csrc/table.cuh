@@ -79,6 +79,22 @@ TALC_HDN bool table_probe_from(const TableView& t, u64 b, u64 key, u32& count, u
     if (r >= 0) return r == 1;
   }
 }
+// the same by value: (colour << 32) | count, 0 when absent (no reference arguments: nothing is forced into local memory)
+TALC_HDN u64 table_probe_from_v(const TableView& t, u64 b, u64 key) {
+  u32 count = 0, colour = 0;
+  table_probe_from(t, b, key, count, colour);
+  return ((u64)colour << 32) | (u64)count;
+}
+// Two consecutive sectors of a probe sequence resolved without branches.  A key cannot sit behind an empty slot of
+// its probe sequence (no deletions), so: found anywhere -> that slot; else any empty slot -> absent; else go on.
+// Returns false when the probe has to continue past the second sector.
+TALC_HD bool resolve4(const Slot& s0, const Slot& s1, const Slot& s2, const Slot& s3, u64 key, u32& count, u32& colour) {
+  const bool h0 = s0.key == key, h1 = s1.key == key, h2 = s2.key == key, h3 = s3.key == key;
+  const bool e = (s0.key == kEmptyKey) | (s1.key == kEmptyKey) | (s2.key == kEmptyKey) | (s3.key == kEmptyKey);
+  count = h0 ? s0.count : h1 ? s1.count : h2 ? s2.count : h3 ? s3.count : 0u;
+  colour = h0 ? s0.colour : h1 ? s1.colour : h2 ? s2.colour : h3 ? s3.colour : 0u;
+  return h0 | h1 | h2 | h3 | e;
+}
 
 // point look-up: (count, colour) or (0,0) when absent (Jellyfish.cpp:317-318,492-493)
 TALC_HD bool table_lookup(const TableView& t, u64 key, u32& count, u32& colour) {
@@ -90,24 +106,25 @@ TALC_HD bool table_lookup(const TableView& t, u64 key, u32& count, u32& colour) 
   return table_probe_from(t, b, key, count, colour);
 }
 
-// the four successor counts in A,C,G,T order (Jellyfish.cpp:308-321): the four home sectors are
-// fetched together (8 independent 16-byte loads in flight), stragglers continue probing one by one
-TALC_HDN void table_next_counts(const TableView& t, u64 kmer, bool right, u32 K, u32 cnt[4], u32 col[4]) {
-  u64 key[4], b[4];
-  Slot s0[4], s1[4];
+// the four successor counts in A,C,G,T order (Jellyfish.cpp:308-321).  Device: lane l probes successor l & 3 (the
+// warp runs one look-up instead of four, lanes 4..31 mirror lanes 0..3) and four shuffles hand every lane all
+// four results.  Host form: the four home sectors one after the other.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ void table_next_counts(const TableView& t, u64 kmer, bool right, u32 K, u32 cnt[4], u32 col[4]) {
+  const u32 b = threadIdx.x & 3u;
+  u32 c, l;
+  table_lookup(t, kmer_next(kmer, b, right, K), c, l);
 #pragma unroll
-  for (u32 i = 0; i < 4; ++i) {
-    key[i] = kmer_next(kmer, i, right, K);
-    b[i] = hash_kmer(key[i]) & t.mask & ~1ull;
-  }
-#pragma unroll
-  for (u32 i = 0; i < 4; ++i) load_sector(t.slots + b[i], s0[i], s1[i]);
-#pragma unroll
-  for (u32 i = 0; i < 4; ++i) {
-    const int r = sector_resolve(s0[i], s1[i], key[i], cnt[i], col[i]);
-    if (r < 0) table_probe_from(t, b[i], key[i], cnt[i], col[i]);
+  for (int i = 0; i < 4; ++i) {
+    cnt[i] = __shfl_sync(0xffffffffu, c, i);
+    col[i] = __shfl_sync(0xffffffffu, l, i);
   }
 }
+#else
+TALC_HDN void table_next_counts(const TableView& t, u64 kmer, bool right, u32 K, u32 cnt[4], u32 col[4]) {
+  for (u32 i = 0; i < 4; ++i) table_lookup(t, kmer_next(kmer, i, right, K), cnt[i], col[i]);
+}
+#endif
 
 // the same in two halves, so that a caller can do arithmetic while the eight loads are in flight
 struct NextProbe {
@@ -132,13 +149,20 @@ TALC_HD void table_next_resolve(const TableView& t, const NextProbe& q, u32 cnt[
 }
 
 // Jellyfish.cpp:383-393
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ int table_out_degree(const TableView& t, u64 kmer, bool right, u32 K, u32 min_count) {
+  u32 c, l;
+  table_lookup(t, kmer_next(kmer, threadIdx.x & 3u, right, K), c, l);
+  return __popc(__ballot_sync(0xffffffffu, c >= min_count) & 0xFu);
+}
+#else
 TALC_HDN int table_out_degree(const TableView& t, u64 kmer, bool right, u32 K, u32 min_count) {
   u32 cnt[4], col[4];
   table_next_counts(t, kmer, right, K, cnt, col);
   int d = 0;
-#pragma unroll
   for (u32 b = 0; b < 4; ++b) d += (cnt[b] >= min_count) ? 1 : 0;
   return d;
 }
+#endif
 
 }  // namespace talc
