@@ -524,9 +524,10 @@ inline int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn
 // the database (ext_rows) and the query (ext_cols).  `wide` sizes the three anti-diagonals for the
 // worst case instead of the X-drop band (second-tier launch).
 TALC_HDN void xdrop_extend_scalar(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen,
-                          int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide, DpStats* st) {
+                          int scoreDropOff, u32& ext_rows, u32& ext_cols, i32& end_score, Arena& ar, bool wide, DpStats* st) {
   ext_rows = 0;
   ext_cols = 0;
+  end_score = 0;
   const i64 cols = (i64)qlen + 1;
   const i64 rows = (i64)dlen + 1;
   if (rows == 1 || cols == 1) return;
@@ -650,6 +651,7 @@ TALC_HDN void xdrop_extend_scalar(const SeqView& query, u32 qoff, u32 qlen, cons
   if (longestExtensionScore != undefined) {
     ext_rows = (u32)longestExtensionRow;
     ext_cols = (u32)longestExtensionCol;
+    end_score = longestExtensionScore;
   }
   ar.release(mk);
 }
@@ -664,18 +666,18 @@ namespace talc {
 // diagonals; beyond that (never seen on the benchmark workloads) every lane runs the scalar routine on the
 // warp's arena.  Must be called by all 32 lanes with identical arguments.
 __device__ __forceinline__ void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff,
-                                             u32 dlen, int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide,
-                                             DpStats* st) {
-  if (scoreDropOff <= 31) xdrop_extend_reg<1>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, st);
-  else if (scoreDropOff <= 63) xdrop_extend_reg<2>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, st);
-  else if (scoreDropOff <= 127) xdrop_extend_reg<4>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, st);
-  else if (scoreDropOff <= 255) xdrop_extend_reg<8>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, st);
-  else xdrop_extend_scalar(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, ar, true, st);
+                                             u32 dlen, int scoreDropOff, u32& ext_rows, u32& ext_cols, i32& end_score,
+                                             Arena& ar, bool wide, DpStats* st) {
+  if (scoreDropOff <= 31) xdrop_extend_reg<1>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, end_score, st);
+  else if (scoreDropOff <= 63) xdrop_extend_reg<2>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, end_score, st);
+  else if (scoreDropOff <= 127) xdrop_extend_reg<4>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, end_score, st);
+  else if (scoreDropOff <= 255) xdrop_extend_reg<8>(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, end_score, st);
+  else xdrop_extend_scalar(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, end_score, ar, true, st);
 }
 #else
 inline void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen,
-                         int scoreDropOff, u32& ext_rows, u32& ext_cols, Arena& ar, bool wide, DpStats* st) {
-  xdrop_extend_scalar(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, ar, wide, st);
+                         int scoreDropOff, u32& ext_rows, u32& ext_cols, i32& end_score, Arena& ar, bool wide, DpStats* st) {
+  xdrop_extend_scalar(query, qoff, qlen, database, doff, dlen, scoreDropOff, ext_rows, ext_cols, end_score, ar, wide, st);
 }
 #endif
 
@@ -696,13 +698,22 @@ TALC_HDN SeedExt seed_and_extension(const SeqView& refArg, const SeqView& candAr
   const SeqView& seq2 = state ? candArg : refArg;   // V / query
   const u32 s = right ? (K - 1) : K;                // Q18: seed (0,0,K-1,K-1) vs (l1-K,l2-K,..)
   u32 er = 0, ec = 0;
-  xdrop_extend(seq2, s, seq2.len - s, seq1, s, seq1.len - s, xdrop, er, ec, ar, wide, st);
+  i32 endScore = 0;
+  xdrop_extend(seq2, s, seq2.len - s, seq1, s, seq1.len - s, xdrop, er, ec, endScore, ar, wide, st);
   const u32 e1 = s + er, e2 = s + ec;
   r.ref_ext = state ? e1 : e2;
   r.cand_ext = state ? e2 : e1;
   const u32 mx = r.ref_ext > r.cand_ext ? r.ref_ext : r.cand_ext;
   if (mx >= K) {
-    r.score = -nw_distance(refArg, r.ref_ext, candArg, r.cand_ext, ar, st);
+    // Trail.cpp:422 runs a global alignment (0,-1,-1) of the two extended prefixes.  Its score is already known:
+    // the cell the X-drop stopped in holds the exact edit distance of the two extensions (a cell survives only
+    // with its true score, see xdrop.cuh), and the s leading bases are the anchor k-mer in both strings -- a common
+    // prefix does not change an edit distance.  The reference's DP cells are still tallied.
+#if defined(TALC_CHECK_SEED_SCORE)
+    if (endScore != -nw_distance(refArg, r.ref_ext, candArg, r.cand_ext, ar, nullptr)) ar.overflow = 2;
+#endif
+    if (st) st->cells_nw += (u64)r.ref_ext * r.cand_ext;
+    r.score = endScore;
     r.stop = false;
   } else {  // Q19
     r.score = -xdrop;

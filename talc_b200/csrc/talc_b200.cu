@@ -354,10 +354,12 @@ __global__ void test_align_kernel(int op, const u8* a, const u64* aoff, const u8
     DpStats ds;
     ds.cells_xdrop = 0;
     u32 er = 0, ec = 0;
-    xdrop_extend(va, 0, va.len, vb, 0, vb.len, aux, er, ec, ar, true, &ds);
+    i32 es = 0;
+    xdrop_extend(va, 0, va.len, vb, 0, vb.len, aux, er, ec, es, ar, true, &ds);
     r0 = (i32)er;
     r1 = (i32)ec;
     r2 = (i32)ds.cells_xdrop;
+    r3 = es;
   } else {
     const SeedExt e = seed_and_extension(va, vb, aux, aux2 != 0, K, ar, true, nullptr);
     r0 = (i32)e.ref_ext;
@@ -935,6 +937,12 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
     for (u32 i = 0; i < 8 && i < n; ++i)
       fprintf(stderr, "[talc debug]   slow read %u: %.1f Mcycles, length %llu\n", idx[i], kc[idx[i]] / 1024.0,
               (unsigned long long)(ho[idx[i] + 1] - ho[idx[i]]));
+    if (const char* path = getenv("TALC_DEBUG_CYCLES_FILE")) {  // raw u32 kilo-cycles per read, input order
+      if (FILE* f = fopen(path, "wb")) {
+        fwrite(kc.data(), 4, n, f);
+        fclose(f);
+      }
+    }
     dbgCycles.release();
   }
   if (counters) {

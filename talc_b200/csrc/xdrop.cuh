@@ -58,7 +58,7 @@ TALC_HD void xd_next_window(i32 d, i32 rows, i32 cols, i32 loC, i32 hiC, i32& mi
 // kXdU when absent; argmax1(lo, hi, col): greatest value of anti-diagonal d-2 over columns [lo, hi], lowest
 // column among equals.
 template <class At, class ArgMax>
-TALC_HD void xd_finish(i32 d, const XdHist& h, At at, ArgMax argmax1, u32& ext_rows, u32& ext_cols) {
+TALC_HD void xd_finish(i32 d, const XdHist& h, At at, ArgMax argmax1, u32& ext_rows, u32& ext_cols, i32& end_score) {
   i32 col = h.max3 - 1;
   i32 row = d - col;
   i32 sc = at(3, col);
@@ -90,6 +90,7 @@ TALC_HD void xd_finish(i32 d, const XdHist& h, At at, ArgMax argmax1, u32& ext_r
   if (sc != kXdU) {
     ext_rows = (u32)row;
     ext_cols = (u32)col;
+    end_score = sc;  // = -(edit distance of the two extended prefixes): every surviving cell holds its exact distance
   }
 }
 
@@ -110,12 +111,14 @@ TALC_HD i32 xd_cell(i32 a, i32 b, i32 dg, bool match, i32 col, i32 d, i32 X, i32
 #if defined(__CUDA_ARCH__)
 template <int S>
 __device__ __noinline__ void xdrop_extend_reg(const SeqView& queryArg, u32 qoff, u32 qlen, const SeqView& databaseArg,
-                                              u32 doff, u32 dlen, int X, u32& ext_rows, u32& ext_cols, DpStats* st) {
+                                              u32 doff, u32 dlen, int X, u32& ext_rows, u32& ext_cols, i32& end_score,
+                                              DpStats* st) {
   const SeqView query = queryArg, database = databaseArg;  // by value: the fields stay in registers
   const i32 lane = (i32)(threadIdx.x & 31u);
   const i32 cols = (i32)qlen + 1, rows = (i32)dlen + 1;
   ext_rows = 0;
   ext_cols = 0;
+  end_score = 0;
   if (rows == 1 || cols == 1) return;
   const i32 g0 = S * lane;
   i32 vE[S], vO[S], vOld[S];
@@ -219,7 +222,7 @@ __device__ __noinline__ void xdrop_extend_reg(const SeqView& queryArg, u32 qoff,
     col = __reduce_min_sync(0xffffffffu, (bv == mx && bv > kXdU) ? bc : INT32_MAX);
     return mx;
   };
-  xd_finish(d, h, at, argmax1, ext_rows, ext_cols);
+  xd_finish(d, h, at, argmax1, ext_rows, ext_cols, end_score);
 }
 #endif
 

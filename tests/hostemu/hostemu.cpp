@@ -209,7 +209,8 @@ void emu_xdrop(const char* query_seg, const char* database_seg, int xdrop, int w
   Arena A; A.init(ar.data(), (u32)ar.size());
   u32 qn = strlen(query_seg), dn = strlen(database_seg);
   u32 er = 0, ec = 0;
-  xdrop_extend(bytes_view(query_seg, qn), 0, qn, bytes_view(database_seg, dn), 0, dn, xdrop, er, ec, A, wide != 0, nullptr);
+  i32 es = 0;
+  xdrop_extend(bytes_view(query_seg, qn), 0, qn, bytes_view(database_seg, dn), 0, dn, xdrop, er, ec, es, A, wide != 0, nullptr);
   *ext_rows = er; *ext_cols = ec; *overflow = (int)A.overflow;
 }
 // Mirror of xdrop_extend_reg<S> (talc_b200/csrc/xdrop.cuh) with the warp's registers laid out as flat arrays
@@ -217,10 +218,11 @@ void emu_xdrop(const char* query_seg, const char* database_seg, int xdrop, int w
 // xd_cell / xd_next_window / xd_finish with the device code, so fuzzing it against xdrop_extend_scalar
 // validates the band layout, the window updates and the end-position rules without a GPU.
 static void xdrop_reg_mirror(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen, int X,
-                             int S, u32& ext_rows, u32& ext_cols, u64* cells_out) {
+                             int S, u32& ext_rows, u32& ext_cols, i32& end_score, u64* cells_out) {
   const i32 cols = (i32)qlen + 1, rows = (i32)dlen + 1;
   ext_rows = 0;
   ext_cols = 0;
+  end_score = 0;
   if (cells_out) *cells_out = 0;
   if (rows == 1 || cols == 1) return;
   const int G = 32 * S;
@@ -297,14 +299,15 @@ static void xdrop_reg_mirror(const SeqView& query, u32 qoff, u32 qlen, const Seq
     }
     return bv;
   };
-  xd_finish(d, h, at, argmax1, ext_rows, ext_cols);
+  xd_finish(d, h, at, argmax1, ext_rows, ext_cols, end_score);
 }
 void emu_xdrop_reg(const char* query_seg, const char* database_seg, int xdrop, int S, uint64_t* ext_rows, uint64_t* ext_cols,
                    uint64_t* cells) {
   u32 qn = strlen(query_seg), dn = strlen(database_seg);
   u32 er = 0, ec = 0;
   u64 c = 0;
-  xdrop_reg_mirror(bytes_view(query_seg, qn), 0, qn, bytes_view(database_seg, dn), 0, dn, xdrop, S, er, ec, &c);
+  i32 es = 0;
+  xdrop_reg_mirror(bytes_view(query_seg, qn), 0, qn, bytes_view(database_seg, dn), 0, dn, xdrop, S, er, ec, es, &c);
   *ext_rows = er; *ext_cols = ec; *cells = c;
 }
 // built-in fuzzer: random related pairs, every admissible S; returns the number of disagreements with the scalar form
@@ -339,14 +342,28 @@ int emu_xdrop_reg_fuzz(uint64_t seed, int n_cases, int max_len) {
     Arena A; A.init(ar.data(), (u32)ar.size());
     DpStats st; st.cells_xdrop = 0;
     u32 er0 = 0, ec0 = 0;
+    i32 es0 = 0;
     const SeqView qv = bytes_view(q.data(), (u32)q.size()), dv = bytes_view(db.data(), (u32)db.size());
-    xdrop_extend_scalar(qv, qoff, (u32)q.size() - qoff, dv, doff, (u32)db.size() - doff, X, er0, ec0, A, true, &st);
+    xdrop_extend_scalar(qv, qoff, (u32)q.size() - qoff, dv, doff, (u32)db.size() - doff, X, er0, ec0, es0, A, true, &st);
+    {  // the end cell holds the exact edit distance of the two extensions (used instead of a separate NW pass)
+      int dist = (int)(er0 > ec0 ? er0 : ec0);
+      if (er0 > 0 && ec0 > 0) {
+        SeqView qs = qv, ds = dv;
+        qs.start += (i32)qoff; ds.start += (i32)doff;
+        dist = nw_distance_scalar(qs, ec0, ds, er0, A, nullptr);
+      }
+      if (es0 != -dist) {
+        if (bad < 5) fprintf(stderr, "xdrop end score %d != -distance %d (X=%d q=%s db=%s)\n", es0, dist, X, q.c_str(), db.c_str());
+        ++bad;
+      }
+    }
     for (int S : {1, 2, 4, 8}) {
       if (X > 32 * S - 1) continue;
       u32 er = 0, ec = 0;
       u64 cells = 0;
-      xdrop_reg_mirror(qv, qoff, (u32)q.size() - qoff, dv, doff, (u32)db.size() - doff, X, S, er, ec, &cells);
-      if (er != er0 || ec != ec0 || cells != st.cells_xdrop) {
+      i32 es = 0;
+      xdrop_reg_mirror(qv, qoff, (u32)q.size() - qoff, dv, doff, (u32)db.size() - doff, X, S, er, ec, es, &cells);
+      if (er != er0 || ec != ec0 || cells != st.cells_xdrop || es != es0) {
         if (bad < 5)
           fprintf(stderr, "xdrop mismatch S=%d X=%d q=%s db=%s qoff=%u doff=%u scalar=(%u,%u,%llu) reg=(%u,%u,%llu)\n", S, X,
                   q.c_str(), db.c_str(), qoff, doff, er0, ec0, (unsigned long long)st.cells_xdrop, er, ec,
