@@ -361,23 +361,23 @@ __device__ __noinline__ int nw_lcs_fused(const SeqView& a, u32 an, const SeqView
   const u32 rows = last ? (pn - lane * 64) : 64;
   const u32 top = rows - 1;
   u64 Pv = ~0ull, Mv = 0, V = ~0ull;
-  u32 handPrev = 1u;  // (hout + 1) | (cout << 2)
-  u32 cPrev = 4;
+  u32 outPrev = 1u | (4u << 4);  // what this lane hands to the next: (hout + 1) | (cout << 2) | (text character << 4)
+  u32 chunk = 4u;                // the next 32 text characters, one per lane, reloaded every 32 steps
   int acc = 0;
   __syncwarp();
 #pragma unroll 1
   for (u32 t = 0; t < tn + nblocks - 1; ++t) {
-    u32 hand = __shfl_up_sync(0xffffffffu, handPrev, 1);
-    u32 c = __shfl_up_sync(0xffffffffu, cPrev, 1);
-    if (lane == 0) {
-      c = (t < tn) ? txt.code(t) : 4u;
-      hand = 2u;  // hin = +1 (first row of the distance matrix), no carry
-    }
+    const u32 ph = t & 31u;
+    if (ph == 0) chunk = (t + lane < tn) ? txt.code(t + lane) : 4u;
+    u32 in = __shfl_up_sync(0xffffffffu, outPrev, 1);
+    const u32 c0 = __shfl_sync(0xffffffffu, chunk, ph);
+    if (lane == 0) in = 2u | (c0 << 4);  // hin = +1 (first row of the distance matrix), no carry
+    const u32 c = in >> 4;
     const bool valid = haveBlk && (t >= lane) && (t - lane < tn);
-    u32 handOut = 1u;
+    u32 hand = 1u;
     if (valid) {
       const u64 M = peq[c];
-      const int hin = (int)(hand & 3u) - 1;
+      const int hin = (int)(in & 3u) - 1;
       // Myers / Hyyro
       u64 Eq = M;
       const u64 hneg = (hin < 0) ? 1ull : 0ull;
@@ -397,13 +397,12 @@ __device__ __noinline__ int nw_lcs_fused(const SeqView& a, u32 an, const SeqView
       // bit-parallel LCS
       const u64 U = V & M;
       const u64 tt = V + U;
-      const u64 sum = tt + (u64)(hand >> 2);
+      const u64 sum = tt + (u64)((in >> 2) & 1u);
       const u32 cout = (u32)(tt < V) | (u32)(sum < tt);
       V = sum | (V & ~M);
-      handOut = (u32)(hout + 1) | (cout << 2);
+      hand = (u32)(hout + 1) | (cout << 2);
     }
-    handPrev = handOut;
-    cPrev = c;
+    outPrev = hand | (c << 4);
   }
   const int score = (int)pn + __shfl_sync(0xffffffffu, acc, nblocks - 1);
   int z = 0;
@@ -483,18 +482,22 @@ __device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const S
     const u32 nl = (cn - j0 + 1 < 32u) ? (cn - j0 + 1) : 32u;  // columns in this stripe
     const bool park = (j0 + 32 <= cn) && (lane == 31);          // a further stripe follows
     const u32 cc = act ? cand.code(j - 1) : 9u;
-    i32 up = 0, diag = 0, vPrev = 0;  // S[0][j] = S[0][j-1] = 0
-    u32 rcPrev = 8u;
+    i32 up = 0, diag = 0;  // S[0][j] = S[0][j-1] = 0
+    i32 outPrev = 8;       // what this lane hands to the next: (value << 3) | reference character of the row
+    i32 chunk = 8;         // the same for lane 0, 32 rows at a time: (S[i][j0-1] << 3) | reference character
 #pragma unroll 1
     for (u32 t = 1; t <= rn + nl - 1; ++t) {
-      i32 left = __shfl_up_sync(0xffffffffu, vPrev, 1);
-      u32 rc = __shfl_up_sync(0xffffffffu, rcPrev, 1);
-      if (lane == 0) {
-        const bool in = t <= rn;
-        rc = in ? ref.code(t - 1) : 8u;
-        left = in ? colBuf[t] : 0;
+      const u32 ph = (t - 1) & 31u;
+      if (ph == 0) {
+        const u32 r = t - 1 + lane;  // row r + 1
+        chunk = (r < rn) ? (i32)(((u32)colBuf[r + 1] << 3) | ref.code(r)) : 8;
       }
-      const u32 i = t - lane;  // wraps for t < lane: fails the range test below
+      i32 in = __shfl_up_sync(0xffffffffu, outPrev, 1);
+      const i32 in0 = __shfl_sync(0xffffffffu, chunk, ph);
+      if (lane == 0) in = in0;
+      const u32 rc = (u32)in & 7u;
+      const i32 left = in >> 3;    // arithmetic shift: the value keeps its sign
+      const u32 i = t - lane;      // wraps for t < lane: fails the range test below
       i32 v = 0;
       if (act && i >= 1 && i <= rn) {
         const i32 d = diag + ((rc == cc) ? 4 : -3);
@@ -504,8 +507,7 @@ __device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const S
         up = v;
         if (park) colBuf[i] = v;
       }
-      vPrev = v;
-      rcPrev = rc;
+      outPrev = (i32)(((u32)v << 3) | rc);
     }
     if (j0 + 32 > cn) result = __shfl_sync(0xffffffffu, up, cn - j0);
     __syncwarp();

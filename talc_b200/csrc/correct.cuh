@@ -137,8 +137,8 @@ class Corrector {
   // ------------------------------------------------------------------ table access with counters
   TALC_HDN int out_degree(u32 pos, bool right) {
     if (ctr) ctr->lookups_deg += 4;
-    bool ok;
-    const u64 km = rd.kmer_at(pos, K(), ok);
+    bool ok = true;
+    const u64 km = (rdlg == 5u) ? path_kmer_fwd(rdw, pos, K()) : rd.kmer_at(pos, K(), ok);
     if (!ok) {
       // a k-mer holding N: its successors x[1..]+b may or may not hold N; look each one up by bases
       int d = 0;
@@ -391,6 +391,7 @@ class Corrector {
   }
 
   TALC_HD u64 read_kmer(u32 pos) {  // anchors sit on k-mers with count >= MIN, hence without N
+    if (rdlg == 5u) return path_kmer_fwd(rdw, pos, K());
     bool ok;
     return rd.kmer_at(pos, K(), ok);
   }

@@ -154,9 +154,9 @@ struct ReadView {
 // holds no N (lg = 5: 32 bases per word, the same layout as a trail), else 4 bits per base (lg = 4, N = 4).
 // One access path for both: word idx >> lg, field of 64 >> lg bits, first base most significant.
 TALC_HD u32 packed_code(const u64* w, u32 idx, u32 lg) {
-  const u32 bits = 64u >> lg;
-  const u32 pos = idx & ((1u << lg) - 1u);
-  return (u32)(w[idx >> lg] >> (64u - bits * (pos + 1u))) & ((1u << bits) - 1u);
+  // field width 64 >> lg = 1 << (6 - lg); base j of a word sits (per - 1 - j) fields above bit 0
+  const u32 sh = (~idx & ((1u << lg) - 1u)) << (6u - lg);
+  return (u32)(w[idx >> lg] >> sh) & (lg == 5u ? 3u : 15u);
 }
 struct RefView {
   const u64* w;  // packed read
