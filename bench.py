@@ -42,6 +42,20 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one correct_kernel launch of this very workload (131072 reads),
+    from the committed metrics-only ncu capture (tools/final_profiles.sh); None when the capture is absent."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic_correct_kernel.csv")
+    if not os.path.exists(p):
+        return None
+    import csv
+    tot = 0
+    for row in csv.reader(open(p)):
+        if len(row) > 14 and row[12] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += int(row[14])
+    return tot or None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -300,7 +314,9 @@ def run_gpu(args, rank, world, local_rank):
                            "generate_s": round(t_gen, 1), "table_build_s": round(t_build, 2),
                            "table_broadcast_ms": round(t_bcast_ms, 2), "wall_s_timed_region": round(wall, 3)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "correct_kernel", "peak_source": peak_src,
+                             "traffic": measured_traffic() if B == 131072 and args.config == 2 and args.scale == 1.0 else None,
+                             "traffic_source": "profiles/r01_traffic_correct_kernel.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch of this workload)",
+                             "kernel": "correct_kernel", "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": k_ms,
                              "coverage_kernel": {"achieved": cov_bytes / 1e9 / (cov_ms / 1e3), "ms_per_launch": cov_ms,
                                                  "algorithmic_bytes_per_launch": cov_bytes,
