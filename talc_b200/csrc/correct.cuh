@@ -92,6 +92,7 @@ struct ReadOut {
 class Corrector {
  public:
   TableView T;
+  CtxView CR, CL;  // successor tables for RIGHT- and LEFT-ward questions (device only)
   Params P;
   ModelTabs tabs;  // n == 0: no tables (host emulation)
   ReadView rd;
@@ -160,7 +161,26 @@ class Corrector {
       }
       return d;
     }
+#if defined(__CUDA_ARCH__)
+    {  // one bucket of the successor table holds all four counts
+      u32 c4[4], cm;
+      ctx_lookup(right ? CR : CL, ctx_of(km, right, K()), c4, cm);
+      return (int)(c4[0] >= P.min_count) + (int)(c4[1] >= P.min_count) + (int)(c4[2] >= P.min_count) + (int)(c4[3] >= P.min_count);
+    }
+#else
     return table_out_degree(T, km, right, K(), P.min_count);
+#endif
+  }
+  // the four successor counts / junction flags of a k-mer in the search direction (getNextCountsFromDBG)
+  TALC_HD void next_counts(u64 kmer, u32 cnt[4], u32 col[4]) {
+#if defined(__CUDA_ARCH__)
+    u32 cm;
+    ctx_lookup(dirRight ? CR : CL, ctx_of(kmer, dirRight, K()), cnt, cm);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) col[i] = (cm >> i) & 1u;  // only "colour > 0" is ever tested (Explorer.cpp:1258)
+#else
+    table_next_counts(T, kmer, dirRight, K(), cnt, col);
+#endif
   }
 
   // ------------------------------------------------------------------ Read.cpp:493-518
@@ -677,16 +697,14 @@ class Corrector {
     if (nT == 0 || nT > 7 || nT > P.max_branches || nAims > 32) return;
     const u32 lane = threadIdx.x & 31u;
     const u64 myAim = (!border && lane < nAims) ? aims[lane].kmer : ~0ull;  // ~0 is not a k-mer (<= 60 bits)
-    const u32 t = lane >> 2, b = lane & 3u;
-    const bool act = t < nT;
+    const bool act = lane < nT;  // lane t owns trail t: ONE bucket of the successor table answers its whole step
     const u32 k = P.K;
     const bool right = dirRight;
-    const TableView tv = T;
-    const Params prm = P;
-    const ModelTabs mt = tabs;
-    const u64 kmask = kmer_mask(k);
-    const u32 stride = (prm.cycle_mode == 0) ? k : 1u;
-    const Trail tr = cur[act ? t : 0];
+    const CtxView cv = right ? CR : CL;
+    const u32 minCount = P.min_count;
+    const u64 kmask = kmer_mask(k), cmask = kmer_mask(k - 1);
+    const u32 stride = (P.cycle_mode == 0) ? k : 1u;
+    const Trail tr = cur[act ? lane : 0];
     u64* const w = slot_ptr(tr.slot);
     u64 kmer = tr.kmer;
     u32 count = tr.count;
@@ -694,67 +712,42 @@ class Corrector {
     u64 rkmer = 0;  // the last k-mer with its bases in reverse order (LEFT walks compare in walk order)
     for (u32 i = 0; i < k; ++i) rkmer |= ((kmer >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
     u32 st = step, nSteps = 0;
-    const u32 grp = lane & ~3u;
 #pragma unroll 1
     while (st < pathMax) {
       if (border && ((st + 1) % kCheckInterval == 0)) break;  // scoreEdges is due after this step
       const u32 plen = k + st;
-      // ---- every successor of every trail, one per lane
-      u32 cnt = 0, col = 0;
-      if (act) {
-        // home sector and the next one of the probe sequence are fetched together and resolved without branches
-        // (3 of 4 successors are absent from the graph, and ~15% of the probes that end at an empty slot end
-        // one sector further on)
-        const u64 key = kmer_next(kmer, b, right, k);
-        const u64 bucket = hash_kmer(key) & tv.mask & ~1ull;
-        const u64 bucket2 = (bucket + 2) & tv.mask;
-        Slot s0, s1, s2, s3;
-        load_sector(tv.slots + bucket, s0, s1);
-        load_sector(tv.slots + bucket2, s2, s3);
-        if (!resolve4(s0, s1, s2, s3, key, cnt, col)) {
-          const u64 v = table_probe_from_v(tv, bucket2, key);
-          cnt = (u32)v;
-          col = (u32)(v >> 32);
-        }
-      }
-      const u32 mAll = __ballot_sync(0xffffffffu, cnt >= prm.min_count);
-      const u32 m = (mAll >> grp) & 0xFu;
+      // ---- the four successors of every trail: one sector per trail
       int child = -1;
+      u32 childCnt = 0;
       if (act) {
+        u32 c4[4], cm;
+        ctx_lookup(cv, right ? (kmer & cmask) : (kmer >> 2), c4, cm);
+        const u32 m = (u32)(c4[0] >= minCount) | ((u32)(c4[1] >= minCount) << 1) | ((u32)(c4[2] >= minCount) << 2) |
+                      ((u32)(c4[3] >= minCount) << 3);
         if (m != 0 && (m & (m - 1)) == 0) {
           child = __ffs((int)m) - 1;  // the only successor in the graph: EXPECTED by the counter == 1 rule
         } else if (m != 0) {
-          u32 cnt4[4], col4[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            cnt4[i] = __shfl_sync(0xFu << grp, cnt, grp + i);  // the four lanes of a group branch together
-            col4[i] = __shfl_sync(0xFu << grp, col, grp + i);
-          }
-          const StepBounds sb = step_bounds_tab(count, prm, mt);
-          u8 tag[4];
-          tag_next_nodes(cnt4, col4, sb, prm, false, tag);
-          int nChildren = 0;
-          for (int i = 0; i < 4; ++i)
-            if (tag[i] != kUnexpected) { child = i; ++nChildren; }
-          if (nChildren != 1) child = -1;
+          child = pick_single_child(c4, cm, count);  // exact tagger; -1 unless exactly one successor is admissible
         }
+        const u32 ch = (u32)(child < 0 ? 0 : child);
+        childCnt = ch == 0 ? c4[0] : ch == 1 ? c4[1] : ch == 2 ? c4[2] : c4[3];
       }
       if (__ballot_sync(0xffffffffu, act && child < 0)) break;  // dead end or branching somewhere: general step
-      const u32 childCnt = __shfl_sync(0xffffffffu, cnt, grp + (u32)(child < 0 ? 0 : child));
-      const u64 ck = kmer_next(kmer, (u32)(child < 0 ? 0 : child), right, k);
+      const u32 ch = (u32)(child < 0 ? 0 : child);
+      const u64 ck = kmer_next(kmer, ch, right, k);
       if (!border) {  // aim reached by any trail: the general step records the bridge (one aim k-mer per lane)
         bool aim = false;
 #pragma unroll 1
-        for (u32 q = 0; q < nT; ++q) aim |= (myAim == __shfl_sync(0xffffffffu, ck, 4 * q));
+        for (u32 q = 0; q < nT; ++q) aim |= (myAim == __shfl_sync(0xffffffffu, ck, q));
         if (__ballot_sync(0xffffffffu, aim)) break;
       }
       // ---- cycle test of every trail against its own sequence, one window per lane
       if (plen > k) {
-        const u64 myNeedle = right ? ck : (((rkmer << 2) | (u64)(child < 0 ? 0 : child)) & kmask);
+        const u64 myNeedle = right ? ck : (((rkmer << 2) | (u64)ch) & kmask);
         bool cyc = false;
         for (u32 q = 0; q < nT && !cyc; ++q) {
-          const u64 needle = __shfl_sync(0xffffffffu, myNeedle, 4 * q);
-          const u64* wq = (const u64*)__shfl_sync(0xffffffffu, (unsigned long long)w, 4 * q);
+          const u64 needle = __shfl_sync(0xffffffffu, myNeedle, q);
+          const u64* wq = (const u64*)__shfl_sync(0xffffffffu, (unsigned long long)w, q);
           for (u32 base = 0; (u64)base * stride + k <= plen; base += 32) {
             const u32 p = (base + lane) * stride;
             bool match = false;
@@ -769,13 +762,15 @@ class Corrector {
         if (cyc) break;
       }
       // ---- commit the step: one base per trail
-      if (act && b == 0) path_set(w, plen, (u32)child);
-      __syncwarp();
-      if (count != childCnt) {  // a zero numerator adds +0.0 (and would take the slow path of the double division)
-        const double sq = (count < mt.n) ? mt.sq[count] : sqrt_cold(count);
-        dsum = dsum + fabs((double)count - (double)childCnt) / sq;
+      if (act) {
+        path_set(w, plen, ch);
+        if (count != childCnt) {  // a zero numerator adds +0.0 (and would take the slow path of the double division)
+          const double sq = (count < tabs.n) ? tabs.sq[count] : sqrt_cold(count);
+          dsum = dsum + fabs((double)count - (double)childCnt) / sq;
+        }
       }
-      if (!right) rkmer = ((rkmer << 2) | (u64)(child < 0 ? 0 : child)) & kmask;
+      __syncwarp();
+      if (!right) rkmer = ((rkmer << 2) | (u64)ch) & kmask;
       kmer = ck;
       count = childCnt;
       ++st;
@@ -783,10 +778,10 @@ class Corrector {
     }
     __syncwarp();
     if (nSteps) {
-      if (act && b == 0) {
-        cur[t].kmer = kmer;
-        cur[t].count = count;
-        cur[t].dist = dsum;
+      if (act) {
+        cur[lane].kmer = kmer;
+        cur[lane].count = count;
+        cur[lane].dist = dsum;
       }
       __syncwarp();
       step = st;
@@ -797,6 +792,18 @@ class Corrector {
         ctr->lookups_walk += 4ull * nSteps * nT;
       }
     }
+  }
+  // more than one successor in the graph: the exact tagging rules decide (rare on the fast path, kept out of line)
+  __device__ __noinline__ int pick_single_child(const u32 c4[4], u32 cm, u32 count) {
+    u32 col4[4];
+    for (int i = 0; i < 4; ++i) col4[i] = (cm >> i) & 1u;
+    const StepBounds sb = step_bounds_tab(count, P, tabs);
+    u8 tag[4];
+    tag_next_nodes(c4, col4, sb, P, false, tag);
+    int child = -1, n = 0;
+    for (int i = 0; i < 4; ++i)
+      if (tag[i] != kUnexpected) { child = i; ++n; }
+    return n == 1 ? child : -1;
   }
 #else
   inline void fast_walk(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border) {
@@ -987,7 +994,7 @@ class Corrector {
         for (u32 t = 0; t < nCur; ++t) {
           const Trail par = cur[t];
           u32 cnt[4], col[4];
-          table_next_counts(T, par.kmer, dirRight, k, cnt, col);
+          next_counts(par.kmer, cnt, col);
           if (ctr) ctr->lookups_walk += 4;
           u8 tag[4];
           const StepBounds sb = step_bounds_tab(par.count, P, tabs);
@@ -1316,7 +1323,7 @@ class Corrector {
         for (u32 t = 0; t < nCur; ++t) {
           Trail par = cur[t];
           u32 cnt[4], col[4];
-          table_next_counts(T, par.kmer, dirRight, k, cnt, col);
+          next_counts(par.kmer, cnt, col);
           if (ctr) ctr->lookups_walk += 4;
           u8 tag[4];
           const StepBounds sb = step_bounds_tab(par.count, P, tabs);

@@ -165,4 +165,62 @@ TALC_HDN int table_out_degree(const TableView& t, u64 kmer, bool right, u32 K, u
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------------------
+// Successor tables (device only): the walk never asks for ONE k-mer, it asks for the four successors of a k-mer
+// (getNextCountsFromDBG / getOutDegree, Jellyfish.cpp:308-321,383-393).  RIGHT successors x[1..]+b share the
+// (K-1)-mer context x[1..], LEFT successors b+x[..K-2] share x[..K-2]; so two more tables, keyed by context --
+// one holding, per (K-1)-mer c, the counts of the four k-mers c+b (RIGHT walks), the other those of b+c (LEFT
+// walks) -- answer such a question with ONE 32-byte sector instead of four.  They are derived on the device
+// from the k-mer table above whenever that one is sealed (built, imported or copied), so the exchange format
+// between GPUs stays the k-mer table.  Only "colour > 0" is ever tested on successors (Explorer.cpp:1258): one
+// bit per successor.
+struct __attribute__((aligned(32))) CtxBucket {
+  u64 ctx;      // (K-1)-mer context, kEmptyKey when free
+  u32 cnt[4];   // counts of the four successors in A,C,G,T order (0 = absent)
+  u32 colmask;  // bit b: successor b carries a junction colour
+  u32 pad;
+};
+struct CtxView {
+  const CtxBucket* b;
+  u64 mask;  // capacity - 1 (power of two)
+};
+TALC_HD u64 ctx_of(u64 kmer, bool right, u32 K) { return right ? (kmer & kmer_mask(K - 1)) : (kmer >> 2); }
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void load_bucket(const CtxBucket* p, u64& ctx, u32 cnt[4], u32& colmask) {
+  u64 x0, x1, x2, x3;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x0), "=l"(x1), "=l"(x2), "=l"(x3) : "l"(p));
+  ctx = x0;
+  cnt[0] = (u32)x1;
+  cnt[1] = (u32)(x1 >> 32);
+  cnt[2] = (u32)x2;
+  cnt[3] = (u32)(x2 >> 32);
+  colmask = (u32)x3;
+}
+__device__ __noinline__ void ctx_probe_from(const CtxView& v, u64 i, u64 ctx, u32 cnt[4], u32& colmask) {
+  for (;;) {
+    i = (i + 1) & v.mask;
+    u64 c;
+    load_bucket(v.b + i, c, cnt, colmask);
+    if (c == ctx) return;
+    if (c == kEmptyKey) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; colmask = 0; return; }
+  }
+}
+// the four successor counts of a context: home bucket and the next one are fetched together
+__device__ __forceinline__ void ctx_lookup(const CtxView& v, u64 ctx, u32 cnt[4], u32& colmask) {
+  const u64 i = hash_kmer(ctx) & v.mask, i2 = (i + 1) & v.mask;
+  u64 c0, c1;
+  u32 n1[4], m1;
+  load_bucket(v.b + i, c0, cnt, colmask);
+  load_bucket(v.b + i2, c1, n1, m1);
+  if (c0 == ctx) return;
+  const bool second = (c0 != kEmptyKey) & (c1 == ctx);
+  const bool none = (c0 == kEmptyKey) | (c1 == kEmptyKey);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) cnt[q] = second ? n1[q] : 0u;
+  colmask = second ? m1 : 0u;
+  if (!second && !none) ctx_probe_from(v, i2, ctx, cnt, colmask);
+}
+#endif
+
 }  // namespace talc

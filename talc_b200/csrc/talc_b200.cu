@@ -90,6 +90,41 @@ __global__ void table_colour_kernel(Slot* slots, u64 mask, const u64* keys, cons
     }
   }
 }
+// successor tables (table.cuh): every occupied slot of the k-mer table enters its RIGHT context bucket (key
+// without its last base) and its LEFT context bucket (key without its first base); a bucket is claimed with CAS
+// on the context, each of its four count fields has exactly one writer
+__global__ void ctx_fill_empty_kernel(CtxBucket* b, u64 capacity) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
+    b[i].ctx = kEmptyKey;
+    b[i].cnt[0] = b[i].cnt[1] = b[i].cnt[2] = b[i].cnt[3] = 0;
+    b[i].colmask = 0;
+    b[i].pad = 0;
+  }
+}
+__device__ __forceinline__ void ctx_insert(CtxBucket* tb, u64 mask, u64 ctx, u32 b, u32 count, u32 colour) {
+  u64 i = hash_kmer(ctx) & mask;
+  for (;;) {
+    unsigned long long prev = *(volatile unsigned long long*)&tb[i].ctx;
+    if (prev == kEmptyKey) prev = atomicCAS((unsigned long long*)&tb[i].ctx, (unsigned long long)kEmptyKey, (unsigned long long)ctx);
+    if (prev == kEmptyKey || prev == ctx) {
+      tb[i].cnt[b] = count;
+      if (colour) atomicOr(&tb[i].colmask, 1u << b);
+      return;
+    }
+    i = (i + 1) & mask;
+  }
+}
+__global__ void ctx_build_kernel(const Slot* slots, u64 capacity, CtxBucket* right, CtxBucket* left, u64 mask, u32 K) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
+    const Slot s = slots[i];
+    if (s.key == kEmptyKey) continue;
+    ctx_insert(right, mask, s.key >> 2, (u32)(s.key & 3ull), s.count, s.colour);
+    ctx_insert(left, mask, s.key & kmer_mask(K - 1), (u32)(s.key >> (2 * (K - 1))), s.count, s.colour);
+  }
+}
+
 __global__ void table_lookup_kernel(TableView tv, const u64* keys, u64 n, u32* counts, u32* colours, u8* found) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -203,6 +238,7 @@ struct CorrectArgs {
   u32* nOverflow;
   u32* outFull;
   u32* readKcycles;  // optional: per-read elapsed SM cycles / 1024 (tuning aid)
+  CtxView cright, cleft;  // successor tables
 };
 
 // One warp owns one read.  All 32 lanes run the per-read control flow on the same data, so the warp
@@ -234,6 +270,8 @@ __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) correct_kernel(CorrectAr
     const u32 r = A.order[qi];
     __syncwarp();
     cx.T = A.tv;
+    cx.CR = A.cright;
+    cx.CL = A.cleft;
     cx.P = A.P;
     cx.tabs = A.tabs;
     for (int i = 0; i < kNumCounters; ++i) ((u64*)&mine)[i] = 0;
@@ -423,6 +461,9 @@ struct talc_ctx {
   u64 nEntries = 0;
   bool tableOwned = true;
   bool tableReady = false;
+  CtxBucket* ctxRight = nullptr;  // successor tables, derived from the k-mer table when it is sealed
+  CtxBucket* ctxLeft = nullptr;
+  u64 ctxCap = 0;
   // scratch sizing
   u32 tier1Bytes = 1u << 20;    // per warp (= per read in flight)
   u32 tier2Bytes = 64u << 20;
@@ -435,6 +476,12 @@ struct talc_ctx {
 };
 
 static const u32 kModelTabN = 16384;
+static void free_ctx_tables(talc_ctx* c) {
+  if (c->ctxRight) cudaFree(c->ctxRight);
+  if (c->ctxLeft) cudaFree(c->ctxLeft);
+  c->ctxRight = c->ctxLeft = nullptr;
+  c->ctxCap = 0;
+}
 static thread_local std::string g_createError;
 
 #define CUDA_TRY(ctx, call)                                                                             \
@@ -530,6 +577,7 @@ void talc_ctx_destroy(talc_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->slots && c->tableOwned) cudaFree(c->slots);
+  free_ctx_tables(c);
   if (c->modelTabs) cudaFree(c->modelTabs);
   DevBuf* bufs[] = {&c->bases, &c->offs, &c->kmerOff, &c->nk, &c->cov, &c->order, &c->sortKey, &c->sortKeyOut, &c->sortVal,
                     &c->cubTmp, &c->arenas, &c->outArena, &c->outPos, &c->outLen, &c->outLen64, &c->status, &c->outOffs,
@@ -553,6 +601,7 @@ int talc_table_alloc(talc_ctx* c, uint64_t capacity_slots) {
   if (!c || capacity_slots < 2 || (capacity_slots & (capacity_slots - 1))) return TALC_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
   if (c->slots && c->tableOwned) cudaFree(c->slots);
+  free_ctx_tables(c);
   c->slots = nullptr;
   c->tableReady = false;
   CUDA_TRY(c, cudaMalloc((void**)&c->slots, capacity_slots * sizeof(Slot)));
@@ -569,9 +618,27 @@ int talc_table_device_ptr(talc_ctx* c, void** p) {
   *p = c->slots;
   return TALC_OK;
 }
+static int build_ctx_tables(talc_ctx* c) {
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  free_ctx_tables(c);
+  u64 cap = 4;
+  while (cap < 3 * c->nEntries + 4) cap <<= 1;  // load <= 1/3: a look-up rarely leaves its home pair of buckets
+  CUDA_TRY(c, cudaMalloc((void**)&c->ctxRight, cap * sizeof(CtxBucket)));
+  CUDA_TRY(c, cudaMalloc((void**)&c->ctxLeft, cap * sizeof(CtxBucket)));
+  c->ctxCap = cap;
+  const int blocks = c->sms * 8;
+  ctx_fill_empty_kernel<<<blocks, 256, 0, c->stream>>>(c->ctxRight, cap);
+  ctx_fill_empty_kernel<<<blocks, 256, 0, c->stream>>>(c->ctxLeft, cap);
+  ctx_build_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, c->capacity, c->ctxRight, c->ctxLeft, cap - 1, c->P.K);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return TALC_OK;
+}
 int talc_table_seal(talc_ctx* c, uint64_t n_entries) {
   if (!c || !c->slots) return TALC_ERR_ARG;
   c->nEntries = n_entries;
+  const int rc = build_ctx_tables(c);
+  if (rc) return rc;
   c->tableReady = true;
   return TALC_OK;
 }
@@ -650,6 +717,8 @@ static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vec
   if (dKeys) cudaFree(dKeys);
   if (dCounts) cudaFree(dCounts);
   c->nEntries = hN;
+  rc = build_ctx_tables(c);
+  if (rc) return rc;
   c->tableReady = true;
   if (n_kept) *n_kept = hN;
   return TALC_OK;
@@ -842,6 +911,8 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
 
   CorrectArgs A;
   A.tv = TableView{c->slots, c->capacity - 1};
+  A.cright = CtxView{c->ctxRight, c->ctxCap - 1};
+  A.cleft = CtxView{c->ctxLeft, c->ctxCap - 1};
   A.P = c->P;
   A.tabs.lower = c->modelTabs;
   A.tabs.upper = c->modelTabs + kModelTabN;
