@@ -955,6 +955,9 @@ class Corrector {
     u32 limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
     bool found = false;
     const u32 mk0 = scratch.mark();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1  // at most 5 start anchors: unrolled, the whole search would be in the binary five times
+#endif
     for (u32 s = 0; s < limit && !found; ++s) {
       scratch.release(mk0);
       if (ctr) ctr->gap_attempts++;
@@ -991,6 +994,9 @@ class Corrector {
         if (ctr) { ctr->steps_inner++; ctr->frontier_sum += nCur; }
         nNxt = 0;
         const bool complex_ = (nCur > P.max_branches);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
         for (u32 t = 0; t < nCur; ++t) {
           const Trail par = cur[t];
           u32 cnt[4], col[4];
@@ -1002,6 +1008,9 @@ class Corrector {
           u32 nChildren = 0;
           for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
           bool parentSlotTaken = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1  // the body is large: unrolled four times it floods the instruction cache
+#endif
           for (int i = 0; i < nt; ++i) {
             if (tag[i] == kUnexpected) continue;
             Trail ch;
@@ -1297,6 +1306,9 @@ class Corrector {
     bestShort.seq = (u64*)scratch.alloc(bestWords * 8);
     if (!bestLong.seq || !bestShort.seq) return false;
     const u32 mk0 = scratch.mark();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (u32 s = 0; s < limit; ++s) {
       scratch.release(mk0);
       int xdrop = (int)((int)kCheckInterval * 0.3 + 1);  // Q15: 2
@@ -1320,6 +1332,9 @@ class Corrector {
         if (ctr) { ctr->steps_border++; ctr->frontier_sum += nCur; }
         nNxt = 0;
         const bool complex_ = (nCur > 7);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
         for (u32 t = 0; t < nCur; ++t) {
           Trail par = cur[t];
           u32 cnt[4], col[4];
@@ -1331,6 +1346,9 @@ class Corrector {
           u32 nChildren = 0;
           for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
           bool parentSlotTaken = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1  // the body is large: unrolled four times it floods the instruction cache
+#endif
           for (int i = 0; i < nt; ++i) {
             if (tag[i] == kUnexpected) continue;
             Trail ch;
