@@ -143,9 +143,11 @@ class Corrector {
     if (!ok) {
       // a k-mer holding N: its successors x[1..]+b may or may not hold N; look each one up by bases
       int d = 0;
+      TALC_ROLLED
       for (u32 b = 0; b < 4; ++b) {
         bool ok2 = true;
         u64 v = 0;
+        TALC_ROLLED
         for (u32 j = 0; j < K(); ++j) {
           u32 c;
           if (right) c = (j + 1 < K()) ? rd.code(pos + j + 1) : b;
@@ -199,9 +201,11 @@ class Corrector {
     for (int nib = top; nib >= 0; --nib) {  // radix select, most significant nibble first
       u32 hist[16];
       u64 hsum[16];
+      TALC_ROLLED
       for (int i = 0; i < 16; ++i) { hist[i] = 0; hsum[i] = 0; }
       const u32 shift = 4 * nib;
       const u32 himask = (nib == 7) ? 0u : (~0u << (shift + 4));
+      TALC_ROLLED
       for (u32 i = lane; i < C; i += nl) {  // each lane bins every nl-th count
         const u32 v = cov[i];
         if (v < P.min_count) continue;
@@ -212,6 +216,7 @@ class Corrector {
       }
       u32 d = 15;
       bool found = false;
+      TALC_ROLLED
       for (int q = 0; q < 16; ++q) {
         const u32 h = warp_sum(hist[q]);
         const u64 hs = warp_sum64(hsum[q]);
@@ -228,6 +233,7 @@ class Corrector {
 
   TALC_HDN double seq_error_threshold() {
     u32 n = 0, maxv = 0;
+    TALC_ROLLED
     for (u32 i = lane_id(); i < C; i += lane_count()) {
       n += (cov[i] >= P.min_count) ? 1 : 0;
       maxv = cov[i] > maxv ? cov[i] : maxv;
@@ -255,9 +261,11 @@ class Corrector {
     // 32 k-mers per ballot: a run starts where a set bit follows a clear one (carry = last bit of the previous
     // word) and ends where a clear bit follows a set one; C <= 1 yields no region (Read.cpp:446)
     const u32 lane = threadIdx.x & 31u;
+    TALC_ROLLED
     for (int pass = 0; pass < 2; ++pass) {
       u32 n = 0, cs = 0, carry = 0;
       if (C > 1) {
+        TALC_ROLLED
         for (u32 base = 0; base < C; base += 32) {
           const u32 pos = base + lane;
           const u32 m = __ballot_sync(0xffffffffu, pos < C && cov[pos] >= P.min_count);
@@ -294,6 +302,7 @@ class Corrector {
     u32 n = 0;
     bool state = false;
     if (C > 1) {
+      TALC_ROLLED
       for (u32 pos = 0; pos < C; ++pos) {
         const bool in = cov[pos] >= P.min_count;
         if (in & !state) state = true;
@@ -307,6 +316,7 @@ class Corrector {
     u32 k = 0, cs = 0;
     state = false;
     if (C > 1) {
+      TALC_ROLLED
       for (u32 pos = 0; pos < C; ++pos) {
         const bool in = cov[pos] >= P.min_count;
         if (in & !state) { cs = pos; state = true; }
@@ -324,6 +334,7 @@ class Corrector {
     Region* kept = (Region*)keep.alloc((nregs ? nregs : 1) * sizeof(Region));
     if (!kept) return;
     u32 nk = 0;
+    TALC_ROLLED
     for (u32 reg = 0; reg < nregs; ++reg) {
       int span = 0;
       bool OK = true;
@@ -359,6 +370,7 @@ class Corrector {
         }
         if (OK) {
           u32 c = 0;
+          TALC_ROLLED
           for (u32 i = ns; i <= ne; ++i) c = c < cov[i] ? cov[i] : c;
           if (!expected_by_model(c, (u32)thr, P.alpha, true)) {
             kept[nk].start = ns;
@@ -369,6 +381,7 @@ class Corrector {
       }
     }
     if (nk > 0) {
+      TALC_ROLLED
       for (u32 i = 0; i < nk; ++i) regs[i] = kept[i];
       nregs = nk;
     }
@@ -381,6 +394,7 @@ class Corrector {
     headPresent = tailPresent = false;
     if (regs[0].start > 0) { headPresent = true; len += regs[0].start; }
     if (regs[nregs - 1].end + 1 < C) { tailPresent = true; len += Lr - (regs[nregs - 1].end + K()); }
+    TALC_ROLLED
     for (u32 i = 0; i + 1 < nregs; ++i) {
       if (regs[i].end + K() < regs[i].start) return false;  // undefined in the reference; cannot sum to L
       len += regs[i].end + K() - regs[i].start;
@@ -399,6 +413,7 @@ class Corrector {
     SortKey* keys = (SortKey*)scratch.alloc(n * sizeof(SortKey));
     AnchorRec* tmp = (AnchorRec*)scratch.alloc(n * sizeof(AnchorRec));
     if (!keys || !tmp) return;
+    TALC_ROLLED
     for (u32 i = 0; i < n; ++i) {
       int d = cc - (int)a[i].count;
       keys[i].key = d < 0 ? -(i64)d : (i64)d;
@@ -406,6 +421,7 @@ class Corrector {
       tmp[i] = a[i];
     }
     std_sort_keys(keys, n);
+    TALC_ROLLED
     for (u32 i = 0; i < n; ++i) a[i] = tmp[keys[i].idx];
     scratch.release(mk);
   }
@@ -447,6 +463,7 @@ class Corrector {
       }
       if (left) --j; else ++j;
     }
+    TALC_ROLLED
     for (u32 anc = 0; anc < nPos; ++anc) {
       const int degree = out_degree(anchorPos[anc], left);  // LEFT region looks RIGHT, and vice versa
       if ((anc == 0) || ((anc != 0) & (degree > 1))) {
@@ -502,6 +519,7 @@ class Corrector {
     slotPool = (u64*)scratch.alloc(n * slotWords * 8);
     if (!freeList || !slotPool) return false;
     nFree = n;
+    TALC_ROLLED
     for (u32 i = lane_id(); i < n; i += lane_count()) freeList[i] = (u16)(n - 1 - i);
     warp_sync();
     nCur = nNxt = 0;
@@ -517,6 +535,7 @@ class Corrector {
     const u32 nw = (nbases + 31) / 32;
     u64* d = slot_ptr(dst);
     const u64* s = slot_ptr(src);
+    TALC_ROLLED
     for (u32 i = lane_id(); i < nw; i += lane_count()) d[i] = s[i];  // the warp's lanes share the copy
     warp_sync();
   }
@@ -526,7 +545,9 @@ class Corrector {
     const int s = slot_alloc();
     if (s < 0) return false;
     u64* w = slot_ptr((u32)s);
+    TALC_ROLLED
     for (u32 i = 0; i < slotWords; ++i) w[i] = 0;
+    TALC_ROLLED
     for (u32 i = 0; i < K(); ++i) {
       // walk order: RIGHT = k-mer as is, LEFT = k-mer reversed
       const u32 src = dirRight ? i : (K() - 1 - i);
@@ -557,9 +578,11 @@ class Corrector {
       u64 nd = needle;
       if (!dirRight) {
         nd = 0;
+        TALC_ROLLED
         for (u32 i = 0; i < k; ++i) nd |= ((needle >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
       }
       const u32 lane = threadIdx.x & 31u;
+      TALC_ROLLED
       for (u32 base = 0; (u64)base * stride + k <= plen; base += 32) {
         const u32 p = (base + lane) * stride;
         bool match = false;
@@ -571,13 +594,16 @@ class Corrector {
     }
 #endif
     if (dirRight) {
+      TALC_ROLLED
       for (u32 p = 0; p + k <= plen; p += stride)
         if (path_kmer_fwd(w, p, k) == needle) return p > 0;
       return false;
     }
     // LEFT: actual sequence is the reversed walk; actual window p <-> walk window plen-k-p, reversed
     u64 rev = 0;
+    TALC_ROLLED
     for (u32 i = 0; i < k; ++i) rev |= ((needle >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
+    TALC_ROLLED
     for (u32 p = 0; p + k <= plen; p += stride)
       if (path_kmer_fwd(w, plen - k - p, k) == rev) return p > 0;
     return false;
@@ -605,6 +631,7 @@ class Corrector {
     const u32 stride = (P.cycle_mode == 0) ? k : 1u;
     const u64 kmask = kmer_mask(k);
     u64 rkmer = 0;  // the last k-mer with its bases in reverse order
+    TALC_ROLLED
     for (u32 i = 0; i < k; ++i) rkmer |= ((kmer >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
     // the word of the packed sequence that is being filled lives in a register
     u32 cwIdx = (k + st) >> 5;
@@ -628,6 +655,7 @@ class Corrector {
       const u64 ck = kmer_next(kmer, (u32)child, right, k);
       if (!border) {
         bool aim = false;
+        TALC_ROLLED
         for (u32 a = 0; a < nAims; ++a) aim |= (aims[a].kmer == ck);
         if (aim) break;
       }
@@ -636,6 +664,7 @@ class Corrector {
         bool hit = false, cyc = false;
         // LEFT walks compare in walk order, i.e. against the reversed k-mer, which is maintained incrementally
         const u64 needle = right ? ck : (((rkmer << 2) | (u64)child) & kmask);
+        TALC_ROLLED
         for (u32 p = 0; p + k <= plen && !hit; p += stride) {
           const u32 wi0 = right ? p : (plen - k - p);
           const u32 wi = wi0 >> 5, off = 2 * (wi0 & 31);
@@ -710,6 +739,7 @@ class Corrector {
     u32 count = tr.count;
     double dsum = tr.dist;
     u64 rkmer = 0;  // the last k-mer with its bases in reverse order (LEFT walks compare in walk order)
+    TALC_ROLLED
     for (u32 i = 0; i < k; ++i) rkmer |= ((kmer >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
     u32 st = step, nSteps = 0;
 #pragma unroll 1
@@ -745,9 +775,11 @@ class Corrector {
       if (plen > k) {
         const u64 myNeedle = right ? ck : (((rkmer << 2) | (u64)ch) & kmask);
         bool cyc = false;
+        TALC_ROLLED
         for (u32 q = 0; q < nT && !cyc; ++q) {
           const u64 needle = __shfl_sync(0xffffffffu, myNeedle, q);
           const u64* wq = (const u64*)__shfl_sync(0xffffffffu, (unsigned long long)w, q);
+          TALC_ROLLED
           for (u32 base = 0; (u64)base * stride + k <= plen; base += 32) {
             const u32 p = (base + lane) * stride;
             bool match = false;
@@ -796,11 +828,13 @@ class Corrector {
   // more than one successor in the graph: the exact tagging rules decide (rare on the fast path, kept out of line)
   __device__ __noinline__ int pick_single_child(const u32 c4[4], u32 cm, u32 count) {
     u32 col4[4];
+    TALC_ROLLED
     for (int i = 0; i < 4; ++i) col4[i] = (cm >> i) & 1u;
     const StepBounds sb = step_bounds_tab(count, P, tabs);
     u8 tag[4];
     tag_next_nodes(c4, col4, sb, P, false, tag);
     int child = -1, n = 0;
+    TALC_ROLLED
     for (int i = 0; i < 4; ++i)
       if (tag[i] != kUnexpected) { child = i; ++n; }
     return n == 1 ? child : -1;
@@ -827,6 +861,7 @@ class Corrector {
     u32 nNew = 0;
     bool isComplex = false;
     u32 nb = n < MAXP ? n : MAXP;
+    TALC_ROLLED
     for (u32 t = 0; t < n; ++t) {
       rankings[t].idx = t; rankings[t].r1 = 0; rankings[t].r2 = 0; rankings[t].sum = 0;
       sk[t].key = -(i64)nxt[t].score;  // sortByScore: descending score
@@ -836,11 +871,13 @@ class Corrector {
     {
       u32 rk = 0;
       rankings[sk[0].idx].r1 = 0;
+      TALC_ROLLED
       for (u32 t = 1; t < n; ++t) {
         if (!(sk[t].key == sk[t - 1].key)) rk++;
         rankings[sk[t].idx].r1 = rk;
       }
     }
+    TALC_ROLLED
     for (u32 t = 0; t < n; ++t) {
       sk[t].key = sort_key_of_nonneg_double(nxt[t].dist);  // sortByLikelihood: ascending distance
       sk[t].idx = t;
@@ -849,18 +886,22 @@ class Corrector {
     {
       u32 rk = 0;
       rankings[sk[0].idx].r2 = 0;
+      TALC_ROLLED
       for (u32 t = 1; t < n; ++t) {
         if (!(sk[t].key == sk[t - 1].key)) rk++;
         rankings[sk[t].idx].r2 = rk;
       }
     }
+    TALC_ROLLED
     for (u32 t = 0; t < n; ++t) {
       rankings[t].sum = rankings[t].r1 + rankings[t].r2;
       if ((rankings[t].sum == 0) || (n <= MAXP)) newr[nNew++] = rankings[t];
     }
     if (nNew == 0) {
+      TALC_ROLLED
       for (u32 t = 0; t < n; ++t) { sk[t].key = (i64)rankings[t].r1; sk[t].idx = t; tmpr[t] = rankings[t]; }
       std_sort_keys(sk, n);  // sortByMaxScore
+      TALC_ROLLED
       for (u32 t = 0; t < n; ++t) rankings[t] = tmpr[sk[t].idx];
       u32 s = 0;
       bool ties = false;
@@ -882,14 +923,19 @@ class Corrector {
         }
         if ((nNew > MAXP) & (newr[0].r1 == atMax.r1)) {  // Q16
           isComplex = true;
+          TALC_ROLLED
           for (u32 t = 0; t < nNew; ++t) { sk[t].key = (i64)newr[t].r2; sk[t].idx = t; tmpr[t] = newr[t]; }
           std_sort_keys(sk, nNew);  // sortByMinDist
+          TALC_ROLLED
           for (u32 t = 0; t < nNew; ++t) newr[t] = tmpr[sk[t].idx];
+          TALC_ROLLED
           for (u32 t = 0; t < MAXP; ++t) kept[nKept++] = newr[t].idx;
         }
       }
+      TALC_ROLLED
       for (u32 t = 0; t < nNew; ++t) kept[nKept++] = newr[t].idx;
     } else {
+      TALC_ROLLED
       for (u32 t = 0; t < nNew; ++t) kept[nKept++] = newr[t].idx;
     }
     scratch.release(mk);
@@ -902,11 +948,16 @@ class Corrector {
     const u32 mk = scratch.mark();
     u8* used = (u8*)scratch.alloc(nNxt ? nNxt : 1);
     if (!used) return false;
+    TALC_ROLLED
     for (u32 i = 0; i < nNxt; ++i) used[i] = 0;
+    TALC_ROLLED
     for (u32 i = 0; i < nKept; ++i) used[kept[i]] = 1;
+    TALC_ROLLED
     for (u32 i = 0; i < nNxt; ++i)
       if (!used[i]) slot_free(nxt[i].slot);
+    TALC_ROLLED
     for (u32 i = 0; i < nNxt; ++i) used[i] = 0;
+    TALC_ROLLED
     for (u32 i = 0; i < nKept; ++i) {
       Trail t = nxt[kept[i]];
       if (used[kept[i]]) {  // duplicate of an already adopted trail: private copy of the sequence
@@ -1006,6 +1057,7 @@ class Corrector {
           const StepBounds sb = step_bounds_tab(par.count, P, tabs);
           const int nt = tag_next_nodes(cnt, col, sb, P, complex_, tag);
           u32 nChildren = 0;
+          TALC_ROLLED
           for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
           bool parentSlotTaken = false;
 #if defined(__CUDA_ARCH__)
@@ -1033,6 +1085,7 @@ class Corrector {
             // cycle test looks at the parent's sequence only, so it may run before the append
             bool aim = false;
             u32 aimPos = 0;
+            TALC_ROLLED
             for (u32 a = 0; a < nAims; ++a) {  // Trail.cpp:273-285, first match in sorted aim order
               if (aims[a].kmer == ch.kmer) { aim = true; aimPos = aims[a].pos; break; }
             }
@@ -1074,6 +1127,7 @@ class Corrector {
                 if (nBrSeq >= maxKeep) { scratch.overflow = 1; return false; }
                 u64* dst = brSeq + (u64)nBrSeq * slotWords;
                 const u64* src = slot_ptr(ch.slot);
+                TALC_ROLLED
                 for (u32 wi = 0; wi < (clen + 31) / 32; ++wi) dst[wi] = src[wi];
                 b.seqSlot = (i32)nBrSeq++;
               }
@@ -1096,6 +1150,7 @@ class Corrector {
           u32 bound = k + step + P.window;
           const u32 rn = (bound >= ref.len) ? ref.len : bound;
           if (P.q11_zero) {
+            TALC_ROLLED
             for (u32 j = 0; j < nNxt; ++j) {
               const SeqView pv = view_of_path(slot_ptr(nxt[j].slot), k + step);
               nxt[j].score = overlap_score(refv, rn, pv, k + step, scratch, &dps);
@@ -1118,12 +1173,15 @@ class Corrector {
       if (nBr > 0) {
         // Q9: if cutAnchors rejected some bridges the survivors are the FIRST nOk entries
         u32 nOk = 0;
+        TALC_ROLLED
         for (u32 t = 0; t < nBr; ++t) nOk += br[t].ok ? 1 : 0;
         const u32 nUse = nOk;  // == nBr when nothing was rejected
         if (nUse > 0) {
           u32 best = 0;
+          TALC_ROLLED
           for (u32 i = 1; i < nUse; ++i)
             if (br[i].score > br[best].score) best = i;
+          TALC_ROLLED
           for (u32 i = best + 1; i < nUse; ++i)
             if (br[i].score == br[best].score && br[i].md > br[best].md) best = i;  // sequential update == Q21
           const BridgeRec& B = br[best];
@@ -1140,6 +1198,7 @@ class Corrector {
               if (B.seqSlot < 0) { scratch.overflow = 1; return false; }  // cannot happen: see fold argument
               const u64* w = brSeq + (u64)B.seqSlot * slotWords;
               PathView pv; pv.w = w; pv.len = B.fullLen;
+              TALC_ROLLED
               for (u32 i = 0; i < bestLen; ++i) {
                 const u32 wi = dirRight ? (k + i) : (B.fullLen - k - 1 - i);
                 dst[i] = code_char(pv.code(wi));
@@ -1240,6 +1299,7 @@ class Corrector {
       dst.ref_start = ref.start;
       dst.ref_len = ref.len;
       const u64* src = slot_ptr(t.slot);
+      TALC_ROLLED
       for (u32 wi = 0; wi < (pathKeep + 31) / 32; ++wi) dst.seq[wi] = src[wi];
     }
     (void)newLen;
@@ -1257,6 +1317,7 @@ class Corrector {
     u8* okf = (u8*)scratch.alloc(nNxt);
     if (!okf) return false;
     u32 nSel = 0;
+    TALC_ROLLED
     for (u32 t = 0; t < nNxt; ++t) {
       const bool ok = trail_seed_extend(nxt[t], tlen, refv, xdrop);
       if (scratch.overflow) return false;
@@ -1269,6 +1330,7 @@ class Corrector {
     }
     xdrop = new_xdrop;
     if (nSel == 0) {
+      TALC_ROLLED
       for (u32 t = 0; t < nNxt; ++t) {
         if (!record_edge(nxt[t], tlen, ref, whichStart, bestLong, bestShort)) return false;
         slot_free(nxt[t].slot);
@@ -1276,6 +1338,7 @@ class Corrector {
       nNxt = 0;
     } else {
       u32 w = 0;
+      TALC_ROLLED
       for (u32 t = 0; t < nNxt; ++t) {
         if (okf[t]) nxt[w++] = nxt[t];
         else slot_free(nxt[t].slot);
@@ -1294,6 +1357,7 @@ class Corrector {
     const u32 limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
     // running bests of m_longPaths / m_shortPaths across all anchors
     u32 maxGap = 0;
+    TALC_ROLLED
     for (u32 s = 0; s < limit; ++s) {
       const u32 g = (location == 0) ? anchors[s].pos : (rd.len - (anchors[s].pos + k));
       maxGap = g > maxGap ? g : maxGap;
@@ -1344,6 +1408,7 @@ class Corrector {
           const StepBounds sb = step_bounds_tab(par.count, P, tabs);
           const int nt = tag_next_nodes(cnt, col, sb, P, complex_, tag);
           u32 nChildren = 0;
+          TALC_ROLLED
           for (int i = 0; i < nt; ++i) nChildren += (tag[i] != kUnexpected) ? 1 : 0;
           bool parentSlotTaken = false;
 #if defined(__CUDA_ARCH__)
@@ -1425,6 +1490,7 @@ class Corrector {
         // walk-order sequence: trail prefix, then raw border; minus the first K (the anchor);
         // TAIL is already in read orientation, HEAD is reversed
         PathView pv; pv.w = W.seq; pv.len = W.path_keep;
+        TALC_ROLLED
         for (u32 i = 0; i < wlen; ++i) {
           const u32 wi = k + i;  // walk index
           u8 ch;
@@ -1462,12 +1528,15 @@ class Corrector {
       u64* pw = (u64*)keep.alloc(nw4 * 8);
       if (!pw) return kReadOverflow;
       bool hasN = false;
+      TALC_ROLLED
       for (u32 i = lane_id(); i < rd.len; i += lane_count()) hasN |= rd.code(i) > 3;
       hasN = warp_any(hasN);
       const u32 per = hasN ? 16u : 32u, bits = hasN ? 4u : 2u;
       const u32 nw = (rd.len + per - 1) / per + 1;
+      TALC_ROLLED
       for (u32 wi = lane_id(); wi < nw; wi += lane_count()) {
         u64 x = 0;
+        TALC_ROLLED
         for (u32 j = 0; j < per; ++j) {
           const u32 idx = wi * per + j;
           x = (x << bits) | (u64)((idx < rd.len) ? rd.code(idx) : 0u);
@@ -1480,6 +1549,7 @@ class Corrector {
     }
     // Read::reCoverage gate (Read.cpp:190, Q1: strictly greater)
     u32 nbIn = 0;
+    TALC_ROLLED
     for (u32 i = lane_id(); i < C; i += lane_count()) nbIn += (cov[i] > P.min_count) ? 1 : 0;
     nbIn = warp_sum(nbIn);
     if (nbIn == 0) return kReadNoSolid;
@@ -1495,13 +1565,16 @@ class Corrector {
     tailRaw = tailPresent ? rd.len - (regs[nregs - 1].end + k) : 0;
     gapPiece = (Piece*)keep.alloc((nregs ? nregs : 1) * sizeof(Piece));
     if (!gapPiece) return kReadOverflow;
+    TALC_ROLLED
     for (u32 i = 0; i + 1 < nregs; ++i) gapPiece[i].len = -1;
     headPiece.len = tailPiece.len = -1;
     complexRegion = false;
     // Read::correct2 (Read.cpp:336-386)
+    TALC_ROLLED
     for (u32 reg = 0; reg + 1 < nregs; ++reg) {
       if (ctr) ctr->gaps++;
       bool success = false;
+      TALC_ROLLED
       for (int attempt = 0; attempt < 2 && !success; ++attempt) {
         // initializeINNER (Explorer.cpp:228-243)
         scratch.release(0);
@@ -1568,6 +1641,7 @@ class Corrector {
     const u32 k = P.K;
     u32 n = 0;
     n += (headPiece.len >= 0) ? (u32)headPiece.len : (headPresent ? headRaw : 0);
+    TALC_ROLLED
     for (u32 i = 0; i < nregs; ++i) {
       n += regs[i].end + k - regs[i].start;
       if (i + 1 < nregs) n += (gapPiece[i].len >= 0) ? (u32)gapPiece[i].len : gapRawLen(i);
@@ -1585,30 +1659,38 @@ class Corrector {
     const u32 k = P.K;
     u32 o = 0;
     if (headPiece.len >= 0) {
+      TALC_ROLLED
       for (u32 i = lane; i < (u32)headPiece.len; i += nl) out[o + i] = keep.base[headPiece.off + i];
       o += (u32)headPiece.len;
     } else if (headPresent) {
+      TALC_ROLLED
       for (u32 i = lane; i < headRaw; i += nl) out[o + i] = code_char(rd.code(i));
       o += headRaw;
     }
+    TALC_ROLLED
     for (u32 r = 0; r < nregs; ++r) {
       const u32 a = regs[r].start, n = regs[r].end + k - regs[r].start;
+      TALC_ROLLED
       for (u32 i = lane; i < n; i += nl) out[o + i] = code_char(rd.code(a + i));
       o += n;
       if (r + 1 < nregs) {
         if (gapPiece[r].len >= 0) {
+          TALC_ROLLED
           for (u32 i = lane; i < (u32)gapPiece[r].len; i += nl) out[o + i] = keep.base[gapPiece[r].off + i];
           o += (u32)gapPiece[r].len;
         } else {
           const u32 g0 = regs[r].end + k, gn = gapRawLen(r);
+          TALC_ROLLED
           for (u32 i = lane; i < gn; i += nl) out[o + i] = code_char(rd.code(g0 + i));
           o += gn;
         }
       }
     }
     if (tailPiece.len >= 0) {
+      TALC_ROLLED
       for (u32 i = lane; i < (u32)tailPiece.len; i += nl) out[o + i] = keep.base[tailPiece.off + i];
     } else if (tailPresent) {
+      TALC_ROLLED
       for (u32 i = lane; i < tailRaw; i += nl) out[o + i] = code_char(rd.code(rd.len - tailRaw + i));
     }
   }

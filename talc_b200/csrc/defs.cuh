@@ -10,6 +10,13 @@
 
 // TALC_HD: small helpers, always inlined.  TALC_HDN: the big routines; they stay real calls on the device
 // (forcing the whole per-read pipeline into one function body makes the NVVM optimiser run for an hour).
+// Loops of the per-read control code stay rolled on the device: the correction kernel is bound by instruction
+// delivery, and unrolled copies of rarely-hot loop bodies only evict the hot loops.
+#if defined(__CUDACC__)
+#define TALC_ROLLED _Pragma("unroll 1")
+#else
+#define TALC_ROLLED
+#endif
 #if defined(__CUDACC__)
 #define TALC_HD __host__ __device__ __forceinline__
 #define TALC_HDN __host__ __device__ __noinline__

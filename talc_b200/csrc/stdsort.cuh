@@ -29,6 +29,7 @@ TALC_HD void move_median_to_first(T* result, T* a, T* b, T* c, Less less) {
 
 template <class T, class Less>
 TALC_HD T* unguarded_partition(T* first, T* last, T* pivot, Less less) {
+  TALC_ROLLED
   for (;;) {
     while (less(*first, *pivot)) ++first;
     --last;
@@ -73,6 +74,7 @@ TALC_HD void heap_sort_all(T* first, T* last, Less less) {  // __partial_sort(fi
   const i64 len = last - first;
   if (len >= 2) {  // __make_heap
     i64 parent = (len - 2) / 2;
+    TALC_ROLLED
     for (;;) {
       T value = first[parent];
       adjust_heap(first, parent, len, value, less);
@@ -104,9 +106,11 @@ TALC_HD void unguarded_linear_insert(T* last, Less less) {
 template <class T, class Less>
 TALC_HD void insertion_sort(T* first, T* last, Less less) {
   if (first == last) return;
+  TALC_ROLLED
   for (T* i = first + 1; i != last; ++i) {
     if (less(*i, *first)) {
       T val = *i;
+      TALC_ROLLED
       for (T* p = i; p != first; --p) *p = *(p - 1);  // move_backward(first, i, i + 1)
       *first = val;
     } else
@@ -127,6 +131,7 @@ TALC_HD void std_sort(T* first, T* last, Less less) {
   Frame stack[40];  // depth limit 2*floor(lg n) <= 38 for any n < 2^19
   int sp = 0;
   int lg = 0;
+  TALC_ROLLED
   for (i64 v = n; v > 1; v >>= 1) ++lg;  // std::__lg
   stack[sp++] = Frame{first, last, 2 * lg};
   while (sp > 0) {
@@ -147,6 +152,7 @@ TALC_HD void std_sort(T* first, T* last, Less less) {
   // __final_insertion_sort
   if (n > 16) {
     insertion_sort(first, first + 16, less);
+    TALC_ROLLED
     for (T* i = first + 16; i != last; ++i) unguarded_linear_insert(i, less);
   } else
     insertion_sort(first, last, less);
