@@ -198,159 +198,29 @@ TALC_HDN int lcs_length_scalar(const SeqView& a, u32 an, const SeqView& b, u32 b
 }
 
 #if defined(__CUDA_ARCH__)
-// Device forms: the 64-row blocks of the pattern are spread over the lanes and the text streams through them
-// as a systolic pipeline -- lane L works on text column t-L at time t and hands its horizontal delta (Myers)
-// or its addition carry (LCS) to lane L+1 with one shuffle.  More than 32 blocks are processed in stripes with
-// the boundary deltas parked in the scratch arena, exactly like the scalar form does for every block.
-__device__ __noinline__ int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
-  // rows (bit-parallel, 64 per lane) = the LONGER sequence while it fits one stripe of 32 lanes: the systolic
-  // pipeline then runs for shorter + blocks steps instead of longer + blocks; beyond 2048 the shorter one again
-  const u32 longer = an >= bn ? an : bn;
-  if (longer <= 64) return nw_distance_scalar(a, an, b, bn, ar, st);
-  const bool a_is_pat = (longer <= 2048) ? (an >= bn) : (an <= bn);
-  const u32 pn = a_is_pat ? an : bn;
-  const SeqView pat = a_is_pat ? a : b;  // by value: the fields stay in registers
-  const SeqView txt = a_is_pat ? b : a;
-  const u32 tn = a_is_pat ? bn : an;
-  if (st) st->cells_nw += (u64)an * bn;
-  const u32 lane = threadIdx.x & 31u;
-  const u32 nblocks = (pn + 63) / 64;
-  const u32 mk = ar.mark();
-  signed char* h = nullptr;
-  if (nblocks > 32) {
-    h = (signed char*)ar.alloc(tn);
-    if (!h) return 0;
-  }
-  int score = 0;
-  for (u32 s0 = 0; s0 < nblocks; s0 += 32) {
-    const u32 blk = s0 + lane;
-    const bool haveBlk = blk < nblocks;
-    const u32 nb = (nblocks - s0 < 32u) ? (nblocks - s0) : 32u;  // blocks in this stripe
-    u64 peq[5] = {0, 0, 0, 0, 0};
-    if (haveBlk) build_peq(pat, pn, blk, peq);
-    const bool last = haveBlk && (blk + 1 == nblocks);
-    const u32 top = last ? (pn - blk * 64 - 1) : 63;
-    u64 Pv = ~0ull, Mv = 0;
-    int houtPrev = 0;
-    u32 cPrev = 4;
-    int acc = 0;
-    __syncwarp();
-    for (u32 t = 0; t < tn + nb - 1; ++t) {
-      int hin = __shfl_up_sync(0xffffffffu, houtPrev, 1);
-      u32 c = __shfl_up_sync(0xffffffffu, cPrev, 1);
-      if (lane == 0) {
-        c = (t < tn) ? txt.code(t) : 4u;
-        hin = (s0 == 0) ? 1 : ((t < tn) ? (int)h[t] : 0);
-      }
-      const bool valid = haveBlk && (t >= lane) && (t - lane < tn);
-      int hout = 0;
-      if (valid) {
-        u64 Eq = peq[c];
-        const u64 hneg = (hin < 0) ? 1ull : 0ull;
-        const u64 Xv = Eq | Mv;
-        Eq |= hneg;
-        const u64 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-        u64 Ph = Mv | ~(Xh | Pv);
-        u64 Mh = Pv & Xh;
-        hout = (int)((Ph >> top) & 1ull) - (int)((Mh >> top) & 1ull);
-        Ph <<= 1;
-        Mh <<= 1;
-        Mh |= hneg;
-        Ph |= (hin > 0) ? 1ull : 0ull;
-        Pv = Mh | ~(Xv | Ph);
-        Mv = Ph & Xv;
-        if (last) acc += hout;
-        else if (lane == 31) h[t - lane] = (signed char)hout;  // stripe boundary
-      }
-      houtPrev = hout;
-      cPrev = c;
-    }
-    // the lane that owns the last block carries the score
-    const int lastLane = (int)((nblocks - 1) - s0);
-    if (lastLane >= 0 && lastLane < 32) score = (int)pn + __shfl_sync(0xffffffffu, acc, lastLane);
-    __syncwarp();
-  }
-  ar.release(mk);
-  return score;
-}
-
-__device__ __noinline__ int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
-  const u32 longer = an >= bn ? an : bn;
-  if (longer <= 64) return lcs_length_scalar(a, an, b, bn, ar, st);
-  const bool a_is_pat = (longer <= 2048) ? (an >= bn) : (an <= bn);  // see nw_distance
-  const u32 pn = a_is_pat ? an : bn;
-  const SeqView pat = a_is_pat ? a : b;
-  const SeqView txt = a_is_pat ? b : a;
-  const u32 tn = a_is_pat ? bn : an;
-  if (st) st->cells_lcs += (u64)an * bn;
-  const u32 lane = threadIdx.x & 31u;
-  const u32 nblocks = (pn + 63) / 64;
-  const u32 mk = ar.mark();
-  u8* carry = nullptr;
-  if (nblocks > 32) {
-    carry = (u8*)ar.alloc(tn);
-    if (!carry) return 0;
-  }
-  int lcs = 0;
-  for (u32 s0 = 0; s0 < nblocks; s0 += 32) {
-    const u32 blk = s0 + lane;
-    const bool haveBlk = blk < nblocks;
-    const u32 nb = (nblocks - s0 < 32u) ? (nblocks - s0) : 32u;
-    u64 peq[5] = {0, 0, 0, 0, 0};
-    if (haveBlk) build_peq(pat, pn, blk, peq);
-    const bool last = haveBlk && (blk + 1 == nblocks);
-    const u32 rows = last ? (pn - blk * 64) : 64;
-    u64 V = ~0ull;
-    u32 coutPrev = 0, cPrev = 4;
-    __syncwarp();
-    for (u32 t = 0; t < tn + nb - 1; ++t) {
-      u32 cin = __shfl_up_sync(0xffffffffu, coutPrev, 1);
-      u32 c = __shfl_up_sync(0xffffffffu, cPrev, 1);
-      if (lane == 0) {
-        c = (t < tn) ? txt.code(t) : 4u;
-        cin = (s0 == 0) ? 0u : ((t < tn) ? (u32)carry[t] : 0u);
-      }
-      const bool valid = haveBlk && (t >= lane) && (t - lane < tn);
-      u32 cout = 0;
-      if (valid) {
-        const u64 M = peq[c];
-        const u64 U = V & M;
-        const u64 tt = V + U;
-        const u64 sum = tt + (u64)cin;
-        cout = (u32)(tt < V) | (u32)(sum < tt);
-        V = sum | (V & ~M);
-        if (!last && lane == 31) carry[t - lane] = (u8)cout;
-      }
-      coutPrev = cout;
-      cPrev = c;
-    }
-    int z = 0;
-    if (haveBlk) z = __popcll(~V & ((rows == 64) ? ~0ull : ((1ull << rows) - 1ull)));
-    lcs += (int)__reduce_add_sync(0xffffffffu, (unsigned)z);
-    __syncwarp();
-  }
-  ar.release(mk);
-  return lcs;
-}
 // Edit distance and LCS length of the same pair in ONE systolic pass (Trajectory::scoreSequence computes both,
 // Trajectory.cpp:239-243): the text stream, the match masks and the pipeline are shared, the two recurrences are
 // independent dependency chains that fill each other's issue slots, and the two hand-over values travel in one
 // shuffle.  Falls back to the two separate routines when a stripe of 32 blocks does not hold the longer sequence.
-__device__ __noinline__ int nw_lcs_fused(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st, int& lcsOut) {
+// `what`: 1 = the caller wants the distance, 2 = the LCS length, 3 = both (only decides which cells are tallied;
+// ONE routine serves all three so that the scoring code the warps compete for in the instruction cache stays small).
+__device__ __noinline__ int nw_lcs_fused(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st, int& lcsOut,
+                                         int what) {
   const u32 longer = an >= bn ? an : bn;
-  if (longer <= 64 || longer > 2048) {
-    const int d = nw_distance(a, an, b, bn, ar, st);
-    lcsOut = lcs_length(a, an, b, bn, ar, st);
+  if (longer > 2048) {  // more than one stripe of 32 blocks: the striped scalar forms (rare)
+    const int d = (what & 1) ? nw_distance_scalar(a, an, b, bn, ar, st) : 0;
+    lcsOut = (what & 2) ? lcs_length_scalar(a, an, b, bn, ar, st) : 0;
     return d;
   }
+  // rows (bit-parallel, 64 per lane) = the LONGER sequence: the pipeline runs for shorter + blocks steps
   const bool a_is_pat = an >= bn;
   const u32 pn = a_is_pat ? an : bn;
-  const SeqView pat = a_is_pat ? a : b;
+  const SeqView pat = a_is_pat ? a : b;  // by value: the fields stay in registers
   const SeqView txt = a_is_pat ? b : a;
   const u32 tn = a_is_pat ? bn : an;
   if (st) {
-    st->cells_nw += (u64)an * bn;
-    st->cells_lcs += (u64)an * bn;
+    if (what & 1) st->cells_nw += (u64)an * bn;
+    if (what & 2) st->cells_lcs += (u64)an * bn;
   }
   const u32 lane = threadIdx.x & 31u;
   const u32 nblocks = (pn + 63) / 64;  // <= 32
@@ -411,6 +281,15 @@ __device__ __noinline__ int nw_lcs_fused(const SeqView& a, u32 an, const SeqView
   __syncwarp();
   return score;
 }
+__device__ __forceinline__ int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+  int l;
+  return nw_lcs_fused(a, an, b, bn, ar, st, l, 1);
+}
+__device__ __forceinline__ int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
+  int l;
+  nw_lcs_fused(a, an, b, bn, ar, st, l, 2);
+  return l;
+}
 #else
 inline int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   return nw_distance_scalar(a, an, b, bn, ar, st);
@@ -418,9 +297,9 @@ inline int nw_distance(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena
 inline int lcs_length(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st) {
   return lcs_length_scalar(a, an, b, bn, ar, st);
 }
-inline int nw_lcs_fused(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st, int& lcsOut) {
-  const int d = nw_distance_scalar(a, an, b, bn, ar, st);
-  lcsOut = lcs_length_scalar(a, an, b, bn, ar, st);
+inline int nw_lcs_fused(const SeqView& a, u32 an, const SeqView& b, u32 bn, Arena& ar, DpStats* st, int& lcsOut, int what) {
+  const int d = (what & 1) ? nw_distance_scalar(a, an, b, bn, ar, st) : 0;
+  lcsOut = (what & 2) ? lcs_length_scalar(a, an, b, bn, ar, st) : 0;
   return d;
 }
 #endif
@@ -665,7 +544,7 @@ namespace talc {
 
 #if defined(__CUDA_ARCH__)
 // Device form: the anti-diagonals live in registers (xdrop.cuh) while the band |diagonal| <= X fits 32*S
-// diagonals; beyond that (never seen on the benchmark workloads) every lane runs the scalar routine on the
+// diagonals (S = 1, 2, 4, 8; the slow tail of a batch are reads with long borders and large drop-offs, so S = 4 pays); beyond that (never seen on the benchmark workloads) every lane runs the scalar routine on the
 // warp's arena.  Must be called by all 32 lanes with identical arguments.
 __device__ __forceinline__ void xdrop_extend(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff,
                                              u32 dlen, int scoreDropOff, u32& ext_rows, u32& ext_cols, i32& end_score,

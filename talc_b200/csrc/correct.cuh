@@ -136,33 +136,32 @@ class Corrector {
   TALC_HD u32 K() const { return P.K; }
 
   // ------------------------------------------------------------------ table access with counters
+  // a k-mer holding N: its successors x[1..]+b may or may not hold N; look each one up by bases (rare, out of line)
+  TALC_HDN int out_degree_with_n(u32 pos, bool right) {
+    int d = 0;
+    for (u32 b = 0; b < 4; ++b) {
+      bool ok2 = true;
+      u64 v = 0;
+      for (u32 j = 0; j < K(); ++j) {
+        u32 c;
+        if (right) c = (j + 1 < K()) ? rd.code(pos + j + 1) : b;
+        else c = (j == 0) ? b : rd.code(pos + j - 1);
+        if (c > 3) { ok2 = false; break; }
+        v = (v << 2) | c;
+      }
+      if (ok2) {
+        u32 cn, cl;
+        table_lookup(T, v, cn, cl);
+        d += (cn >= P.min_count) ? 1 : 0;
+      }
+    }
+    return d;
+  }
   TALC_HDN int out_degree(u32 pos, bool right) {
     if (ctr) ctr->lookups_deg += 4;
     bool ok = true;
     const u64 km = (rdlg == 5u) ? path_kmer_fwd(rdw, pos, K()) : rd.kmer_at(pos, K(), ok);
-    if (!ok) {
-      // a k-mer holding N: its successors x[1..]+b may or may not hold N; look each one up by bases
-      int d = 0;
-      TALC_ROLLED
-      for (u32 b = 0; b < 4; ++b) {
-        bool ok2 = true;
-        u64 v = 0;
-        TALC_ROLLED
-        for (u32 j = 0; j < K(); ++j) {
-          u32 c;
-          if (right) c = (j + 1 < K()) ? rd.code(pos + j + 1) : b;
-          else c = (j == 0) ? b : rd.code(pos + j - 1);
-          if (c > 3) { ok2 = false; break; }
-          v = (v << 2) | c;
-        }
-        if (ok2) {
-          u32 cn, cl;
-          table_lookup(T, v, cn, cl);
-          d += (cn >= P.min_count) ? 1 : 0;
-        }
-      }
-      return d;
-    }
+    if (!ok) return out_degree_with_n(pos, right);
 #if defined(__CUDA_ARCH__)
     {  // one bucket of the successor table holds all four counts
       u32 c4[4], cm;
@@ -1109,7 +1108,7 @@ class Corrector {
               b.rightAnchor = dirRight ? aimPos : whichStart;
               const SeqView pv = view_of_path(slot_ptr(ch.slot), clen);
               int lcs = 0;
-              b.score = -nw_lcs_fused(refv, ref.len, pv, clen, scratch, &dps, lcs);
+              b.score = -nw_lcs_fused(refv, ref.len, pv, clen, scratch, &dps, lcs, 3);
               b.idscore = (double)lcs / (double)(ref.len > clen ? ref.len : clen);
               // cutAnchors INNER (Trajectory.cpp:176-197), limit = RIGHT.end
               b.ok = true;

@@ -168,7 +168,13 @@ struct SortKey {
 struct SortKeyLess {
   TALC_HD bool operator()(const SortKey& a, const SortKey& b) const { return a.key < b.key; }
 };
-TALC_HDN void std_sort_keys(SortKey* first, u32 n) { std_sort(first, first + n, SortKeyLess()); }
+TALC_HDN void std_sort_keys_large(SortKey* first, u32 n) { std_sort(first, first + n, SortKeyLess()); }
+// up to 16 elements std::sort is its final insertion sort alone (the introsort loop does nothing): the anchor
+// lists of every gap attempt take this short path and never touch the introsort code
+TALC_HDN void std_sort_keys(SortKey* first, u32 n) {
+  if (n > 16) { std_sort_keys_large(first, n); return; }
+  if (n > 1) stdsort_detail::insertion_sort(first, first + n, SortKeyLess());
+}
 // non-negative doubles order like their bit patterns
 TALC_HD i64 sort_key_of_nonneg_double(double d) {
   i64 k;

@@ -386,7 +386,7 @@ __global__ void test_align_kernel(int op, const u8* a, const u64* aoff, const u8
   else if (op == 2) r0 = overlap_score(va, va.len, vb, vb.len, ar, nullptr);
   else if (op == 5) {  // fused distance + LCS
     int l = 0;
-    r0 = -nw_lcs_fused(va, va.len, vb, vb.len, ar, nullptr, l);
+    r0 = -nw_lcs_fused(va, va.len, vb, vb.len, ar, nullptr, l, 3);
     r1 = l;
   } else if (op == 4) {  // raw X-drop: a = query segment, b = database segment, aux = score drop-off
     DpStats ds;
