@@ -741,9 +741,11 @@ class Corrector {
     TALC_ROLLED
     for (u32 i = 0; i < k; ++i) rkmer |= ((kmer >> (2 * i)) & 3ull) << (2 * (k - 1 - i));
     u32 st = step, nSteps = 0;
+    const u32 topShift = 2 * (k - 1);
+    u32 untilCheck = border ? (kCheckInterval - 1u - (st % kCheckInterval)) : ~0u;  // steps before scoreEdges is due
 #pragma unroll 1
     while (st < pathMax) {
-      if (border && ((st + 1) % kCheckInterval == 0)) break;  // scoreEdges is due after this step
+      if (untilCheck == 0) break;  // border: (st + 1) % kCheckInterval == 0, scoreEdges is due after this step
       const u32 plen = k + st;
       // ---- the four successors of every trail: one sector per trail
       int child = -1;
@@ -763,7 +765,7 @@ class Corrector {
       }
       if (__ballot_sync(0xffffffffu, act && child < 0)) break;  // dead end or branching somewhere: general step
       const u32 ch = (u32)(child < 0 ? 0 : child);
-      const u64 ck = kmer_next(kmer, ch, right, k);
+      const u64 ck = right ? (((kmer << 2) | (u64)ch) & kmask) : ((kmer >> 2) | ((u64)ch << topShift));
       if (!border) {  // aim reached by any trail: the general step records the bridge (one aim k-mer per lane)
         bool aim = false;
 #pragma unroll 1
@@ -806,6 +808,7 @@ class Corrector {
       count = childCnt;
       ++st;
       ++nSteps;
+      --untilCheck;
     }
     __syncwarp();
     if (nSteps) {
