@@ -146,6 +146,43 @@ __global__ void kmer_count_kernel(const u64* offs, u32 n, u32 K, u64* nk, u32* s
   sortKey[i] = 0xFFFFFFFFu - (u32)len;  // ascending key = descending length
   sortVal[i] = i;
 }
+// Scheduling key of a read (results do not depend on it): reads are handed to the warps most expensive first.
+// Cost grows with the length and, much faster, with the length of a correctable head / tail (<= 500 bases:
+// Read.cpp:361,368): a border search re-scores every trail from its seed every 6 steps (Explorer.cpp:709-740),
+// quadratic in the border length (profiles/r01_slow_reads.log).  One warp per read scans its coverage for the
+// first and the last solid k-mer.
+__global__ void cost_key_kernel(const u32* __restrict__ cov, const u64* __restrict__ kmerOff, const u64* __restrict__ offs, u32 n,
+                                u32 minCount, u32* sortKey, u32* sortVal) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warpsPerBlock = blockDim.x >> 5;
+  for (u32 r = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < n; r += gridDim.x * warpsPerBlock) {
+    const u32 C = (u32)(kmerOff[r + 1] - kmerOff[r]);
+    const u32* cv = cov + kmerOff[r];
+    u32 first = C, last = 0;
+    bool any = false;
+    for (u32 base = 0; base < C && !any; base += 32) {
+      const u32 m = __ballot_sync(0xffffffffu, base + lane < C && cv[base + lane] >= minCount);
+      if (m) { first = base + (u32)__ffs((int)m) - 1; any = true; }
+    }
+    if (any) {
+      for (u32 top = C; top > 0; top -= (top < 32 ? top : 32)) {
+        const u32 base = top < 32 ? 0 : top - 32;
+        const u32 m = __ballot_sync(0xffffffffu, base + lane < top && cv[base + lane] >= minCount);
+        if (m) { last = base + 31 - (u32)__clz((int)m); break; }
+      }
+    }
+    if (lane == 0) {
+      const u64 len = offs[r + 1] - offs[r];
+      u64 est = 0;
+      if (any) {
+        const u64 h = first <= kBorderMaxLen ? first : 0, t = (C - 1 - last) <= kBorderMaxLen ? (C - 1 - last) : 0;
+        est = len + (h * h + t * t) / 5;
+      }
+      sortKey[r] = 0xFFFFFFFFu - (u32)(est > 0xFFFFFFFEull ? 0xFFFFFFFEull : est);  // ascending key = descending cost
+      sortVal[r] = r;
+    }
+  }
+}
 // One warp per read; each lane rolls a 2-bit k-mer over 4 consecutive positions (K+3 byte loads for 4
 // probes), probes the table (one 32-byte sector per probe), and the warp writes 512 contiguous bytes.
 __global__ void __launch_bounds__(256) coverage_kernel(TableView tv, u32 K, const u8* __restrict__ bases,
@@ -852,9 +889,6 @@ static int prepare_batch(talc_ctx* c, const u8* dBases, const u64* dOffs, u32 n,
   CUDA_TRY(c, c->cubTmp.reserve(std::max(tmp1, tmp2)));
   size_t tb = c->cubTmp.cap;
   CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->cubTmp.p, tb, (u64*)c->nk.p, (u64*)c->kmerOff.p, n + 1, c->stream));
-  tb = c->cubTmp.cap;
-  CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubTmp.p, tb, (u32*)c->sortKey.p, (u32*)c->sortKeyOut.p, (u32*)c->sortVal.p,
-                                              (u32*)c->order.p, (int)n, 0, 32, c->stream));
   u64 hk = 0;
   CUDA_TRY(c, cudaMemcpyAsync(&hk, (u64*)c->kmerOff.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -866,6 +900,13 @@ static int prepare_batch(talc_ctx* c, const u8* dBases, const u64* dOffs, u32 n,
   coverage_kernel<<<blocks, 256, 0, c->stream>>>(tv, K, dBases, dOffs, (const u64*)c->kmerOff.p, n, (u32*)c->cov.p);
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaEventRecord(c->ev[2], c->stream));
+  // processing order of the correction kernel: estimated cost, descending
+  cost_key_kernel<<<blocks, 256, 0, c->stream>>>((const u32*)c->cov.p, (const u64*)c->kmerOff.p, dOffs, n, c->P.min_count,
+                                                 (u32*)c->sortKey.p, (u32*)c->sortVal.p);
+  CUDA_TRY(c, cudaGetLastError());
+  tb = c->cubTmp.cap;
+  CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->cubTmp.p, tb, (u32*)c->sortKey.p, (u32*)c->sortKeyOut.p, (u32*)c->sortVal.p,
+                                              (u32*)c->order.p, (int)n, 0, 32, c->stream));
   (void)totalBases;
   return TALC_OK;
 }
