@@ -250,7 +250,7 @@ def run_gpu(args, rank, world, local_rank):
         c = ctx.correct_device(r, o, nb, d_out, d_ooff, d_st)
         dev_ms += c["ms_total"]
         bases += nb
-        launches += 5 + (1 if c["reads_second_tier"] else 0)  # kmer_count, coverage, correct(+tier2), len_to_u64, gather
+        launches += 6 + (1 if c["reads_second_tier"] else 0)  # kmer_count, coverage, cost_key, correct(+tier2), len_to_u64, gather
         if agg is None:
             agg = dict(c)
         else:
