@@ -112,6 +112,12 @@ int talc_table_export_device(talc_ctx* ctx, void* dst_device, uint64_t bytes);
 int talc_table_import_device(talc_ctx* ctx, const void* src_device, uint64_t capacity_slots, uint64_t n_entries);
 /* single-process replication: copy src's sealed table to dst's device (peer copy over NVLink)    */
 int talc_table_copy(talc_ctx* dst, talc_ctx* src);
+/* binary cache of the built table (at 30 M+ lines the text parse of buildCDBG,
+ * Jellyfish.cpp:251-269, dominates start-up once correction is fast).  save writes the sealed slot array with a
+ * small header (magic, K, MIN_COUNT, capacity, entries); load checks K and MIN_COUNT against the context,
+ * uploads the array and seals it -- the result is the table the dump would have built.            */
+int talc_table_save(talc_ctx* ctx, const char* path);
+int talc_table_load_cache(talc_ctx* ctx, const char* path, uint64_t* n_entries);
 /* point look-ups from the host (tests, debugging): found[i] in {0,1}                              */
 int talc_table_lookup(talc_ctx* ctx, const uint64_t* keys, uint64_t n, uint32_t* counts, uint32_t* colours,
                       uint8_t* found);

@@ -59,6 +59,8 @@ def lib():
         L.talc_table_device_ptr.argtypes = [vp, C.POINTER(vp)]
         L.talc_table_seal.argtypes = [vp, C.c_uint64]
         L.talc_table_copy.argtypes = [vp, vp]
+        L.talc_table_save.argtypes = [vp, C.c_char_p]
+        L.talc_table_load_cache.argtypes = [vp, C.c_char_p, u64p]
         L.talc_table_export_device.argtypes = [vp, vp, C.c_uint64]
         L.talc_table_import_device.argtypes = [vp, vp, C.c_uint64, C.c_uint64]
         L.talc_table_lookup.argtypes = [vp, vp, C.c_uint64, vp, vp, vp]
@@ -133,6 +135,14 @@ class Talc:
         self._check(lib().talc_table_load_packed(self.h, _ptr(keys), _ptr(counts), len(keys), _ptr(jk), _ptr(jc), len(jk),
                                                  1 if uj else 0, C.byref(nk)), "talc_table_load_packed")
         return nk.value
+
+    def table_save(self, path: str) -> None:
+        self._check(lib().talc_table_save(self.h, path.encode()), "talc_table_save")
+
+    def table_load_cache(self, path: str) -> int:
+        n = C.c_uint64(0)
+        self._check(lib().talc_table_load_cache(self.h, path.encode(), C.byref(n)), "talc_table_load_cache")
+        return n.value
 
     def table_info(self):
         cap, nbytes, n = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

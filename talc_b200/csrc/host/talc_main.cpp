@@ -23,7 +23,7 @@
 #include "talc_b200.h"
 
 struct Cli {
-  std::string reads, dump, junctions, out = "out", queryMode = "memory";
+  std::string reads, dump, junctions, out = "out", queryMode = "memory", tableCache;
   bool useJunctions = false, reverse = false;
   int threads = 1, gpus = 1;
   talc_params p;
@@ -57,6 +57,7 @@ static int parse(int argc, const char** argv, Cli& c) {
     else if (a == "-qm" || a == "--query-mode") { if (!val(c.queryMode) || (c.queryMode != "memory" && c.queryMode != "jellyfish2")) return 1; }
     else if (a == "-SR" || a == "--SRCounts") { if (!val(c.dump)) return 1; c.haveSR = true; }
     else if (a == "-j" || a == "--junctions") { if (!val(c.junctions)) return 1; c.useJunctions = true; }
+    else if (a == "--tableCache") { if (!val(c.tableCache)) return 1; }  // extension: binary cache of the built table
     else if (a == "-jf2" || a == "--pathToJF2") { if (!val(v)) return 1; }
     else if (a == "-MIN_INNER_SCORE" || a == "--MIN_INNER_SCORE") { if (!val(v) || !to_dbl(v, d) || d < 0.3 || d > 0.9) return 1; c.p.min_inner_score = d; }
     else if (a == "-MIN_BORDER_SCORE" || a == "--MIN_BORDER_SCORE") { if (!val(v) || !to_dbl(v, d) || d < 0.5 || d > 0.9) return 1; c.p.min_border_score = d; }
@@ -183,7 +184,7 @@ int main(int argc, const char** argv) {
   Cli cli;
   const int pr = parse(argc, argv, cli);
   if (pr == 2) {
-    std::cout << "talc <reads> --SRCounts <dump> [--junctions <dump>] -k <K> [-o <prefix>] [-t <N>] [--gpus <N>]\n";
+    std::cout << "talc <reads> --SRCounts <dump> [--junctions <dump>] -k <K> [-o <prefix>] [-t <N>] [--gpus <N>] [--tableCache <file>]\n";
     return 0;
   }
   if (pr != 0) { std::cerr << "talc: PARSE_ERROR\n"; return 1; }
@@ -208,7 +209,15 @@ int main(int argc, const char** argv) {
     }
   }
   uint64_t nLines = 0, nKept = 0;
-  int rc = talc_table_load_dump(ctx[0], cli.dump.c_str(), cli.useJunctions ? cli.junctions.c_str() : nullptr, &nLines, &nKept);
+  int rc = -1;
+  // --tableCache <file> (extension): reuse the built table if the file exists, else build it from the
+  // dump and write the file; the cache must have been made from the same --SRCounts / --junctions / -k / MIN_COUNT
+  if (!cli.tableCache.empty()) rc = talc_table_load_cache(ctx[0], cli.tableCache.c_str(), &nKept);
+  if (rc != 0) {
+    rc = talc_table_load_dump(ctx[0], cli.dump.c_str(), cli.useJunctions ? cli.junctions.c_str() : nullptr, &nLines, &nKept);
+    if (rc == 0 && nKept > 0 && !cli.tableCache.empty() && talc_table_save(ctx[0], cli.tableCache.c_str()) != 0)
+      std::cerr << "talc: " << talc_last_error(ctx[0]) << "\n";
+  }
   if (rc != 0) { std::cerr << "talc: " << talc_last_error(ctx[0]) << "\n"; nKept = 0; }
   std::cout << "[TALC]: SR-dBG contains " << nKept << " nodes." << std::endl;
   if (nKept == 0) {

@@ -710,6 +710,64 @@ extern "C" int talc_table_copy(talc_ctx* dst, talc_ctx* src) {
   return talc_table_seal(dst, src->nEntries);
 }
 
+// ---- binary table cache (include/talc_b200.h): header + raw slot array, streamed in 64 MiB pieces
+struct TableCacheHeader {
+  char magic[8];  // "TALCTBL1"
+  u32 K, min_count;
+  u64 capacity, entries;
+};
+extern "C" int talc_table_save(talc_ctx* c, const char* path) {
+  if (!c || !path || !c->tableReady) return TALC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  FILE* f = fopen(path, "wb");
+  if (!f) { c->err = std::string("cannot write ") + path; return TALC_ERR_IO; }
+  TableCacheHeader h;
+  memcpy(h.magic, "TALCTBL1", 8);
+  h.K = c->P.K; h.min_count = c->P.min_count; h.capacity = c->capacity; h.entries = c->nEntries;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  const size_t total = (size_t)c->capacity * sizeof(Slot), piece = 64u << 20;
+  std::vector<char> buf(std::min(total, piece));
+  for (size_t o = 0; o < total && ok; o += piece) {
+    const size_t nb = std::min(piece, total - o);
+    if (cudaMemcpy(buf.data(), (const char*)c->slots + o, nb, cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+    else ok = fwrite(buf.data(), 1, nb, f) == nb;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { c->err = std::string("error while writing ") + path; return TALC_ERR_IO; }
+  return TALC_OK;
+}
+extern "C" int talc_table_load_cache(talc_ctx* c, const char* path, uint64_t* n_entries) {
+  if (!c || !path) return TALC_ERR_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) { c->err = std::string("cannot read ") + path; return TALC_ERR_IO; }
+  TableCacheHeader h;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "TALCTBL1", 8) != 0 || h.capacity < 2 ||
+      (h.capacity & (h.capacity - 1))) {
+    fclose(f);
+    c->err = std::string(path) + " is not a table cache";
+    return TALC_ERR_IO;
+  }
+  if (h.K != c->P.K || h.min_count != c->P.min_count) {
+    fclose(f);
+    c->err = "table cache was built with another k-mer size or MIN_COUNT";
+    return TALC_ERR_ARG;
+  }
+  int rc = talc_table_alloc(c, h.capacity);
+  if (rc) { fclose(f); return rc; }
+  const size_t total = (size_t)h.capacity * sizeof(Slot), piece = 64u << 20;
+  std::vector<char> buf(std::min(total, piece));
+  bool ok = true;
+  for (size_t o = 0; o < total && ok; o += piece) {
+    const size_t nb = std::min(piece, total - o);
+    ok = fread(buf.data(), 1, nb, f) == nb &&
+         cudaMemcpy((char*)c->slots + o, buf.data(), nb, cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  fclose(f);
+  if (!ok) { c->err = std::string("truncated table cache ") + path; return TALC_ERR_IO; }
+  if (n_entries) *n_entries = h.entries;
+  return talc_table_seal(c, h.entries);
+}
+
 // entries: dump order, already filtered to count >= MIN and valid ACGT k-mers of length K
 static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vector<u32>& counts,
                        const std::vector<u64>& ckeys, const std::vector<u32>& ccols, uint64_t* n_kept) {

@@ -53,6 +53,27 @@ def test_table_matches_oracle(api, case_c3):
     assert (col > 0).any(), "junction colours must be exercised"
 
 
+def test_table_cache_round_trip(api, case_c3, tmp_path):
+    """talc_table_save / talc_table_load_cache: the cached table answers every look-up like the
+    table built from the dump (junction colours included), corrects to the same bytes, and a cache made for
+    another k-mer size is refused."""
+    case = case_c3
+    t = _ctx(api, case)
+    path = str(tmp_path / "table.bin")
+    t.table_save(path)
+    t2 = api.Talc(api.default_params(case.cfg.k))
+    assert t2.table_load_cache(path) == t.table_info()["entries"]
+    probe = np.concatenate([case.keys[:5000], case.keys[:5000] ^ np.uint64(5)])
+    c1, l1, f1 = t.lookup(probe)
+    c2, l2, f2 = t2.lookup(probe)
+    assert np.array_equal(c1, c2) and np.array_equal(l1, l2) and np.array_equal(f1, f2)
+    out, off, st, ctr = t2.correct(case.reads, case.off)
+    _assert_same(case, out, off, st, ctr)
+    t3 = api.Talc(api.default_params(case.cfg.k + 2))
+    with pytest.raises(api.TalcError):
+        t3.table_load_cache(path)
+
+
 def test_coverage_matches_oracle(api, case_c1):
     case = case_c1
     t = _ctx(api, case)
@@ -196,6 +217,60 @@ def test_alignment_primitives_on_device(api, case_c1):
         for i, (r, c) in enumerate(zip(refs, cands)):
             re_, ce_, pos, sc, stop = po.seed_extend(r[::-1], c[::-1], x, False, k)
             assert tuple(res[i]) == (re_, ce_, int(sc), int(stop)), (i, x)
+
+
+def test_config2_scale_sampled_parity_and_split_invariance(api):
+    """A config-2-like workload two orders of magnitude above the other cases (0.76 M-entry table, 6 000 reads): the
+    oracle checks a random sample of reads byte for byte, and the whole batch is checked through properties that do
+    not need the oracle -- correcting the batch in two halves, or in reverse order, changes no read and no counter
+    (the processing order inside the kernel is cost-driven and must not leak into the results)."""
+    from oracle import pyoracle as po
+    from talc_b200 import synth
+    cfg = synth.baseline_config(2, 0.02)
+    cfg.n_reads = 6000
+    w = synth.make_workload(cfg)
+    keys, counts = w.keys.numpy().astype(np.uint64), w.counts.numpy().astype(np.int64)
+    reads, off = w.reads.numpy(), w.read_off.numpy().astype(np.uint64)
+    n = len(off) - 1
+    t = api.Talc(api.default_params(cfg.k))
+    t.load_packed(keys, counts)
+    out, ooff, st, ctr = t.correct(reads, off)
+    assert ctr["reads_ok"] > 0.95 * n and ctr["gaps_bridged"] > 0
+
+    def sub(idx):
+        parts = [reads[int(off[r]):int(off[r + 1])] for r in idx]
+        so = np.zeros(len(idx) + 1, dtype=np.uint64)
+        so[1:] = np.cumsum([len(x) for x in parts])
+        return np.concatenate(parts), so
+
+    # (1) oracle on a sample
+    rng = np.random.default_rng(4)
+    sample = sorted(rng.choice(n, 150, replace=False).tolist())
+    ot = po.OracleTable(po.make_params(k=cfg.k)).build_packed(keys, counts)
+    sr, so = sub(sample)
+    o_out, o_off, o_st, _, _ = ot.correct(sr, so, threads=8)
+    for i, r in enumerate(sample):
+        assert st[r] == o_st[i], r
+        assert out[int(ooff[r]):int(ooff[r + 1])].tobytes() == o_out[int(o_off[i]):int(o_off[i + 1])].tobytes(), r
+    # (2) two halves == whole, counters add up
+    half = n // 2
+    a_r, a_o = sub(range(half))
+    b_r, b_o = sub(range(half, n))
+    oa, fa, sa, ca = t.correct(a_r, a_o)
+    ob, fb, sb, cb = t.correct(b_r, b_o)
+    assert np.array_equal(np.concatenate([sa, sb]), st)
+    assert np.array_equal(np.concatenate([oa[: int(fa[-1])], ob[: int(fb[-1])]]), out[: int(ooff[-1])])
+    for k2 in SHARED:
+        assert ca[k2] + cb[k2] == ctr[k2], k2
+    # (3) reversed input order == reversed output
+    rev = list(range(n - 1, -1, -1))
+    r_r, r_o = sub(rev)
+    orr, frr, srr, crr = t.correct(r_r, r_o)
+    assert np.array_equal(srr, st[::-1])
+    for i in (0, 1, n // 3, n - 1):
+        r = rev[i]
+        assert orr[int(frr[i]):int(frr[i + 1])].tobytes() == out[int(ooff[r]):int(ooff[r + 1])].tobytes()
+    assert {k2: crr[k2] for k2 in SHARED} == {k2: ctr[k2] for k2 in SHARED}
 
 
 def test_xdrop_register_band_on_device(api, case_c1):
