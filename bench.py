@@ -322,6 +322,11 @@ def run_gpu(args, rank, world, local_rank):
                                                  "algorithmic_bytes_per_launch": cov_bytes,
                                                  "frac": cov_bytes / 1e9 / (cov_ms / 1e3) / peak}},
                 "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                # stage-4 integer work: DP cell updates of the reference algorithm per second of correct_kernel
+                "dp": {"cells_per_launch": (agg["cells_nw"] + agg["cells_lcs"] + agg["cells_ovl"] + agg["cells_xdrop"]) / steps,
+                       "gcups": (agg["cells_nw"] + agg["cells_lcs"] + agg["cells_ovl"] + agg["cells_xdrop"]) / steps / 1e9 / (k_ms / 1e3),
+                       "note": "cells the reference's DP visits (oracle-equal counters); bit-parallel rows, the register X-drop band "
+                               "and the end-cell score mean far fewer machine operations than cells"},
                 "gpu_launches": launches,
                 "clocks": clocks,
                 "counters": {k2: agg[k2] for k2 in ("lookups_seg", "lookups_deg", "lookups_walk", "steps_inner", "steps_border",
