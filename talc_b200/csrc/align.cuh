@@ -333,19 +333,23 @@ TALC_HDN int overlap_score_scalar(const SeqView& ref, u32 rn, const SeqView& can
 }
 
 #if defined(__CUDA_ARCH__)
-// Device form: a skewed wavefront over stripes of 32 columns.  Lane l owns column j0+l of the stripe and works on
-// row t-l at time t, so the cell to its left (lane l-1, same row) was computed one step earlier and arrives by one
-// shuffle; the diagonal term is the left value of the step before, the vertical term the lane's own previous
-// value.  The reference character of a row travels down the lanes with the wavefront.  The last column of a
-// stripe is parked in the arena (one value per row) and feeds lane 0 of the next stripe; lane 0 runs 31 rows
-// ahead of lane 31, so the same buffer is read and overwritten in place.  Same integer recurrence as the scalar
-// form, ~1 warp instruction per cell instead of a prefix-maximum scan per row.
+// Device form: a skewed wavefront over stripes of 32 x kOvlCols columns.  Lane l owns kOvlCols adjacent columns
+// of the stripe and works on row t-l at time t: the cell left of its first column (lane l-1, same row) was
+// computed one step earlier and arrives by one shuffle together with the row's reference character; the diagonal
+// term of the first column is the left value of the step before; inside the lane the columns chain through
+// registers.  The last column of a stripe is parked in the arena (one value per row) and feeds lane 0 of the next
+// stripe 32 rows at a time; lane 0 runs 31 rows ahead of lane 31, so the same buffer is read and overwritten in
+// place.  Same integer recurrence as the scalar form; shuffles, loop control and the row feed are paid once per
+// kOvlCols cells.  (Gardening scores EVERY trail of the frontier against the reference: with junction colours or
+// at 15 % error this is the largest DP of a read -- 0.9 M and 4.5 M cells per read on configs 3 and 5.)
+#define kOvlCols 4
 __device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const SeqView& candArg, u32 cn, Arena& ar,
                                           DpStats* st) {
   if (st) st->cells_ovl += (u64)rn * cn;
+  const u32 W = 32u * kOvlCols;  // stripe width
   // the recurrence and its all-zero first row and column are symmetric in the two sequences: put on the lanes
   // the one that wastes fewer of them (stripes x steps per stripe)
-  const bool swap = (u64)((rn + 31) / 32) * (cn + 31) < (u64)((cn + 31) / 32) * (rn + 31);
+  const bool swap = (u64)((rn + W - 1) / W) * (cn + 31) < (u64)((cn + W - 1) / W) * (rn + 31);
   const SeqView ref = swap ? candArg : refArg, cand = swap ? refArg : candArg;  // by value: fields in registers
   if (swap) { const u32 x = rn; rn = cn; cn = x; }
   const u32 lane = threadIdx.x & 31u;
@@ -355,15 +359,21 @@ __device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const S
   for (u32 i = lane; i <= rn; i += 32) colBuf[i] = 0;  // column 0: leading gaps are free
   __syncwarp();
   int result = 0;
-  for (u32 j0 = 1; j0 <= cn; j0 += 32) {
-    const u32 j = j0 + lane;
-    const bool act = j <= cn;
-    const u32 nl = (cn - j0 + 1 < 32u) ? (cn - j0 + 1) : 32u;  // columns in this stripe
-    const bool park = (j0 + 32 <= cn) && (lane == 31);          // a further stripe follows
-    const u32 cc = act ? cand.code(j - 1) : 9u;
-    i32 up = 0, diag = 0;  // S[0][j] = S[0][j-1] = 0
-    i32 outPrev = 8;       // what this lane hands to the next: (value << 3) | reference character of the row
-    i32 chunk = 8;         // the same for lane 0, 32 rows at a time: (S[i][j0-1] << 3) | reference character
+  for (u32 j0 = 1; j0 <= cn; j0 += W) {
+    const u32 jf = j0 + kOvlCols * lane;  // this lane's first column
+    const u32 ncols = cn - j0 + 1 < W ? cn - j0 + 1 : W;
+    const u32 nl = (ncols + kOvlCols - 1) / kOvlCols;   // lanes that own a column of this stripe
+    const bool park = (j0 + W <= cn) && (lane == 31);    // a further stripe follows
+    u32 cc[kOvlCols];
+    i32 up[kOvlCols];
+#pragma unroll
+    for (int c = 0; c < kOvlCols; ++c) {
+      cc[c] = (jf + c <= cn) ? cand.code(jf + c - 1) : 9u;  // 9 never matches: columns beyond cn only ever feed
+      up[c] = 0;                                            // columns further right, which do not exist either
+    }
+    i32 diag = 0;     // S[i-1][jf-1]
+    i32 outPrev = 8;  // what this lane hands to the next: (value of its last column << 3) | reference character
+    i32 chunk = 8;    // the same for lane 0, 32 rows at a time: (S[i][j0-1] << 3) | reference character
 #pragma unroll 1
     for (u32 t = 1; t <= rn + nl - 1; ++t) {
       const u32 ph = (t - 1) & 31u;
@@ -375,20 +385,32 @@ __device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const S
       const i32 in0 = __shfl_sync(0xffffffffu, chunk, ph);
       if (lane == 0) in = in0;
       const u32 rc = (u32)in & 7u;
-      const i32 left = in >> 3;    // arithmetic shift: the value keeps its sign
+      const i32 leftIn = in >> 3;  // arithmetic shift: the value keeps its sign
       const u32 i = t - lane;      // wraps for t < lane: fails the range test below
       i32 v = 0;
-      if (act && i >= 1 && i <= rn) {
-        const i32 d = diag + ((rc == cc) ? 4 : -3);
-        const i32 g = (up > left ? up : left) - 2;
-        v = d > g ? d : g;
-        diag = left;
-        up = v;
+      if (lane < nl && i >= 1 && i <= rn) {
+        i32 left = leftIn, dg = diag;
+#pragma unroll
+        for (int c = 0; c < kOvlCols; ++c) {
+          const i32 d = dg + ((rc == cc[c]) ? 4 : -3);
+          const i32 g = (up[c] > left ? up[c] : left) - 2;
+          v = d > g ? d : g;
+          dg = up[c];   // S[i-1][col] is the diagonal term of the next column
+          up[c] = v;
+          left = v;
+        }
+        diag = leftIn;
         if (park) colBuf[i] = v;
       }
       outPrev = (i32)(((u32)v << 3) | rc);
     }
-    if (j0 + 32 > cn) result = __shfl_sync(0xffffffffu, up, cn - j0);
+    if (j0 + W > cn) {  // the last stripe holds column cn: lane (cn - j0) / kOvlCols, its column (cn - j0) % kOvlCols
+      const u32 c = (cn - j0) % kOvlCols;
+      i32 x = up[0];
+#pragma unroll
+      for (int q = 1; q < kOvlCols; ++q) x = (c == (u32)q) ? up[q] : x;
+      result = __shfl_sync(0xffffffffu, x, (cn - j0) / kOvlCols);
+    }
     __syncwarp();
   }
   ar.release(mk);

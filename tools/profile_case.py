@@ -6,11 +6,13 @@ from talc_b200 import api, synth
 
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-cfg = synth.baseline_config(2, 0.02)
+cfg = synth.baseline_config(int(os.environ.get("TALC_PROFILE_CONFIG", "2")), 0.02)
 cfg.n_reads = n_reads
 w = synth.make_workload(cfg, device="cuda")
 t = api.Talc(api.default_params(cfg.k))
-t.load_packed(w.keys.cpu().numpy().astype(np.uint64), w.counts.cpu().numpy())
+use_j = os.environ.get("TALC_PROFILE_CONFIG", "2") == "3"  # config 3 = config 2 + the junction k-mer dump
+t.load_packed(w.keys.cpu().numpy().astype(np.uint64), w.counts.cpu().numpy(),
+              w.jkeys.cpu().numpy().astype(np.uint64) if use_j else None, w.jcounts.cpu().numpy() if use_j else None)
 n, total = w.n_reads(), w.total_bases()
 d_reads = w.reads.contiguous()
 d_off = w.read_off.to(torch.int64).contiguous()
