@@ -343,23 +343,21 @@ TALC_HDN int overlap_score_scalar(const SeqView& ref, u32 rn, const SeqView& can
 // kOvlCols cells.  (Gardening scores EVERY trail of the frontier against the reference: with junction colours or
 // at 15 % error this is the largest DP of a read -- 0.9 M and 4.5 M cells per read on configs 3 and 5.)
 #define kOvlCols 4
-__device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const SeqView& candArg, u32 cn, Arena& ar,
-                                          DpStats* st) {
+// `bufs` (optional): one parked boundary column of rn+1 values per stripe, kept by the caller across calls.  The
+// trails of a frontier share long prefixes (they branched from common ancestors) and are scored against the same
+// reference in one scoreBridges round: a call may `skip` the leading stripes that lie inside the prefix the
+// candidate shares with the candidate of the previous call -- their boundary columns are still valid.
+__device__ __noinline__ int overlap_score_stripes(const SeqView& refArg, u32 rn, const SeqView& candArg, u32 cn, i32* bufs,
+                                                  u32 skip, DpStats* st) {
   if (st) st->cells_ovl += (u64)rn * cn;
   const u32 W = 32u * kOvlCols;  // stripe width
-  // the recurrence and its all-zero first row and column are symmetric in the two sequences: put on the lanes
-  // the one that wastes fewer of them (stripes x steps per stripe)
-  const bool swap = (u64)((rn + W - 1) / W) * (cn + 31) < (u64)((cn + W - 1) / W) * (rn + 31);
-  const SeqView ref = swap ? candArg : refArg, cand = swap ? refArg : candArg;  // by value: fields in registers
-  if (swap) { const u32 x = rn; rn = cn; cn = x; }
+  const SeqView ref = refArg, cand = candArg;  // by value: fields in registers
   const u32 lane = threadIdx.x & 31u;
-  const u32 mk = ar.mark();
-  i32* colBuf = (i32*)ar.alloc((rn + 1) * 4);  // S[i][j0-1] for the stripe that starts at column j0
-  if (!colBuf) return 0;
-  for (u32 i = lane; i <= rn; i += 32) colBuf[i] = 0;  // column 0: leading gaps are free
-  __syncwarp();
   int result = 0;
-  for (u32 j0 = 1; j0 <= cn; j0 += W) {
+  for (u32 j0 = 1 + skip * W; j0 <= cn; j0 += W) {
+    const u32 sIdx = (j0 - 1) / W;
+    const i32* colIn = sIdx ? bufs + (size_t)(sIdx - 1) * (rn + 1) : nullptr;  // S[i][j0-1]; column 0 is all zeros
+    i32* colOut = bufs + (size_t)sIdx * (rn + 1);
     const u32 jf = j0 + kOvlCols * lane;  // this lane's first column
     const u32 ncols = cn - j0 + 1 < W ? cn - j0 + 1 : W;
     const u32 nl = (ncols + kOvlCols - 1) / kOvlCols;   // lanes that own a column of this stripe
@@ -379,7 +377,7 @@ __device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const S
       const u32 ph = (t - 1) & 31u;
       if (ph == 0) {
         const u32 r = t - 1 + lane;  // row r + 1
-        chunk = (r < rn) ? (i32)(((u32)colBuf[r + 1] << 3) | ref.code(r)) : 8;
+        chunk = (r < rn) ? (i32)(((u32)(colIn ? colIn[r + 1] : 0) << 3) | ref.code(r)) : 8;
       }
       i32 in = __shfl_up_sync(0xffffffffu, outPrev, 1);
       const i32 in0 = __shfl_sync(0xffffffffu, chunk, ph);
@@ -400,7 +398,7 @@ __device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const S
           left = v;
         }
         diag = leftIn;
-        if (park) colBuf[i] = v;
+        if (park) colOut[i] = v;
       }
       outPrev = (i32)(((u32)v << 3) | rc);
     }
@@ -413,8 +411,33 @@ __device__ __noinline__ int overlap_score(const SeqView& refArg, u32 rn, const S
     }
     __syncwarp();
   }
-  ar.release(mk);
   return result;
+}
+// one pair on its own
+__device__ __forceinline__ int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {
+  const u32 mk = ar.mark();
+  const u32 ns = (cn + 32u * kOvlCols - 1) / (32u * kOvlCols);
+  i32* bufs = (i32*)ar.alloc((ns ? ns : 1) * (rn + 1) * 4);
+  if (!bufs) return 0;
+  const int r = overlap_score_stripes(ref, rn, cand, cn, bufs, 0, st);
+  ar.release(mk);
+  return r;
+}
+// length of the common prefix (in bases, at most n) of two packed trails
+__device__ __forceinline__ u32 packed_lcp(const u64* a, const u64* b, u32 n) {
+  const u32 lane = threadIdx.x & 31u, nw = (n + 31) / 32;
+  for (u32 base = 0; base < nw; base += 32) {
+    const u32 wi = base + lane;
+    const u64 x = (wi < nw) ? (a[wi] ^ b[wi]) : 0ull;
+    const u32 m = __ballot_sync(0xffffffffu, x != 0ull);
+    if (m) {
+      const u32 l = (u32)__ffs((int)m) - 1;
+      const u64 xl = __shfl_sync(0xffffffffu, x, l);
+      const u32 p = (base + l) * 32 + (u32)__clzll((long long)xl) / 2;
+      return p < n ? p : n;
+    }
+  }
+  return n;
 }
 #else
 inline int overlap_score(const SeqView& ref, u32 rn, const SeqView& cand, u32 cn, Arena& ar, DpStats* st) {

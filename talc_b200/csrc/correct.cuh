@@ -1152,11 +1152,31 @@ class Corrector {
           u32 bound = k + step + P.window;
           const u32 rn = (bound >= ref.len) ? ref.len : bound;
           if (P.q11_zero) {
+#if defined(__CUDA_ARCH__)
+            // every trail of the frontier against the same reference: the stripes of the DP that lie inside the
+            // prefix a trail shares with its predecessor in the list (siblings are neighbours) are not recomputed
+            const u32 cn = k + step, W = 32u * kOvlCols, ns = (cn + W - 1) / W;
+            const u32 mks = scratch.mark();
+            i32* bufs = (i32*)scratch.alloc(ns * (rn + 1) * 4);
+            if (!bufs) return false;
+            TALC_ROLLED
+            for (u32 j = 0; j < nNxt; ++j) {
+              u32 skip = 0;
+              if (j) {
+                skip = packed_lcp(slot_ptr(nxt[j].slot), slot_ptr(nxt[j - 1].slot), cn) / W;
+                if (skip > ns - 1) skip = ns - 1;  // the last stripe carries the result
+              }
+              const SeqView pv = view_of_path(slot_ptr(nxt[j].slot), cn);
+              nxt[j].score = overlap_score_stripes(refv, rn, pv, cn, bufs, skip, &dps);
+            }
+            scratch.release(mks);
+#else
             TALC_ROLLED
             for (u32 j = 0; j < nNxt; ++j) {
               const SeqView pv = view_of_path(slot_ptr(nxt[j].slot), k + step);
               nxt[j].score = overlap_score(refv, rn, pv, k + step, scratch, &dps);
             }
+#endif
           }
           const u32 mkg = scratch.mark();
           u32* kept = (u32*)scratch.alloc((nNxt + P.max_branches + 1) * 4);
