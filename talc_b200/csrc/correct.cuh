@@ -135,6 +135,18 @@ class Corrector {
 
   TALC_HD u32 K() const { return P.K; }
 
+  // ------------------------------------------------------------------ prediction intervals from the per-context tables
+  // (filled on the device by model_lower_bound / model_upper_bound themselves, so the comparisons are the ones of
+  // expected_by_model, Explorer.cpp:1185-1217, bit for bit; counts beyond the tables are computed)
+  TALC_HD bool expected_upper_tab(u32 nextc, u32 cc) {
+    if (cc < tabs.n) return (double)nextc <= tabs.upper[cc];
+    return expected_by_model(nextc, cc, P.alpha, true);
+  }
+  TALC_HD bool expected_last_node_tab(u32 nextc, u32 cc) {
+    if (cc < tabs.n) return ((double)nextc <= tabs.upper[cc]) & ((double)nextc >= tabs.lower[cc]);
+    return expected_by_last_node(nextc, cc, P.alpha);
+  }
+
   // ------------------------------------------------------------------ table access with counters
   // a k-mer holding N: its successors x[1..]+b may or may not hold N; look each one up by bases (rare, out of line)
   TALC_HDN int out_degree_with_n(u32 pos, bool right) {
@@ -371,7 +383,7 @@ class Corrector {
           u32 c = 0;
           TALC_ROLLED
           for (u32 i = ns; i <= ne; ++i) c = c < cov[i] ? cov[i] : c;
-          if (!expected_by_model(c, (u32)thr, P.alpha, true)) {
+          if (!expected_upper_tab(c, (u32)thr)) {
             kept[nk].start = ns;
             kept[nk].end = ne;
             ++nk;
@@ -453,7 +465,7 @@ class Corrector {
       const u32 q = left ? j - 1 : j + 1;
       next_count = (double)cov[q];
       if ((next_count >= P.min_count) & (next_count < kMaxInCount))
-        goFurther = expected_by_last_node((u32)next_count, (u32)current_count, P.alpha);
+        goFurther = expected_last_node_tab((u32)next_count, (u32)current_count);
       else goFurther = false;
       if (!goFurther & (current_count >= P.min_count) & (next_count >= P.min_count) & (next_count < kMaxInCount)) {
         anchorPos[nPos++] = q;
