@@ -10,8 +10,9 @@
 // algorithm on reversed strings (global/LCS scores are reversal-invariant, EXTEND_LEFT consumes the
 // prefixes back to front, and AlignConfig<false,false,true,true> on reversed strings is
 // AlignConfig<true,true,false,false>).
-// One thread runs one alignment: 64 DP rows per machine word, rows > 64 in stripes with the
-// 2-bit horizontal deltas of the stripe boundary parked in the thread's scratch arena.
+// Host form (tests/hostemu): one thread runs one alignment, 64 DP rows per machine word, rows > 64 in stripes
+// with the horizontal deltas of the stripe boundary parked in the scratch arena.  Device forms: the warp that
+// owns the read runs one alignment with the blocks / columns / diagonals spread over its lanes.
 #pragma once
 #include "defs.cuh"
 

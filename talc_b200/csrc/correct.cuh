@@ -1,7 +1,13 @@
 // correct.cuh -- per-read segmentation, anchor selection, bounded de Bruijn graph search and
-// path scoring.  One thread owns one read: the oracle's counters show a mean
-// frontier of ~1 trail per step, so the parallelism is across reads, not inside a gap, and the gaps
-// of a read form a dependency chain anyway.
+// path scoring.  One WARP owns one read: the gaps of a read form a dependency chain
+//  and a frontier holds 1-3 trails for most steps, so the parallelism is across reads; inside a
+// read the 32 lanes run the control code on identical data (no divergence) and split every primitive --
+// trails of the frontier (fast_walk), windows of the cycle test, blocks / columns / diagonals of the scoring
+// routines (align.cuh, xdrop.cuh), k-mers of a ballot (find_in_regions).  On the host (tests/hostemu) a
+// "warp" is one lane and the same TALC_HD code runs scalar.
+//
+// The kernel is bound by instruction delivery: loops of the control code stay rolled
+// (TALC_ROLLED), rare paths sit out of line, and one routine serves where several would be faster apart.
 //
 // Reference files restated here (all under /root/reference/src):
 //   Read.cpp:174-386,440-600   Explorer.cpp:155-297,402-1118   Trail.cpp:48-131,193-216,273-338

@@ -25,10 +25,8 @@
 #define TALC_HDN inline
 #endif
 
-// launch shape of the correction kernel: 4 warps (= 4 reads in flight) per 128-thread block; per-warp
-// shared-memory staging for the X-drop anti-diagonals
+// launch shape of the correction kernel: 4 warps (= 4 reads in flight) per 128-thread block
 #define TALC_WARPS_PER_BLOCK 4
-#define TALC_XD_CAP 192
 
 namespace talc {
 

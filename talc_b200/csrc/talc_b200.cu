@@ -2,7 +2,9 @@
 //
 // Kernels (all HBM / integer bound; nothing here is a dense contraction, so no tensor cores):
 //   table_insert_kernel / table_finalize_kernel / table_colour_kernel   k-mer table build in HBM
+//   ctx_fill_empty_kernel / ctx_build_kernel                            successor tables derived from the k-mer table
 //   kmer_count_kernel + coverage_kernel                                 Read::reCoverage, batched
+//   cost_key_kernel (+ cub radix sort)                                  processing order: estimated cost, descending
 //   correct_kernel<wide>                                                segmentation + graph search + scoring
 //   gather_kernel                                                       corrected reads back into input order
 // Grid sizes are multiples of the SM count; per-thread scratch lives in HBM (180 GB makes that cheap).
