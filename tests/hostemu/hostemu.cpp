@@ -374,6 +374,169 @@ int emu_xdrop_reg_fuzz(uint64_t seed, int n_cases, int max_len) {
   }
   return bad;
 }
+// ---------------------------------------------------------------------------------------------------------
+// Groundwork for an incremental border scoring (DESIGN.md "what comes next"): the gapped X-drop with Score(0,-1,-1)
+// characterised through a Landau-Vishkin table instead of a cell-by-cell DP.  F[e][k] = furthest row on diagonal
+// k = col - row whose cell has edit distance <= e.  A cell survives the X-drop iff its distance is <= X, with the two
+// boundary quirks of SeqAn's routine: a first-row / first-column cell at distance d survives only if d < X (or
+// d == 1 <= X), and therefore a cell of diagonal +-X survives only if it can be reached without passing through
+// that boundary cell.  The window bookkeeping, the cell tally and the end-position rules are then replayed on the
+// surviving set.  Fuzzed against xdrop_extend_scalar; F only depends on the sequences, so it can be extended base by
+// base as a trail grows instead of re-running the extension from the seed every six steps.
+static void xdrop_lv_mirror(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen, int X,
+                            u32& ext_rows, u32& ext_cols, i32& end_score, u64* cells_out) {
+  const i32 Q = (i32)qlen, T = (i32)dlen, cols = Q + 1, rows = T + 1;
+  ext_rows = ext_cols = 0;
+  end_score = 0;
+  if (cells_out) *cells_out = 0;
+  if (rows == 1 || cols == 1) return;
+  const i32 NONE = -1000000;
+  const i32 XX = X < 0 ? -1 : X;
+  // F[e][k + XX], k in [-e, e]
+  std::vector<std::vector<i32>> F((size_t)(XX + 1 > 0 ? XX + 1 : 0), std::vector<i32>((size_t)(2 * (XX > 0 ? XX : 0) + 1), NONE));
+  auto slide = [&](i32 r, i32 k) {
+    while (r < T && r + k < Q && query.code(qoff + (u32)(r + k)) == database.code(doff + (u32)r)) ++r;
+    return r;
+  };
+  auto inside = [&](i32 r, i32 k) { return r >= 0 && r <= T && r + k >= 0 && r + k <= Q; };
+  for (i32 e = 0; e <= XX; ++e) {
+    for (i32 k = -e; k <= e; ++k) {
+      i32 r = NONE;
+      if (e == 0) r = 0;
+      else {
+        auto get = [&](i32 kk) { return (kk >= -(e - 1) && kk <= e - 1) ? F[e - 1][kk + XX] : NONE; };
+        const i32 a = get(k - 1);          // insertion: column + 1, same row
+        const i32 b = get(k);              // substitution: row + 1
+        const i32 c = get(k + 1);          // deletion: row + 1
+        // every cell up to the furthest point of a neighbour diagonal can make the move, so a move that would leave
+        // the matrix is clipped to the last row of this diagonal rather than dropped
+        const i32 rmax = (T < Q - k) ? T : Q - k, rmin = k < 0 ? -k : 0;
+        auto clip = [&](i32 x) { return x > rmax ? rmax : x; };
+        if (a != NONE && clip(a) >= rmin) r = clip(a) > r ? clip(a) : r;
+        if (b != NONE && clip(b + 1) >= rmin) r = clip(b + 1) > r ? clip(b + 1) : r;
+        if (c != NONE && clip(c + 1) >= rmin) r = clip(c + 1) > r ? clip(c + 1) : r;
+      }
+      if (r != NONE && inside(r, k)) F[e][k + XX] = slide(r, k);
+    }
+  }
+  // distance of a cell, or a large value when it exceeds X
+  auto dist = [&](i32 r, i32 c) -> i32 {
+    const i32 k = c - r;
+    if (k < -XX || k > XX) return 1 << 20;
+    for (i32 e = (k < 0 ? -k : k); e <= XX; ++e)
+      if (F[e][k + XX] != NONE && F[e][k + XX] >= r) return e;
+    return 1 << 20;
+  };
+  // Surviving cells of diagonal k = the rows [sK[k], fK[k]] (empty when sK > fK): distances do not decrease along a
+  // diagonal, so the set is a prefix that ends at the furthest point of level X; it starts at the boundary cell of
+  // the diagonal if that one survives (distance |k| < X, or |k| == 1 <= X), else one row further in; and a diagonal
+  // +-X (X >= 2) survives at all only if it can be entered beyond its boundary cell.
+  std::vector<i32> sK((size_t)(2 * (XX > 0 ? XX : 0) + 1), 1), fK((size_t)(2 * (XX > 0 ? XX : 0) + 1), 0);
+  for (i32 k = -XX; k <= XX && XX >= 0; ++k) {
+    const i32 ak = k < 0 ? -k : k, first = k < 0 ? -k : 0;
+    const bool boundaryOk = (k == 0) || (ak < X) || (ak == 1 && X >= 1);
+    i32 s0 = boundaryOk ? first : first + 1, f0 = F[XX][k + XX];
+    if (f0 == NONE) { s0 = 1; f0 = 0; }
+    if (X >= 2 && ak == X) {
+      const i32 r0 = F[X - 1][(k > 0 ? X - 1 : -(X - 1)) + XX];
+      const bool ok = r0 != NONE && (k > 0 ? r0 >= 1 : r0 + 1 >= X + 1);
+      if (!ok) { s0 = 1; f0 = 0; }
+    }
+    sK[k + XX] = s0;
+    fK[k + XX] = f0;
+  }
+  auto value = [&](i32 d, i32 c) -> i32 {
+    const i32 r = d - c;
+    if (c < 0 || r < 0 || c > Q || r > T) return kXdU;
+    if (d == 0) return 0;
+    const i32 k = c - r;
+    if (k < -XX || k > XX) return kXdU;
+    if (r < sK[k + XX] || r > fK[k + XX]) return kXdU;
+    if (c == 0 || r == 0) return -d;
+    return -dist(r, c);
+  };
+  // replay of the window loop on the surviving set
+  i32 minCol = 1, maxCol = 2, d = 1;
+  XdHist h = xd_hist_init();
+  u64 cells = 0;
+  while (minCol < maxCol) {
+    ++d;
+    h.push(minCol, maxCol);
+    i32 loC = INT32_MAX, hiC = INT32_MIN;
+    for (i32 c = minCol; c <= maxCol; ++c) {
+      const bool here = (c < maxCol || (d == maxCol)) ? value(d, c) != kXdU : false;  // col maxCol: only the row-0 sentinel
+      if (here || value(d - 1, c - 1) != kXdU) { loC = c; break; }
+    }
+    for (i32 c = maxCol - 1; c >= minCol - 1; --c) {
+      const bool here = (c >= minCol || (minCol == 1)) ? value(d, c) != kXdU : false;  // col minCol-1: only the col-0 sentinel
+      if (here || value(d - 1, c) != kXdU) { hiC = c; break; }
+    }
+    cells += (u64)(maxCol - minCol);
+    xd_next_window(d, rows, cols, loC, hiC, minCol, maxCol);
+  }
+  if (cells_out) *cells_out = cells;
+  auto inwin = [&](i32 dd, i32 mn, i32 mx, i32 c) -> i32 {  // the array of anti-diagonal dd: cols [mn-1, mx]
+    if (c < mn - 1 || c > mx) return kXdU;
+    if (c == mn - 1 && !(mn == 1)) return kXdU;               // low sentinel is only ever the column-0 cell
+    if (c == mx && !(dd == mx)) return kXdU;                  // high sentinel is only ever the row-0 cell
+    return value(dd, c);
+  };
+  auto at = [&](int which, i32 c) -> i32 {
+    return which == 3 ? inwin(d, h.min3, h.max3, c) : inwin(d - 1, h.min2, h.max2, c);
+  };
+  auto argmax1 = [&](i32 lo, i32 hi, i32& col) -> i32 {
+    i32 bv = kXdU;
+    col = INT32_MAX;
+    for (i32 c = lo; c <= hi; ++c) {
+      const i32 v = inwin(d - 2, h.min1, h.max1, c);
+      if (v > bv) { bv = v; col = c; }
+    }
+    return bv;
+  };
+  xd_finish(d, h, at, argmax1, ext_rows, ext_cols, end_score);
+}
+int emu_xdrop_lv_fuzz(uint64_t seed, int n_cases, int max_len) {
+  u64 s = seed * 0x9E3779B97F4A7C15ull + 7;
+  auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  std::vector<u8> ar(1 << 24);
+  int bad = 0;
+  for (int t = 0; t < n_cases; ++t) {
+    const u32 an = 1 + rnd() % max_len;
+    std::string a(an, 'A'), b;
+    const int alpha = (rnd() % 3 == 0) ? 2 : 4;
+    for (u32 i = 0; i < an; ++i) a[i] = "ACGT"[rnd() % alpha];
+    const u32 errPermille = (u32)(rnd() % 300);
+    for (u32 i = 0; i < an; ++i) {
+      const u32 r = rnd() % 1000;
+      if (r < errPermille / 3) continue;
+      if (r < 2 * errPermille / 3) b.push_back("ACGT"[rnd() % alpha]);
+      else b.push_back(a[i]);
+      if (rnd() % 1000 < errPermille / 3) b.push_back("ACGT"[rnd() % alpha]);
+    }
+    if (rnd() % 5 == 0) b.resize(rnd() % (b.size() + 1));
+    if (rnd() % 7 == 0) b += std::string(rnd() % 40, 'A');
+    if (b.empty()) b = "A";
+    const int X = (int)(rnd() % 6 == 0 ? rnd() % 48 : rnd() % 14) - 1;
+    const bool swap = rnd() & 1;
+    const std::string& q = swap ? b : a;
+    const std::string& db = swap ? a : b;
+    Arena A; A.init(ar.data(), (u32)ar.size());
+    DpStats st; st.cells_xdrop = 0;
+    u32 er0 = 0, ec0 = 0, er = 0, ec = 0;
+    i32 es0 = 0, es = 0;
+    u64 cells = 0;
+    const SeqView qv = bytes_view(q.data(), (u32)q.size()), dv = bytes_view(db.data(), (u32)db.size());
+    xdrop_extend_scalar(qv, 0, (u32)q.size(), dv, 0, (u32)db.size(), X, er0, ec0, es0, A, true, &st);
+    xdrop_lv_mirror(qv, 0, (u32)q.size(), dv, 0, (u32)db.size(), X, er, ec, es, &cells);
+    if (er != er0 || ec != ec0 || es != es0 || cells != st.cells_xdrop) {
+      if (bad < 8)
+        fprintf(stderr, "LV mismatch X=%d q=%s db=%s scalar=(%u,%u,%d,%llu) lv=(%u,%u,%d,%llu)\n", X, q.c_str(), db.c_str(), er0,
+                ec0, es0, (unsigned long long)st.cells_xdrop, er, ec, es, (unsigned long long)cells);
+      ++bad;
+    }
+  }
+  return bad;
+}
 // getSeedAndExtension on walk-order strings (RIGHT as is; for LEFT pass reversed strings and right=0)
 void emu_seed_extend(const char* reference, const char* candidate, int xdrop, int right, uint32_t K, int32_t* ref_ext,
                      int32_t* cand_ext, int32_t* score, int32_t* stop) {

@@ -110,6 +110,16 @@ def test_xdrop_register_band_mirror_matches_scalar():
         assert L.emu_xdrop_reg_fuzz(1000 + seed, n, max_len) == 0
 
 
+def test_xdrop_landau_vishkin_characterisation_matches_scalar():
+    """Groundwork for an incremental border scoring (what comes next): the X-drop's surviving cells are, per
+    diagonal, the row interval that ends at the Landau-Vishkin furthest point of level X, with SeqAn's two boundary
+    quirks; replaying the window rules on that set reproduces end position, end score and the number of cells
+    visited of the cell-by-cell routine."""
+    L = pyemu.lib()
+    for seed, (n, max_len) in enumerate([(60000, 10), (40000, 40), (8000, 300)]):
+        assert L.emu_xdrop_lv_fuzz(2000 + seed, n, max_len) == 0
+
+
 def test_std_sort_replica_matches_libstdcxx():
     L = pyemu.lib()
     rng = np.random.default_rng(5)
