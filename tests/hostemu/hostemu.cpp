@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -383,6 +384,8 @@ int emu_xdrop_reg_fuzz(uint64_t seed, int n_cases, int max_len) {
 // that boundary cell.  The window bookkeeping, the cell tally and the end-position rules are then replayed on the
 // surviving set.  Fuzzed against xdrop_extend_scalar; F only depends on the sequences, so it can be extended base by
 // base as a trail grows instead of re-running the extension from the seed every six steps.
+static int g_lv_skip = 2;  // 0: replay every anti-diagonal, 1: jump between any interval boundaries, 2: only outermost ones
+static u64 g_lv_steps = 0, g_lv_skipped = 0;
 static void xdrop_lv_mirror(const SeqView& query, u32 qoff, u32 qlen, const SeqView& database, u32 doff, u32 dlen, int X,
                             u32& ext_rows, u32& ext_cols, i32& end_score, u64* cells_out) {
   const i32 Q = (i32)qlen, T = (i32)dlen, cols = Q + 1, rows = T + 1;
@@ -455,11 +458,74 @@ static void xdrop_lv_mirror(const SeqView& query, u32 qoff, u32 qlen, const SeqV
     if (c == 0 || r == 0) return -d;
     return -dist(r, c);
   };
-  // replay of the window loop on the surviving set
+  // replay of the window loop on the surviving set.  Between the O(X) anti-diagonals where a diagonal's interval
+  // starts or ends (and before the ends of the sequences clamp the window) the loop is periodic: the windows of
+  // anti-diagonals d+2, d+3 are those of d, d+1 moved one column on.  Once that is observed the replay jumps over
+  // the rest of the quiet stretch in one step (`skip` below), so its cost is O(X) events, not O(length).
+  std::vector<i32> events;
+  for (i32 k = -XX; k <= XX && XX >= 0; ++k) {
+    if (sK[k + XX] > fK[k + XX]) continue;
+    events.push_back(2 * sK[k + XX] + k);
+    events.push_back(2 * fK[k + XX] + k);
+  }
+  std::sort(events.begin(), events.end());
   i32 minCol = 1, maxCol = 2, d = 1;
   XdHist h = xd_hist_init();
   u64 cells = 0;
+  u64 skipped = 0;
   while (minCol < maxCol) {
+    if (g_lv_skip && d >= 6) {
+      // windows of d-2 (h.min2/max2 is d-1's... careful: h.*3 = window of d, h.*2 = d-1, h.*1 = d-2), next = d+1
+      const bool periodic = (minCol == h.min2 + 1) && (maxCol == h.max2 + 1) && (h.min3 == h.min1 + 1) && (h.max3 == h.max1 + 1);
+      if (periodic) {
+        // quiet stretch: until an interval of one of the OUTERMOST surviving diagonals (per parity, looking back over
+        // the last four anti-diagonals) ends, or a diagonal outside them starts; inner diagonals come and go freely
+        i32 nextEv = INT32_MAX;
+        if (g_lv_skip == 2) {
+          i32 kmin[2] = {INT32_MAX, INT32_MAX}, kmax[2] = {INT32_MIN, INT32_MIN};
+          bool changing = false;
+          for (i32 k = -XX; k <= XX; ++k) {
+            const i32 s0 = sK[k + XX], f0 = fK[k + XX];
+            if (s0 > f0) continue;
+            const i32 dS = 2 * s0 + k, dE = 2 * f0 + k;
+            if (dS <= d - 4 && dE >= d) {  // alive throughout the observed period
+              const int p = k & 1;
+              kmin[p] = k < kmin[p] ? k : kmin[p];
+              kmax[p] = k > kmax[p] ? k : kmax[p];
+            } else if (dE >= d - 4 && dS <= d) changing = true;  // started or ended inside the observed period
+          }
+          if (!changing && kmin[0] != INT32_MAX && kmin[1] != INT32_MAX) {
+            for (i32 k = -XX; k <= XX; ++k) {
+              const i32 s0 = sK[k + XX], f0 = fK[k + XX];
+              if (s0 > f0) continue;
+              const i32 dS = 2 * s0 + k, dE = 2 * f0 + k;
+              const int p = k & 1;
+              if (k == kmin[p] || k == kmax[p]) nextEv = dE < nextEv ? dE : nextEv;             // an outermost one ends
+              if ((k < kmin[p] || k > kmax[p]) && dS > d) nextEv = dS < nextEv ? dS : nextEv;   // one further out starts
+              if ((k < kmin[p] || k > kmax[p]) && dS <= d && dE >= d - 4) nextEv = d;           // (cannot happen: not alive)
+            }
+          } else nextEv = d;
+        } else {
+          auto it = std::upper_bound(events.begin(), events.end(), d - 4);
+          nextEv = (it == events.end()) ? INT32_MAX : *it;
+        }
+        if (nextEv > d + 6) {
+          i64 m = ((i64)(nextEv == INT32_MAX ? (i64)rows + cols : nextEv) - d - 6) / 2;  // double steps that stay clear of it
+          const i64 m1 = (i64)rows + minCol - d - 8;  // the database-end clamp d+2-rows stays below minCol
+          const i64 m2 = (i64)cols - maxCol - 3;      // the query-end clamp stays above maxCol
+          if (m1 < m) m = m1;
+          if (m2 < m) m = m2;
+          if (m >= 1) {
+            // anti-diagonals d+1 .. d+2m: window of d+1 is [minCol,maxCol), of d+2 is [h.min3+1, h.max3+1), ...
+            cells += (u64)m * (u64)((maxCol - minCol) + (h.max3 - h.min3));
+            skipped += (u64)(2 * m);
+            d += (i32)(2 * m);
+            minCol += (i32)m; maxCol += (i32)m;
+            h.min1 += (i32)m; h.max1 += (i32)m; h.min2 += (i32)m; h.max2 += (i32)m; h.min3 += (i32)m; h.max3 += (i32)m;
+          }
+        }
+      }
+    }
     ++d;
     h.push(minCol, maxCol);
     i32 loC = INT32_MAX, hiC = INT32_MIN;
@@ -475,6 +541,8 @@ static void xdrop_lv_mirror(const SeqView& query, u32 qoff, u32 qlen, const SeqV
     xd_next_window(d, rows, cols, loC, hiC, minCol, maxCol);
   }
   if (cells_out) *cells_out = cells;
+  g_lv_steps += (u64)d;
+  g_lv_skipped += skipped;
   auto inwin = [&](i32 dd, i32 mn, i32 mx, i32 c) -> i32 {  // the array of anti-diagonal dd: cols [mn-1, mx]
     if (c < mn - 1 || c > mx) return kXdU;
     if (c == mn - 1 && !(mn == 1)) return kXdU;               // low sentinel is only ever the column-0 cell
@@ -494,6 +562,37 @@ static void xdrop_lv_mirror(const SeqView& query, u32 qoff, u32 qlen, const SeqV
     return bv;
   };
   xd_finish(d, h, at, argmax1, ext_rows, ext_cols, end_score);
+}
+void emu_xdrop_lv_stats(uint64_t* steps, uint64_t* skipped) { *steps = g_lv_steps; *skipped = g_lv_skipped; }
+void emu_xdrop_lv_mode(int mode) { g_lv_skip = mode; g_lv_steps = g_lv_skipped = 0; }
+// realistic pairs: a read-like sequence against a copy with `err_permille` errors, fixed drop-off
+int emu_xdrop_lv_fuzz_realistic(uint64_t seed, int n_cases, int len, int err_permille, int X) {
+  u64 s = seed * 0x9E3779B97F4A7C15ull + 11;
+  auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  std::vector<u8> ar(1 << 24);
+  int bad = 0;
+  for (int t = 0; t < n_cases; ++t) {
+    std::string a((size_t)len, 'A'), b;
+    for (int i = 0; i < len; ++i) a[i] = "ACGT"[rnd() % 4];
+    for (int i = 0; i < len; ++i) {
+      const u32 r = rnd() % 1000;
+      if ((int)r < err_permille * 3 / 10) continue;
+      if ((int)r < err_permille * 7 / 10) b.push_back("ACGT"[rnd() % 4]);
+      else b.push_back(a[i]);
+      if ((int)(rnd() % 1000) < err_permille * 3 / 10) b.push_back("ACGT"[rnd() % 4]);
+    }
+    if (b.empty()) b = "A";
+    Arena A; A.init(ar.data(), (u32)ar.size());
+    DpStats st; st.cells_xdrop = 0;
+    u32 er0 = 0, ec0 = 0, er = 0, ec = 0;
+    i32 es0 = 0, es = 0;
+    u64 cells = 0;
+    const SeqView qv = bytes_view(a.data(), (u32)a.size()), dv = bytes_view(b.data(), (u32)b.size());
+    xdrop_extend_scalar(qv, 0, (u32)a.size(), dv, 0, (u32)b.size(), X, er0, ec0, es0, A, true, &st);
+    xdrop_lv_mirror(qv, 0, (u32)a.size(), dv, 0, (u32)b.size(), X, er, ec, es, &cells);
+    if (er != er0 || ec != ec0 || es != es0 || cells != st.cells_xdrop) ++bad;
+  }
+  return bad;
 }
 int emu_xdrop_lv_fuzz(uint64_t seed, int n_cases, int max_len) {
   u64 s = seed * 0x9E3779B97F4A7C15ull + 7;

@@ -54,6 +54,8 @@ def lib():
                                 C.POINTER(C.c_int)]
         L.emu_xdrop_reg_fuzz.argtypes = [C.c_uint64, C.c_int, C.c_int]
         L.emu_xdrop_lv_fuzz.argtypes = [C.c_uint64, C.c_int, C.c_int]
+        L.emu_xdrop_lv_fuzz_realistic.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.emu_xdrop_lv_mode.argtypes = [C.c_int]
         L.emu_seed_extend.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.emu_std_sort_perm.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]

@@ -116,8 +116,11 @@ def test_xdrop_landau_vishkin_characterisation_matches_scalar():
     quirks; replaying the window rules on that set reproduces end position, end score and the number of cells
     visited of the cell-by-cell routine."""
     L = pyemu.lib()
-    for seed, (n, max_len) in enumerate([(60000, 10), (40000, 40), (8000, 300)]):
-        assert L.emu_xdrop_lv_fuzz(2000 + seed, n, max_len) == 0
+    for mode in (0, 1, 2):  # replay every anti-diagonal / jump over quiet stretches (any boundary, outermost only)
+        L.emu_xdrop_lv_mode(mode)
+        for seed, (n, max_len) in enumerate([(30000, 10), (20000, 40), (4000, 300)]):
+            assert L.emu_xdrop_lv_fuzz(2000 + seed, n, max_len) == 0
+        assert L.emu_xdrop_lv_fuzz_realistic(5, 300, 600, 100, 24) == 0
 
 
 def test_std_sort_replica_matches_libstdcxx():
