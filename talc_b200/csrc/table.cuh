@@ -185,6 +185,12 @@ struct CtxView {
   u64 mask;  // capacity - 1 (power of two)
 };
 TALC_HD u64 ctx_of(u64 kmer, bool right, u32 K) { return right ? (kmer & kmer_mask(K - 1)) : (kmer >> 2); }
+// bucket index of a context: one multiply and the high half (the walk hashes once per trail and step; a full
+// 64-bit finaliser is five dependent multiplies and shifts on its critical path)
+TALC_HD u64 hash_ctx(u64 c) {
+  c *= 0x9E3779B97F4A7C15ull;
+  return c ^ (c >> 32);
+}
 
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ void load_bucket(const CtxBucket* p, u64& ctx, u32 cnt[4], u32& colmask) {
@@ -208,7 +214,7 @@ __device__ __noinline__ void ctx_probe_from(const CtxView& v, u64 i, u64 ctx, u3
 }
 // the four successor counts of a context: home bucket and the next one are fetched together
 __device__ __forceinline__ void ctx_lookup(const CtxView& v, u64 ctx, u32 cnt[4], u32& colmask) {
-  const u64 i = hash_kmer(ctx) & v.mask, i2 = (i + 1) & v.mask;
+  const u64 i = hash_ctx(ctx) & v.mask, i2 = (i + 1) & v.mask;
   u64 c0, c1;
   u32 n1[4], m1;
   load_bucket(v.b + i, c0, cnt, colmask);

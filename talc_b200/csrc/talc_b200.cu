@@ -105,7 +105,7 @@ __global__ void ctx_fill_empty_kernel(CtxBucket* b, u64 capacity) {
   }
 }
 __device__ __forceinline__ void ctx_insert(CtxBucket* tb, u64 mask, u64 ctx, u32 b, u32 count, u32 colour) {
-  u64 i = hash_kmer(ctx) & mask;
+  u64 i = hash_ctx(ctx) & mask;
   for (;;) {
     unsigned long long prev = *(volatile unsigned long long*)&tb[i].ctx;
     if (prev == kEmptyKey) prev = atomicCAS((unsigned long long*)&tb[i].ctx, (unsigned long long)kEmptyKey, (unsigned long long)ctx);
