@@ -57,7 +57,10 @@ enum {
   TALC_READ_OK = 0,
   TALC_READ_NO_SOLID = 1,      /* log: "No solid kmer could be found."            */
   TALC_READ_NO_STRUCTURE = 2,  /* log: "Unable to define convenient structure."   */
-  TALC_READ_SHORT = 3          /* len <= K: passed through, nothing logged        */
+  TALC_READ_SHORT = 3,         /* len <= K: passed through, nothing logged        */
+  TALC_READ_RESOURCE = 4       /* not in the reference (which has no memory bound): the search of this read outgrew even
+                                  the second-tier scratch arena (talc_ctx_set_scratch); the read is passed through
+                                  uncorrected and counted in talc_counters.reads_overflow; the batch itself succeeds */
 };
 
 /* algorithmic work of a batch (properties of the algorithm on the input) and timings */
@@ -80,10 +83,13 @@ enum {
   TALC_ERR_IO = -3,
   TALC_ERR_NO_TABLE = -4,
   TALC_ERR_CAPACITY = -5,   /* an output buffer supplied by the caller is too small */
-  TALC_ERR_SCRATCH = -6     /* a read exhausted even the second-tier scratch arena  */
+  TALC_ERR_STALE = -7,      /* a table cache made for other inputs / parameters: rebuild from the dump */
+  TALC_ERR_SCRATCH = -6     /* reserved (a read that exhausts the second-tier arena is data: TALC_READ_RESOURCE) */
 };
 
 void talc_params_default(talc_params* p, uint32_t K);
+/* sha256 prefix of the sources this binary was compiled from (talc_b200/build.py refuses a stale prebuilt library) */
+const char* talc_build_source_hash(void);
 
 int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out);
 void talc_ctx_destroy(talc_ctx* ctx);
@@ -114,10 +120,16 @@ int talc_table_import_device(talc_ctx* ctx, const void* src_device, uint64_t cap
 int talc_table_copy(talc_ctx* dst, talc_ctx* src);
 /* binary cache of the built table (at 30 M+ lines the text parse of buildCDBG,
  * Jellyfish.cpp:251-269, dominates start-up once correction is fast).  save writes the sealed slot array with a
- * small header (magic, K, MIN_COUNT, capacity, entries); load checks K and MIN_COUNT against the context,
+ * small header (magic, K, MIN_COUNT, capacity, entries, provenance); load checks K and MIN_COUNT against the context,
  * uploads the array and seals it -- the result is the table the dump would have built.            */
 int talc_table_save(talc_ctx* ctx, const char* path);
 int talc_table_load_cache(talc_ctx* ctx, const char* path, uint64_t* n_entries);
+/* The header also records whether junction colours were baked in and the size + mtime of the --SRCounts / --junctions
+ * files the table was built from.  load_cache_for refuses (TALC_ERR_STALE) a cache made from other inputs, so that a
+ * file left over from another run is rebuilt instead of silently used; both loaders check the file size against the
+ * header, recount the occupied slots on the device and refuse a table that is more than half full.            */
+int talc_table_load_cache_for(talc_ctx* ctx, const char* path, const char* dump_path, const char* junction_path_or_null,
+                              uint64_t* n_entries);
 /* point look-ups from the host (tests, debugging): found[i] in {0,1}                              */
 int talc_table_lookup(talc_ctx* ctx, const uint64_t* keys, uint64_t n, uint32_t* counts, uint32_t* colours,
                       uint8_t* found);
@@ -135,6 +147,14 @@ int talc_correct_batch_device(talc_ctx* ctx, const uint8_t* d_bases, const uint6
 /* Per-read coverage vectors only (Read::reCoverage): counts[sum(max(0,len-K+1))], host buffers.   */
 int talc_coverage_batch(talc_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
                         uint32_t* counts, uint64_t counts_capacity);
+
+/* ---- roofline microbenchmark ("the random-32 B-sector peak must be measured ... and reported") --------
+ * Uniformly random 256-bit read-only loads over a buffer of `buffer_bytes` (rounded down to a power of two; use
+ * >= 2 GiB so that the 126 MB L2 does not help).  dependent = 0: eight independent loads in flight per thread, the
+ * pattern of the coverage kernel; dependent = 1: one chain per thread, the next address hashed from the loaded sector,
+ * the pattern of the graph walk (ns_per_load is then the latency of one hop).  gbs = sectors * 32 B / time.    */
+int talc_bench_random_sectors(talc_ctx* ctx, uint64_t buffer_bytes, int dependent, uint32_t warps_per_sm, double* gbs,
+                              double* ns_per_load);
 
 /* ---- device self-tests of the scoring primitives (used by tests/ on a GPU) ------------------- */
 /* pairs of NUL-free ASCII strings given as (concatenated bytes, offsets[n+1]); op: 0 NW score,

@@ -35,6 +35,7 @@ class TalcCounters(C.Structure):
 
 
 STATUS_MESSAGES = {1: "No solid kmer could be found.", 2: "Unable to define convenient structure."}
+STATUS_RESOURCE = 4  # TALC_READ_RESOURCE: passed through uncorrected, not a reference status
 
 _lib = None
 
@@ -61,6 +62,9 @@ def lib():
         L.talc_table_copy.argtypes = [vp, vp]
         L.talc_table_save.argtypes = [vp, C.c_char_p]
         L.talc_table_load_cache.argtypes = [vp, C.c_char_p, u64p]
+        L.talc_table_load_cache_for.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, u64p]
+        L.talc_bench_random_sectors.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(C.c_double),
+                                                C.POINTER(C.c_double)]
         L.talc_table_export_device.argtypes = [vp, vp, C.c_uint64]
         L.talc_table_import_device.argtypes = [vp, vp, C.c_uint64, C.c_uint64]
         L.talc_table_lookup.argtypes = [vp, vp, C.c_uint64, vp, vp, vp]
@@ -143,6 +147,20 @@ class Talc:
         n = C.c_uint64(0)
         self._check(lib().talc_table_load_cache(self.h, path.encode(), C.byref(n)), "talc_table_load_cache")
         return n.value
+
+    def table_load_cache_for(self, path: str, dump: str, junctions: Optional[str] = None) -> int:
+        n = C.c_uint64(0)
+        self._check(lib().talc_table_load_cache_for(self.h, path.encode(), dump.encode(),
+                                                    junctions.encode() if junctions else None, C.byref(n)),
+                    "talc_table_load_cache_for")
+        return n.value
+
+    def bench_random_sectors(self, buffer_bytes: int = 4 << 30, dependent: bool = False, warps_per_sm: int = 64):
+        """(GB/s of random 32-byte sectors, ns per dependent load) -- the roofline of the hash probes."""
+        g, ns = C.c_double(0), C.c_double(0)
+        self._check(lib().talc_bench_random_sectors(self.h, buffer_bytes, 1 if dependent else 0, warps_per_sm, C.byref(g),
+                                                    C.byref(ns)), "talc_bench_random_sectors")
+        return g.value, ns.value
 
     def table_info(self):
         cap, nbytes, n = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

@@ -27,6 +27,27 @@ def _sources():
            [os.path.join(ROOT, "include", "talc_b200.h")]
 
 
+def source_hash() -> str:
+    """sha256 over the sources the library is compiled from; compiled into the .so (talc_build_source_hash) so that
+    a prebuilt binary can be told from one that is stale with respect to the tree it travels with."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in _sources():
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def library_hash(path: str = LIB):
+    import ctypes
+    try:
+        L = ctypes.CDLL(path)
+        L.talc_build_source_hash.restype = ctypes.c_char_p
+        return L.talc_build_source_hash().decode()
+    except Exception:
+        return None
+
+
 def _stale(target: str, deps) -> bool:
     if not os.path.exists(target):
         return True
@@ -35,12 +56,16 @@ def _stale(target: str, deps) -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    if force or _stale(LIB, _sources()):
+    want = source_hash()
+    if force or _stale(LIB, _sources()) or library_hash() != want:
         if not os.path.exists(NVCC):
-            if os.path.exists(LIB):
-                return LIB  # GPU box without a toolkit: use the prebuilt library from the snapshot
-            raise RuntimeError("nvcc not found and no prebuilt libtalc_b200.so")
-        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "talc_b200.cu")]
+            # a box without a toolkit may only use a prebuilt library that was compiled from exactly this tree
+            if os.path.exists(LIB) and library_hash() == want:
+                return LIB
+            raise RuntimeError("nvcc not found and libtalc_b200.so is missing or was built from other sources "
+                               "(library %s, tree %s)" % (library_hash(), want))
+        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-DTALC_SOURCE_HASH=\"%s\"" % want, "-o", LIB, os.path.join(CSRC, "talc_b200.cu")]
         subprocess.check_call(cmd, cwd=ROOT)
     return LIB
 

@@ -518,7 +518,9 @@ class Corrector {
   // ------------------------------------------------------------------ trail slots
   TALC_HDN bool setup_search(u32 pathMax) {
     slotWords = (K() + pathMax + 2 + 31) / 32 + 1;
-    maxT = wide ? 208u : 48u;
+    // frontier bound: <= 50 trails between steps (Explorer.cpp:940,1055), x4 children, plus the Q16 duplicates
+    // (the MAX_NB_BRANCHES best by distance are pushed before the whole list is pushed again)
+    maxT = 4u * kMaxInnerPaths + P.max_branches + 1u;
     cur = (Trail*)scratch.alloc(maxT * sizeof(Trail));
     nxt = (Trail*)scratch.alloc(maxT * sizeof(Trail));
     if (!cur || !nxt) return false;
@@ -526,8 +528,7 @@ class Corrector {
     const u32 wantSlots = 2 * maxT + 8;
     u32 avail = scratch.cap - scratch.top;
     // leave room for DP scratch (horizontal deltas, X-drop diagonals, bridge copies)
-    const u32 reserve = wide ? (avail / 2) : (avail / 2);
-    avail -= reserve;
+    avail -= avail / 2;
     u32 n = avail / (slotWords * 8 + 2);
     if (n > wantSlots) n = wantSlots;
     if (n < 6) { scratch.overflow = 1; return false; }
@@ -1045,8 +1046,13 @@ class Corrector {
       if (!setup_search(pathMax)) return false;
       if (!push_root(anchors[s])) return false;
       // bridges: metadata for all, sequences only for running-best record setters
-      const u32 maxBridges = wide ? 1024u : 96u;
-      const u32 maxKeep = wide ? 32u : 6u;
+      // the reference puts no cap on recorded bridges: the caps grow with the arena (second tier: ~50 000 bridges)
+      const u32 capShare = (scratch.cap - scratch.top) / 16u;
+      u32 maxBridges = capShare / (u32)sizeof(BridgeRec);
+      if (maxBridges < 1024u) maxBridges = 1024u;
+      u32 maxKeep = capShare / (slotWords * 8u);
+      if (maxKeep < 32u) maxKeep = 32u;
+      if (maxKeep > maxBridges) maxKeep = maxBridges;
       BridgeRec* br = (BridgeRec*)scratch.alloc(maxBridges * sizeof(BridgeRec));
       u64* brSeq = (u64*)scratch.alloc(maxKeep * slotWords * 8);
       if (!br || !brSeq) return false;

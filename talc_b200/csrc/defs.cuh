@@ -70,6 +70,7 @@ enum ReadStatus : u8 {
   kReadNoSolid = 1,      // "No solid kmer could be found."
   kReadNoStructure = 2,  // "Unable to define convenient structure."
   kReadShort = 3,        // len <= K : untouched, not logged
+  kReadResource = 4,     // not in the reference: the read exhausted even the last scratch tier and passes through uncorrected
   kReadOverflow = 250    // internal: scratch arena too small, re-run with a larger arena
 };
 

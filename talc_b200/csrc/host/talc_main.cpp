@@ -211,8 +211,12 @@ int main(int argc, const char** argv) {
   uint64_t nLines = 0, nKept = 0;
   int rc = -1;
   // --tableCache <file> (extension): reuse the built table if the file exists, else build it from the
-  // dump and write the file; the cache must have been made from the same --SRCounts / --junctions / -k / MIN_COUNT
-  if (!cli.tableCache.empty()) rc = talc_table_load_cache(ctx[0], cli.tableCache.c_str(), &nKept);
+  // dump and write the file; a cache made from other --SRCounts / --junctions files (size, mtime), another -k or
+  // MIN_COUNT is refused by the library and rebuilt
+  if (!cli.tableCache.empty())
+    rc = talc_table_load_cache_for(ctx[0], cli.tableCache.c_str(), cli.dump.c_str(),
+                                   cli.useJunctions ? cli.junctions.c_str() : nullptr, &nKept);
+  if (rc == TALC_ERR_STALE) std::cout << "[TALC]: " << talc_last_error(ctx[0]) << " -> rebuilding it." << std::endl;
   if (rc != 0) {
     rc = talc_table_load_dump(ctx[0], cli.dump.c_str(), cli.useJunctions ? cli.junctions.c_str() : nullptr, &nLines, &nKept);
     if (rc == 0 && nKept > 0 && !cli.tableCache.empty() && talc_table_save(ctx[0], cli.tableCache.c_str()) != 0)

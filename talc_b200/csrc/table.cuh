@@ -70,14 +70,18 @@ TALC_HD int sector_resolve(const Slot& s0, const Slot& s1, u64 key, u32& count, 
 }
 
 // continue a probe sequence past sector b
+// (bounded by the capacity: a table without a free slot -- refused at seal -- cannot hang the GPU)
 TALC_HDN bool table_probe_from(const TableView& t, u64 b, u64 key, u32& count, u32& colour) {
-  for (;;) {
+  for (u64 n = 0; n <= t.mask; n += 2) {
     b = (b + 2) & t.mask;
     Slot s0, s1;
     load_sector(t.slots + b, s0, s1);
     const int r = sector_resolve(s0, s1, key, count, colour);
     if (r >= 0) return r == 1;
   }
+  count = 0;
+  colour = 0;
+  return false;
 }
 // the same by value: (colour << 32) | count, 0 when absent (no reference arguments: nothing is forced into local memory)
 TALC_HDN u64 table_probe_from_v(const TableView& t, u64 b, u64 key) {
@@ -204,13 +208,15 @@ __device__ __forceinline__ void load_bucket(const CtxBucket* p, u64& ctx, u32 cn
   colmask = (u32)x3;
 }
 __device__ __noinline__ void ctx_probe_from(const CtxView& v, u64 i, u64 ctx, u32 cnt[4], u32& colmask) {
-  for (;;) {
+  for (u64 n = 0; n <= v.mask; ++n) {
     i = (i + 1) & v.mask;
     u64 c;
     load_bucket(v.b + i, c, cnt, colmask);
     if (c == ctx) return;
-    if (c == kEmptyKey) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; colmask = 0; return; }
+    if (c == kEmptyKey) break;
   }
+  cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+  colmask = 0;
 }
 // the four successor counts of a context: home bucket and the next one are fetched together
 __device__ __forceinline__ void ctx_lookup(const CtxView& v, u64 ctx, u32 cnt[4], u32& colmask) {

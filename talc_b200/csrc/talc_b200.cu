@@ -5,12 +5,13 @@
 //   ctx_fill_empty_kernel / ctx_build_kernel                            successor tables derived from the k-mer table
 //   kmer_count_kernel + coverage_kernel                                 Read::reCoverage, batched
 //   cost_key_kernel (+ cub radix sort)                                  processing order: estimated cost, descending
-//   correct_kernel<wide>                                                segmentation + graph search + scoring
+//   correct_kernel                                                      segmentation + graph search + scoring
 //   gather_kernel                                                       corrected reads back into input order
 // Grid sizes are multiples of the SM count; per-thread scratch lives in HBM (180 GB makes that cheap).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <cub/cub.cuh>
@@ -31,13 +32,16 @@ using namespace talc;
 // Entry i of the dump (file order) claims a slot with CAS, then the (line index, count) pair with the
 // smallest line index wins through a 64-bit atomicMin: that is map::insert's "first line wins"
 // (Jellyfish.cpp:262) independent of the order in which threads arrive.
-__global__ void table_insert_kernel(Slot* slots, u64 mask, const u64* keys, const u32* counts, u64 n) {
+// `line0` is the dump-line index of entry 0 (the GPU parser inserts a dump piece by piece); a table without a free
+// slot ends the probe after one lap and raises *fail instead of spinning.
+__global__ void table_insert_kernel(Slot* slots, u64 mask, const u64* keys, const u32* counts, u64 n, u64 line0, u32* fail) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const u64 key = keys[i];
+    if (key == kEmptyKey) continue;  // the GPU parser marks filtered / malformed lines this way
     u64 b = hash_kmer(key) & mask & ~1ull;
     Slot* hit = nullptr;
-    while (!hit) {
+    for (u64 lap = 0; !hit && lap <= mask; lap += 2) {
       for (int j = 0; j < 2 && !hit; ++j) {
         Slot* s = slots + b + j;
         unsigned long long prev = *(volatile unsigned long long*)&s->key;
@@ -46,7 +50,8 @@ __global__ void table_insert_kernel(Slot* slots, u64 mask, const u64* keys, cons
       }
       b = (b + 2) & mask;
     }
-    const unsigned long long v = ((unsigned long long)i << 32) | (unsigned long long)counts[i];
+    if (!hit) { atomicExch(fail, 1u); continue; }
+    const unsigned long long v = ((unsigned long long)(line0 + i) << 32) | (unsigned long long)counts[i];
     atomicMin((unsigned long long*)&hit->count, v);  // {count, colour} viewed as one u64: colour half carries the line index
   }
 }
@@ -80,7 +85,7 @@ __global__ void table_colour_kernel(Slot* slots, u64 mask, const u64* keys, cons
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const u64 key = keys[i];
     u64 b = hash_kmer(key) & mask & ~1ull;
-    for (;;) {
+    for (u64 lap = 0; lap <= mask; lap += 2) {
       bool done = false;
       for (int j = 0; j < 2; ++j) {
         Slot* s = slots + b + j;
@@ -104,9 +109,9 @@ __global__ void ctx_fill_empty_kernel(CtxBucket* b, u64 capacity) {
     b[i].pad = 0;
   }
 }
-__device__ __forceinline__ void ctx_insert(CtxBucket* tb, u64 mask, u64 ctx, u32 b, u32 count, u32 colour) {
+__device__ __forceinline__ void ctx_insert(CtxBucket* tb, u64 mask, u64 ctx, u32 b, u32 count, u32 colour, u32* fail) {
   u64 i = hash_ctx(ctx) & mask;
-  for (;;) {
+  for (u64 lap = 0; lap <= mask; ++lap) {
     unsigned long long prev = *(volatile unsigned long long*)&tb[i].ctx;
     if (prev == kEmptyKey) prev = atomicCAS((unsigned long long*)&tb[i].ctx, (unsigned long long)kEmptyKey, (unsigned long long)ctx);
     if (prev == kEmptyKey || prev == ctx) {
@@ -116,14 +121,22 @@ __device__ __forceinline__ void ctx_insert(CtxBucket* tb, u64 mask, u64 ctx, u32
     }
     i = (i + 1) & mask;
   }
+  atomicExch(fail, 1u);  // no free bucket (cannot happen with the load <= 1/3 sizing from a recounted table)
 }
-__global__ void ctx_build_kernel(const Slot* slots, u64 capacity, CtxBucket* right, CtxBucket* left, u64 mask, u32 K) {
+__global__ void table_count_kernel(const Slot* slots, u64 capacity, unsigned long long* n_entries) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  unsigned long long mine = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) mine += slots[i].key != kEmptyKey ? 1 : 0;
+  mine = __reduce_add_sync(0xffffffffu, (u32)mine);  // <= 32 * (capacity / stride + 1) per warp: fits 32 bits
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_entries, mine);
+}
+__global__ void ctx_build_kernel(const Slot* slots, u64 capacity, CtxBucket* right, CtxBucket* left, u64 mask, u32 K, u32* fail) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
     const Slot s = slots[i];
     if (s.key == kEmptyKey) continue;
-    ctx_insert(right, mask, s.key >> 2, (u32)(s.key & 3ull), s.count, s.colour);
-    ctx_insert(left, mask, s.key & kmer_mask(K - 1), (u32)(s.key >> (2 * (K - 1))), s.count, s.colour);
+    ctx_insert(right, mask, s.key >> 2, (u32)(s.key & 3ull), s.count, s.colour, fail);
+    ctx_insert(left, mask, s.key & kmer_mask(K - 1), (u32)(s.key >> (2 * (K - 1))), s.count, s.colour, fail);
   }
 }
 
@@ -251,7 +264,7 @@ __global__ void __launch_bounds__(256) coverage_kernel(TableView tv, u32 K, cons
 }
 
 // =====================================================================================
-// correction: one thread per read, warps pull 32 reads at a time from a length-sorted queue
+// correction: one warp per read, warps pull reads one at a time from a cost-sorted queue
 // =====================================================================================
 struct CorrectArgs {
   TableView tv;
@@ -278,6 +291,8 @@ struct CorrectArgs {
   u32* outFull;
   u32* readKcycles;  // optional: per-read elapsed SM cycles / 1024 (tuning aid)
   CtxView cright, cleft;  // successor tables
+  u32 wide;      // worst-case sizing of the X-drop anti-diagonals (align.cuh)
+  u32 lastTier;  // no larger arena follows: a read that overflows passes through uncorrected (kReadResource)
 };
 
 // One warp owns one read.  All 32 lanes run the per-read control flow on the same data, so the warp
@@ -289,7 +304,6 @@ struct CorrectArgs {
 #ifndef TALC_MIN_BLOCKS
 #define TALC_MIN_BLOCKS 2
 #endif
-template <bool WIDE>
 __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) correct_kernel(CorrectArgs A) {
   // One copy of the per-read state per warp, in shared memory: with 32 lanes holding identical state, keeping
   // it in (per-lane) local memory multiplies its cache footprint by 32 and the L1 thrashes.
@@ -321,11 +335,15 @@ __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) correct_kernel(CorrectAr
     job.cov = A.cov + A.kmerOff[r];
     job.arena = myArena;
     job.arena_bytes = A.arenaBytes;
-    job.wide = WIDE;
+    job.wide = A.wide != 0;
     __syncwarp();
     const long long t0 = clock64();
-    const u8 st = cx.run(job);
+    u8 st = cx.run(job);
     __syncwarp();
+    if (st == kReadOverflow && A.lastTier) {
+      st = kReadResource;
+      if (lane == 0) mine.reads_overflow += 1;
+    }
     if (A.readKcycles && lane == 0) A.readKcycles[r] = (u32)((clock64() - t0) >> 10);
     if (st == kReadOverflow) {
       if (lane == 0) {
@@ -389,6 +407,37 @@ __global__ void model_tabs_kernel(double alpha, u32 n, double* lower, double* up
   lower[i] = model_lower_bound(i, alpha);
   upper[i] = model_upper_bound(i, alpha);
   sq[i] = sqrt((double)i);
+}
+
+// =====================================================================================
+// random-sector peak: the roofline of the hash probes is not the streaming HBM bandwidth but what the
+// memory system delivers for uniformly random 32-byte sectors.  mode 0: `ILP` independent 256-bit loads in flight
+// per thread (the coverage kernel's pattern); mode 1: one dependent chain per thread -- the next address is a hash
+// of the loaded sector (the walk's pattern: the successor bucket decides the next k-mer).
+// =====================================================================================
+template <int ILP>
+__global__ void __launch_bounds__(256) random_sector_kernel(const ulonglong4* __restrict__ buf, u64 sectorMask, u32 iters, int dependent,
+                                                            unsigned long long* sink) {
+  u64 x[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) x[j] = hash_kmer(((u64)blockIdx.x * blockDim.x + threadIdx.x) * ILP + j + 1);
+  u64 acc = 0;
+  for (u32 it = 0; it < iters; ++it) {
+    u64 v[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      u64 a0, a1, a2, a3;
+      asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(buf + (x[j] & sectorMask)));
+      v[j] = a0 ^ a1 ^ a2 ^ a3;
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      acc += v[j];
+      x[j] = x[j] * 0x9E3779B97F4A7C15ull + (dependent ? v[j] : 0ull) + 0x632BE59BD9B4E019ull;
+      x[j] ^= x[j] >> 29;
+    }
+  }
+  if (acc == 0x1234567ull) *sink = acc;
 }
 
 // =====================================================================================
@@ -500,6 +549,9 @@ struct talc_ctx {
   u64 nEntries = 0;
   bool tableOwned = true;
   bool tableReady = false;
+  // where the table came from (recorded in the binary cache so that a cache of other inputs is not reused silently)
+  u32 provJunctions = 0;
+  u64 provDumpSize = 0, provDumpMtime = 0, provJuncSize = 0, provJuncMtime = 0;
   CtxBucket* ctxRight = nullptr;  // successor tables, derived from the k-mer table when it is sealed
   CtxBucket* ctxLeft = nullptr;
   u64 ctxCap = 0;
@@ -561,6 +613,11 @@ void talc_params_default(talc_params* p, uint32_t K) {
   p->cycle_mode = 0;
   p->q11_zero_init = 1;
 }
+
+#ifndef TALC_SOURCE_HASH
+#define TALC_SOURCE_HASH "unknown"
+#endif
+const char* talc_build_source_hash(void) { return TALC_SOURCE_HASH; }
 
 const char* talc_last_error(talc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
 
@@ -657,25 +714,45 @@ int talc_table_device_ptr(talc_ctx* c, void** p) {
   *p = c->slots;
   return TALC_OK;
 }
+// Recounts the occupied slots on the device (the caller's n_entries is a claim, not a fact), refuses a table without
+// room to end a probe (load > 0.5), sizes the successor tables from the recount and derives them.
 static int build_ctx_tables(talc_ctx* c) {
   CUDA_TRY(c, cudaSetDevice(c->device));
   free_ctx_tables(c);
+  const int blocks = c->sms * 8;
+  unsigned long long* dN = nullptr;
+  CUDA_TRY(c, cudaMalloc((void**)&dN, 16));
+  CUDA_TRY(c, cudaMemsetAsync(dN, 0, 16, c->stream));
+  table_count_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, c->capacity, dN);
+  CUDA_TRY(c, cudaGetLastError());
+  unsigned long long hN[2] = {0, 0};
+  CUDA_TRY(c, cudaMemcpyAsync(hN, dN, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (2 * hN[0] > c->capacity) {
+    cudaFree(dN);
+    c->err = "k-mer table is more than half full (corrupt cache or wrong capacity): refused";
+    return TALC_ERR_ARG;
+  }
+  c->nEntries = hN[0];
   u64 cap = 4;
   while (cap < 3 * c->nEntries + 4) cap <<= 1;  // load <= 1/3: a look-up rarely leaves its home pair of buckets
   CUDA_TRY(c, cudaMalloc((void**)&c->ctxRight, cap * sizeof(CtxBucket)));
   CUDA_TRY(c, cudaMalloc((void**)&c->ctxLeft, cap * sizeof(CtxBucket)));
   c->ctxCap = cap;
-  const int blocks = c->sms * 8;
   ctx_fill_empty_kernel<<<blocks, 256, 0, c->stream>>>(c->ctxRight, cap);
   ctx_fill_empty_kernel<<<blocks, 256, 0, c->stream>>>(c->ctxLeft, cap);
-  ctx_build_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, c->capacity, c->ctxRight, c->ctxLeft, cap - 1, c->P.K);
+  ctx_build_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, c->capacity, c->ctxRight, c->ctxLeft, cap - 1, c->P.K, (u32*)(dN + 1));
   CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaMemcpyAsync(hN + 1, dN + 1, 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  cudaFree(dN);
+  if (hN[1]) { c->err = "successor tables overflowed"; return TALC_ERR_ARG; }
   return TALC_OK;
 }
+// n_entries is informational: the occupied slots are recounted on the device
 int talc_table_seal(talc_ctx* c, uint64_t n_entries) {
   if (!c || !c->slots) return TALC_ERR_ARG;
-  c->nEntries = n_entries;
+  (void)n_entries;
   const int rc = build_ctx_tables(c);
   if (rc) return rc;
   c->tableReady = true;
@@ -709,23 +786,36 @@ extern "C" int talc_table_copy(talc_ctx* dst, talc_ctx* src) {
   int rc = talc_table_alloc(dst, src->capacity);
   if (rc) return rc;
   CUDA_TRY(dst, cudaMemcpyPeer(dst->slots, dst->device, src->slots, src->device, src->capacity * sizeof(Slot)));
+  dst->provJunctions = src->provJunctions;
+  dst->provDumpSize = src->provDumpSize; dst->provDumpMtime = src->provDumpMtime;
+  dst->provJuncSize = src->provJuncSize; dst->provJuncMtime = src->provJuncMtime;
   return talc_table_seal(dst, src->nEntries);
 }
 
 // ---- binary table cache (include/talc_b200.h): header + raw slot array, streamed in 64 MiB pieces
 struct TableCacheHeader {
-  char magic[8];  // "TALCTBL1"
+  char magic[8];  // "TALCTBL2"
   u32 K, min_count;
   u64 capacity, entries;
+  u32 junctions, pad;                                // junction colours baked in?
+  u64 dumpSize, dumpMtime, juncSize, juncMtime;      // identity of the text inputs (0 = built from packed arrays)
 };
+static void file_identity(const char* path, u64& size, u64& mtime) {
+  struct stat st;
+  size = mtime = 0;
+  if (path && stat(path, &st) == 0) { size = (u64)st.st_size; mtime = (u64)st.st_mtime; }
+}
 extern "C" int talc_table_save(talc_ctx* c, const char* path) {
   if (!c || !path || !c->tableReady) return TALC_ERR_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
   FILE* f = fopen(path, "wb");
   if (!f) { c->err = std::string("cannot write ") + path; return TALC_ERR_IO; }
   TableCacheHeader h;
-  memcpy(h.magic, "TALCTBL1", 8);
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "TALCTBL2", 8);
   h.K = c->P.K; h.min_count = c->P.min_count; h.capacity = c->capacity; h.entries = c->nEntries;
+  h.junctions = c->provJunctions;
+  h.dumpSize = c->provDumpSize; h.dumpMtime = c->provDumpMtime; h.juncSize = c->provJuncSize; h.juncMtime = c->provJuncMtime;
   bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
   const size_t total = (size_t)c->capacity * sizeof(Slot), piece = 64u << 20;
   std::vector<char> buf(std::min(total, piece));
@@ -738,21 +828,35 @@ extern "C" int talc_table_save(talc_ctx* c, const char* path) {
   if (!ok) { c->err = std::string("error while writing ") + path; return TALC_ERR_IO; }
   return TALC_OK;
 }
-extern "C" int talc_table_load_cache(talc_ctx* c, const char* path, uint64_t* n_entries) {
+// check_inputs: the cache must have been made from exactly these text files (size + mtime) and junction setting
+static int load_cache(talc_ctx* c, const char* path, bool check_inputs, const char* dump_path, const char* junction_path,
+                      uint64_t* n_entries) {
   if (!c || !path) return TALC_ERR_ARG;
   FILE* f = fopen(path, "rb");
   if (!f) { c->err = std::string("cannot read ") + path; return TALC_ERR_IO; }
   TableCacheHeader h;
-  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "TALCTBL1", 8) != 0 || h.capacity < 2 ||
-      (h.capacity & (h.capacity - 1))) {
+  struct stat st;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "TALCTBL2", 8) != 0 || h.capacity < 2 ||
+      (h.capacity & (h.capacity - 1)) || fstat(fileno(f), &st) != 0 ||
+      (u64)st.st_size != sizeof(h) + h.capacity * sizeof(Slot) || 2 * h.entries > h.capacity) {
     fclose(f);
-    c->err = std::string(path) + " is not a table cache";
+    c->err = std::string(path) + " is not a table cache (or is truncated)";
     return TALC_ERR_IO;
   }
   if (h.K != c->P.K || h.min_count != c->P.min_count) {
     fclose(f);
     c->err = "table cache was built with another k-mer size or MIN_COUNT";
-    return TALC_ERR_ARG;
+    return TALC_ERR_STALE;
+  }
+  if (check_inputs) {
+    u64 ds, dm, js, jm;
+    file_identity(dump_path, ds, dm);
+    file_identity(junction_path, js, jm);
+    if (h.junctions != (junction_path ? 1u : 0u) || h.dumpSize != ds || h.dumpMtime != dm || h.juncSize != js || h.juncMtime != jm) {
+      fclose(f);
+      c->err = "table cache was built from other --SRCounts / --junctions inputs";
+      return TALC_ERR_STALE;
+    }
   }
   int rc = talc_table_alloc(c, h.capacity);
   if (rc) { fclose(f); return rc; }
@@ -766,8 +870,25 @@ extern "C" int talc_table_load_cache(talc_ctx* c, const char* path, uint64_t* n_
   }
   fclose(f);
   if (!ok) { c->err = std::string("truncated table cache ") + path; return TALC_ERR_IO; }
-  if (n_entries) *n_entries = h.entries;
-  return talc_table_seal(c, h.entries);
+  c->provJunctions = h.junctions;
+  c->provDumpSize = h.dumpSize; c->provDumpMtime = h.dumpMtime; c->provJuncSize = h.juncSize; c->provJuncMtime = h.juncMtime;
+  rc = talc_table_seal(c, h.entries);
+  if (rc) return rc;
+  if (c->nEntries != h.entries) {
+    c->tableReady = false;
+    c->err = "table cache is corrupt: occupied slots differ from the header";
+    return TALC_ERR_IO;
+  }
+  if (n_entries) *n_entries = c->nEntries;
+  return TALC_OK;
+}
+extern "C" int talc_table_load_cache(talc_ctx* c, const char* path, uint64_t* n_entries) {
+  return load_cache(c, path, false, nullptr, nullptr, n_entries);
+}
+extern "C" int talc_table_load_cache_for(talc_ctx* c, const char* path, const char* dump_path, const char* junction_path,
+                                         uint64_t* n_entries) {
+  if (!dump_path) return TALC_ERR_ARG;
+  return load_cache(c, path, true, dump_path, junction_path, n_entries);
 }
 
 // entries: dump order, already filtered to count >= MIN and valid ACGT k-mers of length K
@@ -786,12 +907,14 @@ static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vec
     CUDA_TRY(c, cudaMalloc((void**)&dCounts, n * 4));
     CUDA_TRY(c, cudaMemcpyAsync(dKeys, keys.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(dCounts, counts.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
-    table_insert_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap - 1, dKeys, dCounts, n);
-    CUDA_TRY(c, cudaGetLastError());
   }
   unsigned long long* dN = nullptr;
-  CUDA_TRY(c, cudaMalloc((void**)&dN, 8));
-  CUDA_TRY(c, cudaMemsetAsync(dN, 0, 8, c->stream));
+  CUDA_TRY(c, cudaMalloc((void**)&dN, 16));
+  CUDA_TRY(c, cudaMemsetAsync(dN, 0, 16, c->stream));
+  if (n) {
+    table_insert_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap - 1, dKeys, dCounts, n, 0, (u32*)(dN + 1));
+    CUDA_TRY(c, cudaGetLastError());
+  }
   table_finalize_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap, dN);
   CUDA_TRY(c, cudaGetLastError());
   if (!ckeys.empty()) {
@@ -807,17 +930,18 @@ static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vec
     cudaFree(dCk);
     cudaFree(dCc);
   }
-  unsigned long long hN = 0;
-  CUDA_TRY(c, cudaMemcpyAsync(&hN, dN, 8, cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long hN[2] = {0, 0};
+  CUDA_TRY(c, cudaMemcpyAsync(hN, dN, 16, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   cudaFree(dN);
   if (dKeys) cudaFree(dKeys);
   if (dCounts) cudaFree(dCounts);
-  c->nEntries = hN;
+  if (hN[1]) { c->err = "k-mer table overflowed during the build"; return TALC_ERR_ARG; }
+  c->nEntries = hN[0];
   rc = build_ctx_tables(c);
   if (rc) return rc;
   c->tableReady = true;
-  if (n_kept) *n_kept = hN;
+  if (n_kept) *n_kept = c->nEntries;
   return TALC_OK;
 }
 
@@ -876,6 +1000,8 @@ int talc_table_load_packed(talc_ctx* c, const uint64_t* keys, const int64_t* cou
   std::vector<u64> ck;
   std::vector<u32> cc;
   reduce_colours(c->params, jkeys, jcounts, nj, use_junctions != 0, ck, cc);
+  c->provJunctions = use_junctions ? 1u : 0u;
+  c->provDumpSize = c->provDumpMtime = c->provJuncSize = c->provJuncMtime = 0;
   return build_table(c, k, v, ck, cc, n_kept);
 }
 
@@ -903,6 +1029,9 @@ int talc_table_load_dump(talc_ctx* c, const char* dump_path, const char* junctio
   }
   std::vector<u32> v(d.counts.size());
   for (size_t i = 0; i < v.size(); ++i) v[i] = (u32)(int)d.counts[i];
+  c->provJunctions = junction_path ? 1u : 0u;
+  file_identity(dump_path, c->provDumpSize, c->provDumpMtime);
+  file_identity(junction_path, c->provJuncSize, c->provJuncMtime);
   return build_table(c, d.keys, v, ck, cc, n_kept);
 }
 
@@ -1046,14 +1175,15 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
     CUDA_TRY(c, cudaMemsetAsync(dbgCycles.p, 0, (size_t)n * 4, c->stream));
     A.readKcycles = (u32*)dbgCycles.p;
   }
-  correct_kernel<true><<<blocks, 128, 0, c->stream>>>(A);
+  A.wide = 1;
+  A.lastTier = 0;
+  correct_kernel<<<blocks, 128, 0, c->stream>>>(A);
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaEventRecord(c->ev[3], c->stream));
   u32 hOver = 0;
   CUDA_TRY(c, cudaMemcpyAsync(&hOver, dNOver, 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   u64 launches = 4;
-  u32 hOver2 = 0;
   if (hOver > 0) {
     // second tier: only the reads whose first-tier slice was too small, worst-case buffer sizing
     CUDA_TRY(c, cudaMemsetAsync(dWork, 0, 8, c->stream));  // workCounter and nOverflow
@@ -1064,10 +1194,10 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
     B.order = (const u32*)c->sortVal.p;
     B.nOrder = hOver;
     B.arenaBytes = c->tier2Bytes;
+    B.lastTier = 1;
     u32 b2 = std::max<u32>(1, std::min<u32>(c->tier2Warps / 4, (hOver + 3) / 4));
-    correct_kernel<true><<<b2, 128, 0, c->stream>>>(B);
+    correct_kernel<<<b2, 128, 0, c->stream>>>(B);
     CUDA_TRY(c, cudaGetLastError());
-    CUDA_TRY(c, cudaMemcpyAsync(&hOver2, dNOver, 4, cudaMemcpyDeviceToHost, c->stream));
     launches++;
   }
   CUDA_TRY(c, cudaEventRecord(c->ev[4], c->stream));
@@ -1083,10 +1213,6 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
   CUDA_TRY(c, cudaMemcpyAsync(&hOutFull, dOutFull, 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(hCtr, dCounters, sizeof(hCtr), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  if (hOver2 > 0) {
-    c->err = "a read exhausted the second-tier scratch arena; raise it with talc_ctx_set_scratch";
-    return TALC_ERR_SCRATCH;
-  }
   if (hOutFull) { c->err = "internal output arena too small"; return TALC_ERR_CAPACITY; }
   if (hTotalOut > outCapacity) { c->err = "out_capacity too small for the corrected reads"; return TALC_ERR_CAPACITY; }
   gather_kernel<<<c->sms * 8, 256, 0, c->stream>>>((const u8*)c->outArena.p, (const u64*)c->outPos.p, (const u32*)c->outLen.p,
@@ -1122,7 +1248,6 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
     counters->reads = n;
     counters->bases_in = totalBases;
     counters->reads_second_tier = hOver;
-    counters->reads_overflow = hOver2;
     counters->kernel_launches = launches + 3;
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); counters->ms_coverage = ms;
@@ -1194,6 +1319,47 @@ int talc_coverage_batch(talc_ctx* c, const uint8_t* bases, const uint64_t* offse
   if (totalKmers > countsCapacity) { c->err = "counts_capacity too small"; return TALC_ERR_CAPACITY; }
   CUDA_TRY(c, cudaMemcpyAsync(counts, c->cov.p, totalKmers * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return TALC_OK;
+}
+
+// ---------------------------------------------------------------------------------- roofline microbenchmark
+int talc_bench_random_sectors(talc_ctx* c, uint64_t buffer_bytes, int dependent, uint32_t warps_per_sm, double* gbs,
+                              double* ns_per_load) {
+  if (!c || !gbs || buffer_bytes < (1u << 20)) return TALC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  u64 sectors = 1;
+  while (sectors * 2 * 32 <= buffer_bytes) sectors <<= 1;
+  void* buf = nullptr;
+  unsigned long long* sink = nullptr;
+  CUDA_TRY(c, cudaMalloc(&buf, sectors * 32));
+  CUDA_TRY(c, cudaMalloc((void**)&sink, 8));
+  CUDA_TRY(c, cudaMemsetAsync(buf, 0x5a, sectors * 32, c->stream));
+  if (warps_per_sm == 0) warps_per_sm = 64;
+  const u32 blocks = (u32)c->sms * ((warps_per_sm + 7) / 8);
+  const u32 iters = dependent ? 2048u : 1024u;
+  const int ilp = dependent ? 1 : 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+    CUDA_TRY(c, cudaEventRecord(e0, c->stream));
+    if (dependent) random_sector_kernel<1><<<blocks, 256, 0, c->stream>>>((const ulonglong4*)buf, sectors - 1, iters, 1, sink);
+    else random_sector_kernel<8><<<blocks, 256, 0, c->stream>>>((const ulonglong4*)buf, sectors - 1, iters, 0, sink);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(e1, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(sink);
+  const double loads = (double)blocks * 256.0 * iters * ilp;
+  *gbs = loads * 32.0 / 1e9 / (best / 1e3);
+  if (ns_per_load) *ns_per_load = (double)best * 1e6 / iters;  // per thread: latency of one dependent load (mode 1)
   return TALC_OK;
 }
 
