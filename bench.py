@@ -26,6 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "corrected long-read Mbp/s"
+TRAFFIC_SOURCE = ("profiles/r01_traffic_correct_kernel.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch "
+                  "of this workload; captured at commit c62cd49, round 1)")
 
 
 def parse_args():
@@ -216,6 +218,7 @@ def run_gpu(args, rank, world, local_rank):
     B = args.batch_reads
     reads, roff = synth.make_reads(cfg, tr, B * nsteps, dev, seed_offset=3 + 17 * rank)
     cpu_keys = (keys, counts, jk, jc)
+    tr_keep = tr if world > 1 else None
     del tr
     t_gen = time.time() - t0
     roff = roff.to(torch.int64)
@@ -266,32 +269,58 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     value = float(tot) / 1e6 / (float(tmax) / 1e3)
 
-    # ---- end-to-end leg: host (pinned) buffers through talc_correct_batch, copies inside the timed region
-    e2e_ms, e2e_bases, h2d, d2h = 0.0, 0, 0, 0
+    # ---- end-to-end leg: host (pinned) buffers through talc_correct_batch, copies inside the timed region; ALL
+    # steps, timed by the host wall clock around the calls (barrier + synchronize on both sides), max over ranks
     host_out = torch.empty(2 * maxb + 64 * B + 4096, dtype=torch.uint8).pin_memory().numpy()
     host_ooff = np.zeros(B + 1, dtype=np.uint64)
     host_st = np.zeros(B, dtype=np.uint8)
     pinned = []
-    for i in range(args.warmup + args.steps - 1, args.warmup + args.steps + 1):
-        r, o, nb = batch(i)
+    for i in range(3):  # three pinned input batches, cycled (a different slice every step, bounded pinned memory)
+        r, o, nb = batch(args.warmup + i)
         pinned.append((r.cpu().pin_memory().numpy(), o.cpu().numpy().astype(np.uint64), nb))
-    ctx.correct(pinned[1][0], pinned[1][1], host_out, host_ooff, host_st)  # warm-up of the host path
+    ctx.correct(pinned[2][0], pinned[2][1], host_out, host_ooff, host_st)  # warm-up of the host path
+    e2e_bases, h2d, d2h, e2e_dev_ms = 0, 0, 0, 0.0
     barrier()
-    e2e_steps = max(1, min(args.steps, 2))
-    for s in range(e2e_steps):
-        hr, ho, nb = pinned[s % 2]
+    w0 = time.perf_counter()
+    for s_ in range(args.steps):
+        hr, ho, nb = pinned[s_ % 3]
         out, ooff, st, c = ctx.correct(hr, ho, host_out, host_ooff, host_st)
-        e2e_ms += c["ms_total"]
+        e2e_dev_ms += c["ms_total"]
         e2e_bases += nb
         h2d = nb + 8 * (B + 1)
         d2h = int(ooff[-1]) + 8 * (B + 1) + B
     barrier()
-    emax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    e2e_wall_ms = (time.perf_counter() - w0) * 1e3
+    emax = torch.tensor([e2e_wall_ms], dtype=torch.float64, device=dev)
     etot = torch.tensor([float(e2e_bases)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(emax, op=dist.ReduceOp.MAX)
         dist.all_reduce(etot, op=dist.ReduceOp.SUM)
     e2e_value = float(etot) / 1e6 / (float(emax) / 1e3)
+
+    # ---- correctness of what was just timed.  Every rank corrects the SAME batch (rank 0's step-0 slice): the
+    # digests of (bytes, offsets, status) must agree across the replicas of the table, and on rank 0 the first
+    # `--cpu-sample-reads` reads are compared byte for byte with the oracle below (parity field).
+    import hashlib
+    if world > 1:
+        shared_reads, shared_off = synth.make_reads(cfg, tr_keep, B, dev, seed_offset=3)
+        shared_off = shared_off.to(torch.int64)
+        sb_r, sb_o, sb_n = shared_reads.contiguous(), shared_off.contiguous(), int(shared_off[-1])
+    else:
+        sb_r, sb_o, sb_n = batch(0)
+    ctx.correct_device(sb_r, sb_o, sb_n, d_out, d_ooff, d_st)
+    torch.cuda.synchronize()
+    g_off = d_ooff.cpu().numpy().astype(np.uint64)
+    g_out = d_out[: int(g_off[-1])].cpu().numpy()
+    g_st = d_st.cpu().numpy()
+    digest = hashlib.sha256(g_out.tobytes() + g_off.tobytes() + g_st.tobytes()).digest()
+    replica_parity = None
+    if world > 1:
+        mine = torch.tensor(list(digest), dtype=torch.uint8, device=dev)
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        same = all(bool((v == allv[0]).all()) for v in allv)
+        replica_parity = "ok" if same else "MISMATCH"
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -315,13 +344,16 @@ def run_gpu(args, rank, world, local_rank):
                            "table_broadcast_ms": round(t_bcast_ms, 2), "wall_s_timed_region": round(wall, 3)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": measured_traffic() if B == 131072 and args.config == 2 and args.scale == 1.0 else None,
-                             "traffic_source": "profiles/r01_traffic_correct_kernel.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch of this workload)",
+                             "traffic_source": TRAFFIC_SOURCE,
                              "kernel": "correct_kernel", "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": k_ms,
                              "coverage_kernel": {"achieved": cov_bytes / 1e9 / (cov_ms / 1e3), "ms_per_launch": cov_ms,
                                                  "algorithmic_bytes_per_launch": cov_bytes,
                                                  "frac": cov_bytes / 1e9 / (cov_ms / 1e3) / peak}},
-                "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": args.steps, "clock": "host wall clock around talc_correct_batch, max over ranks",
+                        "wall_ms": float(emax), "device_event_ms": e2e_dev_ms},
+                "replica_parity": replica_parity,
                 # stage-4 integer work: DP cell updates of the reference algorithm per second of correct_kernel
                 "dp": {"cells_per_launch": (agg["cells_nw"] + agg["cells_lcs"] + agg["cells_ovl"] + agg["cells_xdrop"]) / steps,
                        "gcups": (agg["cells_nw"] + agg["cells_lcs"] + agg["cells_ovl"] + agg["cells_xdrop"]) / steps / 1e9 / (k_ms / 1e3),
@@ -333,16 +365,41 @@ def run_gpu(args, rank, world, local_rank):
                                                      "cells_nw", "cells_lcs", "cells_ovl", "cells_xdrop", "gaps", "gaps_bridged",
                                                      "reads_second_tier", "reads_ok", "reads")},
                 "cpu_baseline": None}
+        rnd = random_sector_peaks(ctx)
+        line["roofline"].update(rnd)
+        if rnd.get("peak_random"):
+            line["roofline"]["frac_random"] = achieved / rnd["peak_random"]
+            line["roofline"]["coverage_kernel"]["frac_random"] = line["roofline"]["coverage_kernel"]["achieved"] / rnd["peak_random"]
+        bad = 0
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, cfg, cpu_keys, use_j, reads, roff)
+            line["cpu_baseline"], line["parity"] = cpu_baseline(args, cfg, cpu_keys, use_j, reads, roff, (g_out, g_off, g_st))
+            bad = line["parity"]["mismatch"]
         print(json.dumps(line), flush=True)
+        if bad or replica_parity == "MISMATCH":
+            print("bench.py: PARITY FAILURE -- the numbers above are void", file=sys.stderr, flush=True)
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, cfg, cpu_keys, use_j, reads, roff):
-    """The oracle port on this box's host cores, on a bounded sample of the same reads (rank 0, N=1 only)."""
+def random_sector_peaks(ctx):
+    """Random-32-byte-sector read peaks of this GPU, measured now (talc_bench_random_sectors, 4 GiB buffer): the
+    independent-load peak bounds the coverage kernel's probes, the dependent-chain figure the walk's."""
+    try:
+        ind, _ = ctx.bench_random_sectors(4 << 30, dependent=False, warps_per_sm=64)
+        dep, ns = ctx.bench_random_sectors(4 << 30, dependent=True, warps_per_sm=64)
+        return {"peak_random": ind, "peak_random_unit": "GB/s of uniformly random 32 B sectors over 4 GiB, 8 loads in flight per thread, 64 warps/SM",
+                "peak_random_dependent": dep, "dependent_hop_ns": ns}
+    except Exception as e:  # noqa: BLE001
+        return {"peak_random": None, "peak_random_error": str(e)}
+
+
+def cpu_baseline(args, cfg, cpu_keys, use_j, reads, roff, gpu):
+    """The oracle port on this box's host cores, on a bounded sample of the same reads (rank 0, N=1 only), and the
+    byte-for-byte comparison of its output with what the GPU produced for those very reads."""
     import numpy as np
     from oracle import pyoracle as po
     keys, counts, jk, jc = cpu_keys
@@ -350,13 +407,25 @@ def cpu_baseline(args, cfg, cpu_keys, use_j, reads, roff):
     ot = po.OracleTable(po.make_params(k=cfg.k), ordered=False)
     ot.build_packed(keys.cpu().numpy().astype(np.uint64), counts.cpu().numpy(),
                     jk.cpu().numpy().astype(np.uint64) if use_j else None, jc.cpu().numpy() if use_j else None)
-    n = args.cpu_sample_reads
+    n = min(args.cpu_sample_reads, args.batch_reads)
     sub = reads[: int(roff[n])].cpu().numpy()
     so = roff[: n + 1].cpu().numpy().astype(np.uint64)
-    _, _, _, _, secs = ot.correct(sub, so, threads=threads)
-    return {"value": int(so[-1]) / 1e6 / secs, "unit": "Mbp/s", "cores": threads, "kind": "port",
+    o_out, o_off, o_st, _, secs = ot.correct(sub, so, threads=threads)
+    g_out, g_off, g_st = gpu
+    mismatch = int((g_st[:n] != o_st[:n]).sum())
+    if not np.array_equal(g_off[: n + 1], o_off[: n + 1]) or not np.array_equal(g_out[: int(o_off[n])], o_out[: int(o_off[n])]):
+        for r in range(n):
+            a = g_out[int(g_off[r]):int(g_off[r + 1])]
+            b = o_out[int(o_off[r]):int(o_off[r + 1])]
+            if len(a) != len(b) or not np.array_equal(a, b):
+                mismatch += 1
+    base = {"value": int(so[-1]) / 1e6 / secs, "unit": "Mbp/s", "cores": threads, "kind": "port",
             "sample": "first %d reads of the step-0 batch (%.2f Mbp), oracle restatement with a hashed table, %.1f s" % (
                 n, int(so[-1]) / 1e6, secs)}
+    parity = {"reads": n, "mismatch": mismatch,
+              "what": "corrected bytes, offsets and status of the GPU for the first %d reads of the step-0 batch (full-size "
+                      "table, full batch in flight) against the oracle" % n}
+    return base, parity
 
 
 def main():
