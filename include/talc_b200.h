@@ -83,6 +83,7 @@ enum {
   TALC_ERR_IO = -3,
   TALC_ERR_NO_TABLE = -4,
   TALC_ERR_CAPACITY = -5,   /* an output buffer supplied by the caller is too small */
+  TALC_ERR_NCCL = -8,       /* libnccl.so.2 could not be loaded, or an NCCL call failed */
   TALC_ERR_STALE = -7,      /* a table cache made for other inputs / parameters: rebuild from the dump */
   TALC_ERR_SCRATCH = -6     /* reserved (a read that exhausts the second-tier arena is data: TALC_READ_RESOURCE) */
 };
@@ -118,6 +119,17 @@ int talc_table_export_device(talc_ctx* ctx, void* dst_device, uint64_t bytes);
 int talc_table_import_device(talc_ctx* ctx, const void* src_device, uint64_t capacity_slots, uint64_t n_entries);
 /* single-process replication: copy src's sealed table to dst's device (peer copy over NVLink)    */
 int talc_table_copy(talc_ctx* dst, talc_ctx* src);
+/* The collective of the path, owned by the library: ONE ncclBroadcast of the slot array after the build.
+ * NCCL is bound at run time (dlopen libnccl.so.2 -- inside torchrun the copy torch loaded, else the system one).
+ *   talc_table_replicate   one process, n contexts on n devices: ctxs[0] holds the table, the others receive it
+ *                          (ncclCommInitAll + one grouped broadcast; peer copies if NCCL is absent: *used_nccl = 0)
+ *   talc_nccl_unique_id /  one process per GPU: rank 0 makes the id, hands its 128 bytes to the other ranks by any
+ *   talc_table_broadcast   means, every rank calls talc_table_broadcast(ctx, id, rank, world, root): geometry, then
+ *                          the slot array in one broadcast; receivers allocate, receive and seal                   */
+int talc_nccl_available(void);
+int talc_table_replicate(talc_ctx** ctxs, int n, double* broadcast_ms, int* used_nccl);
+int talc_nccl_unique_id(uint8_t id[128]);
+int talc_table_broadcast(talc_ctx* ctx, const uint8_t id[128], int rank, int world, int root, double* broadcast_ms);
 /* binary cache of the built table (at 30 M+ lines the text parse of buildCDBG,
  * Jellyfish.cpp:251-269, dominates start-up once correction is fast).  save writes the sealed slot array with a
  * small header (magic, K, MIN_COUNT, capacity, entries, provenance); load checks K and MIN_COUNT against the context,
@@ -147,6 +159,26 @@ int talc_correct_batch_device(talc_ctx* ctx, const uint8_t* d_bases, const uint6
 /* Per-read coverage vectors only (Read::reCoverage): counts[sum(max(0,len-K+1))], host buffers.   */
 int talc_coverage_batch(talc_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
                         uint32_t* counts, uint64_t counts_capacity);
+
+/* ---- streamed correction (replaces loadSeqData / outputSeqData holding every read: main.cpp:219,310, io.cpp:26-75) ----
+ * Batches of reads pass through one context with the host-to-device copy of batch i+1, the kernels of batch i, the
+ * device-to-host copy of batch i-1 and the caller's own work (FASTA formatting) overlapped: a ring of four slots with
+ * pinned staging, two copy streams and one worker thread inside the library.  Host and device memory are bounded by
+ * the batch size whatever the number of reads; results come back in submission order.
+ *   submit  copies the caller's buffers (free again on return); blocks only while all four slots are busy
+ *   next    blocks until the oldest unfetched batch is complete; the returned pointers (pinned host memory owned by
+ *           the stream) stay valid until the following next / close.  read_stats: per read {span of the final solid
+ *           regions in k-mers, number of regions} -- the columns of outputBasicReadStats (Read.cpp:418-433) that need
+ *           the kernel -- when the stream was opened with want_read_stats, else NULL.
+ * One caller thread per stream; while a stream is open its context must not be used for other correction calls.  */
+typedef struct talc_stream talc_stream;
+int talc_stream_open(talc_ctx* ctx, int want_read_stats, talc_stream** out);
+int talc_stream_submit(talc_stream* s, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads);
+int talc_stream_next(talc_stream* s, const uint8_t** out, const uint64_t** out_offsets, const uint8_t** status,
+                     uint32_t* n_reads, const uint32_t** read_stats, talc_counters* counters);
+uint64_t talc_stream_pending(talc_stream* s);   /* batches submitted and not yet fetched */
+const char* talc_stream_last_error(talc_stream* s);
+void talc_stream_close(talc_stream* s);
 
 /* ---- roofline microbenchmark ("the random-32 B-sector peak must be measured ... and reported") --------
  * Uniformly random 256-bit read-only loads over a buffer of `buffer_bytes` (rounded down to a power of two; use

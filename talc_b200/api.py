@@ -72,6 +72,18 @@ def lib():
         L.talc_correct_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint64, vp, vp,
                                                 C.POINTER(TalcCounters)]
         L.talc_coverage_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint64]
+        L.talc_table_replicate.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.talc_nccl_unique_id.argtypes = [vp]
+        L.talc_table_broadcast.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.talc_stream_open.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.talc_stream_submit.argtypes = [vp, vp, vp, C.c_uint32]
+        L.talc_stream_next.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(vp),
+                                       C.POINTER(TalcCounters)]
+        L.talc_stream_pending.restype = C.c_uint64
+        L.talc_stream_pending.argtypes = [vp]
+        L.talc_stream_last_error.restype = C.c_char_p
+        L.talc_stream_last_error.argtypes = [vp]
+        L.talc_stream_close.argtypes = [vp]
         L.talc_test_align.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp]
         L.talc_test_sort.argtypes = [vp, vp, C.c_uint32, vp]
         _lib = L
@@ -186,6 +198,12 @@ class Talc:
         self._check(lib().talc_table_import_device(self.h, tensor.data_ptr(), capacity, n_entries),
                     "talc_table_import_device")
 
+    def table_broadcast(self, unique_id: np.ndarray, rank: int, world: int, root: int = 0) -> float:
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        ms = C.c_double(0)
+        self._check(lib().talc_table_broadcast(self.h, _ptr(uid), rank, world, root, C.byref(ms)), "talc_table_broadcast")
+        return ms.value
+
     def lookup(self, keys):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         n = len(keys)
@@ -234,6 +252,9 @@ class Talc:
                     "talc_coverage_batch")
         return counts[:total]
 
+    def stream(self, read_stats: bool = False) -> "TalcStream":
+        return TalcStream(self, read_stats)
+
     # ---- device self-tests
     def test_align(self, op: int, a_list, b_list, aux: int = 0, aux2: int = 0) -> np.ndarray:
         def cat(lst):
@@ -255,3 +276,76 @@ class Talc:
         perm = np.zeros(len(keys), dtype=np.uint32)
         self._check(lib().talc_test_sort(self.h, _ptr(keys), len(keys), _ptr(perm)), "talc_test_sort")
         return perm
+
+
+def table_copy(dst: Talc, src: Talc) -> None:
+    dst._check(lib().talc_table_copy(dst.h, src.h), "talc_table_copy")
+
+
+def table_replicate(ctxs) -> float:
+    """ctxs[0] holds the table; one NCCL broadcast issued by the library fills the others.  Returns its device ms."""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    ms, used = C.c_double(0), C.c_int(0)
+    ctxs[0]._check(lib().talc_table_replicate(arr, len(ctxs), C.byref(ms), C.byref(used)), "talc_table_replicate")
+    return ms.value if used.value else -1.0
+
+
+def nccl_unique_id() -> np.ndarray:
+    buf = np.zeros(128, dtype=np.uint8)
+    rc = lib().talc_nccl_unique_id(_ptr(buf))
+    if rc != 0:
+        raise TalcError("talc_nccl_unique_id failed (%d): libnccl.so.2 not loadable" % rc)
+    return buf
+
+
+class TalcStream:
+    """talc_stream_*: batches in, corrected batches out in submission order, copies and kernels overlapped."""
+
+    def __init__(self, ctx: Talc, read_stats: bool = False):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        ctx._check(lib().talc_stream_open(ctx.h, 1 if read_stats else 0, C.byref(self.h)), "talc_stream_open")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise TalcError("%s failed (%d): %s" % (what, rc, lib().talc_stream_last_error(self.h).decode()))
+
+    def submit(self, reads: np.ndarray, offsets: np.ndarray):
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(lib().talc_stream_submit(self.h, _ptr(reads), _ptr(offsets), len(offsets) - 1), "talc_stream_submit")
+
+    def pending(self) -> int:
+        return int(lib().talc_stream_pending(self.h))
+
+    def next(self, copy: bool = True):
+        """(out, out_offsets, status, read_stats or None, counters) of the oldest batch; views into the stream's pinned
+        buffers unless copy=True (they are recycled by the following call)."""
+        po, pf, ps, pt = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_uint32(0)
+        ctr = TalcCounters()
+        self._check(lib().talc_stream_next(self.h, C.byref(po), C.byref(pf), C.byref(ps), C.byref(n), C.byref(pt),
+                                           C.byref(ctr)), "talc_stream_next")
+        nn = n.value
+        off = np.ctypeslib.as_array(C.cast(pf, C.POINTER(C.c_uint64)), shape=(nn + 1,))
+        total = int(off[nn])
+        out = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint8)), shape=(max(total, 1),))[:total]
+        st = np.ctypeslib.as_array(C.cast(ps, C.POINTER(C.c_uint8)), shape=(max(nn, 1),))[:nn]
+        stats = None
+        if pt.value:
+            stats = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_uint32)), shape=(max(nn, 1), 2))[:nn]
+        if copy:
+            out, off, st = out.copy(), off.copy(), st.copy()
+            stats = stats.copy() if stats is not None else None
+        return out, off, st, stats, ctr.as_dict()
+
+    def close(self):
+        if self.h:
+            lib().talc_stream_close(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,239 @@
+// stream.hpp -- batches of reads streamed through one context with copies, kernels and the caller's own work
+// overlapped (replaces the load-everything / write-everything shape of main.cpp:219,310).
+//
+//   caller thread        talc_stream_submit(i+1): copy into pinned staging, async H2D on the copy-in stream
+//   worker thread        batch i: coverage + correction kernels on the context's stream, then async D2H on the
+//                        copy-out stream
+//   caller thread        talc_stream_next(i-1): pinned result buffers, formatted / written by the caller
+//
+// A ring of kSlots slots bounds host and device memory whatever the number of reads; results come back in
+// submission order.  Included at the end of talc_b200.cu (same translation unit as the context).
+#pragma once
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct StreamSlot {
+  PinBuf hBases, hOffs, hOut, hOutOffs, hStatus, hStats;
+  DevBuf dBases, dOffs, dOut, dOutOffs, dStatus, dStats;
+  cudaEvent_t h2dDone = nullptr, d2hDone = nullptr;
+  u32 n = 0;
+  u64 totalBases = 0;
+  talc_counters ctr;
+  int rc = 0;
+  std::string err;
+  int state = 0;  // 0 free, 1 submitted, 2 done (D2H in flight or complete), 3 held by the caller
+};
+
+struct talc_stream {
+  static const int kSlots = 4;
+  talc_ctx* c = nullptr;
+  bool wantStats = false;
+  StreamSlot slot[kSlots];
+  cudaStream_t copyIn = nullptr, copyOut = nullptr;
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv;
+  u64 seqSubmit = 0, seqRun = 0, seqFetch = 0;
+  bool closing = false;
+  std::string err;
+};
+
+static void stream_worker(talc_stream* s) {
+  talc_ctx* c = s->c;
+  cudaSetDevice(c->device);
+  for (;;) {
+    StreamSlot* sl = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(s->mu);
+      s->cv.wait(lk, [&] { return s->closing || s->slot[s->seqRun % talc_stream::kSlots].state == 1; });
+      sl = &s->slot[s->seqRun % talc_stream::kSlots];
+      if (sl->state != 1) return;  // closing and nothing left to run
+    }
+    int rc = TALC_OK;
+    cudaError_t e = cudaStreamWaitEvent(c->stream, sl->h2dDone, 0);
+    if (e != cudaSuccess) rc = TALC_ERR_CUDA;
+    if (rc == TALC_OK)
+      rc = correct_batch_device_impl(c, (const u8*)sl->dBases.p, (const u64*)sl->dOffs.p, sl->n, sl->totalBases, (u8*)sl->dOut.p,
+                                     sl->dOut.cap, (u64*)sl->dOutOffs.p, (u8*)sl->dStatus.p, &sl->ctr,
+                                     s->wantStats ? (u32*)sl->dStats.p : nullptr);
+    if (rc == TALC_OK) {
+      // the compute stream is idle here (the call above ends with a synchronize): results leave on the copy-out
+      // stream while the next batch computes
+      const u64 totalOut = sl->n ? sl->ctr.bases_out : 0;
+      bool ok = sl->hOut.reserve(totalOut + 64) == cudaSuccess;
+      ok = ok && cudaMemcpyAsync(sl->hOutOffs.p, sl->dOutOffs.p, (size_t)(sl->n + 1) * 8, cudaMemcpyDeviceToHost, s->copyOut) == cudaSuccess;
+      if (ok && sl->n) {
+        ok = cudaMemcpyAsync(sl->hStatus.p, sl->dStatus.p, sl->n, cudaMemcpyDeviceToHost, s->copyOut) == cudaSuccess;
+        if (ok && totalOut) ok = cudaMemcpyAsync(sl->hOut.p, sl->dOut.p, totalOut, cudaMemcpyDeviceToHost, s->copyOut) == cudaSuccess;
+        if (ok && s->wantStats)
+          ok = cudaMemcpyAsync(sl->hStats.p, sl->dStats.p, (size_t)sl->n * 8, cudaMemcpyDeviceToHost, s->copyOut) == cudaSuccess;
+      }
+      ok = ok && cudaEventRecord(sl->d2hDone, s->copyOut) == cudaSuccess;
+      if (!ok) { rc = TALC_ERR_CUDA; sl->err = "device-to-host copy of a batch failed"; }
+    } else {
+      sl->err = c->err;
+    }
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      sl->rc = rc;
+      sl->state = 2;
+      s->seqRun++;
+    }
+    s->cv.notify_all();
+  }
+}
+
+extern "C" {
+
+int talc_stream_open(talc_ctx* c, int want_read_stats, talc_stream** out) {
+  if (!c || !out) return TALC_ERR_ARG;
+  *out = nullptr;
+  if (!c->tableReady) { c->err = "no k-mer table loaded"; return TALC_ERR_NO_TABLE; }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  talc_stream* s = new talc_stream;
+  s->c = c;
+  s->wantStats = want_read_stats != 0;
+  bool ok = cudaStreamCreateWithFlags(&s->copyIn, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&s->copyOut, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto& sl : s->slot)
+    ok = ok && cudaEventCreateWithFlags(&sl.h2dDone, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&sl.d2hDone, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    c->err = "talc_stream_open: cannot create CUDA streams / events";
+    delete s;
+    return TALC_ERR_CUDA;
+  }
+  s->worker = std::thread(stream_worker, s);
+  *out = s;
+  return TALC_OK;
+}
+
+// Blocks only while all slots are busy (back-pressure).  The caller's buffers are free again on return.
+int talc_stream_submit(talc_stream* s, const uint8_t* bases, const uint64_t* offsets, uint32_t n) {
+  if (!s || !offsets || (n && !bases) || offsets[0] != 0) return TALC_ERR_ARG;
+  talc_ctx* c = s->c;
+  StreamSlot* sl = &s->slot[s->seqSubmit % talc_stream::kSlots];
+  {
+    std::unique_lock<std::mutex> lk(s->mu);
+    s->cv.wait(lk, [&] { return sl->state == 0; });
+  }
+  if (cudaSetDevice(c->device) != cudaSuccess) { s->err = "cudaSetDevice failed"; return TALC_ERR_CUDA; }
+  const u64 total = offsets[n];
+  const u64 outCap = 2 * total + (u64)n * 64 + 4096;
+  bool ok = sl->hBases.reserve(total + 64) == cudaSuccess && sl->hOffs.reserve((size_t)(n + 1) * 8) == cudaSuccess &&
+            sl->hOutOffs.reserve((size_t)(n + 1) * 8) == cudaSuccess && sl->hStatus.reserve(n + 1) == cudaSuccess &&
+            sl->dBases.reserve(total + 64) == cudaSuccess && sl->dOffs.reserve((size_t)(n + 1) * 8) == cudaSuccess &&
+            sl->dOut.reserve(outCap) == cudaSuccess && sl->dOutOffs.reserve((size_t)(n + 1) * 8) == cudaSuccess &&
+            sl->dStatus.reserve(n + 1) == cudaSuccess;
+  if (ok && s->wantStats) ok = sl->hStats.reserve((size_t)n * 8 + 8) == cudaSuccess && sl->dStats.reserve((size_t)n * 8 + 8) == cudaSuccess;
+  if (!ok) { s->err = "talc_stream_submit: out of pinned host or device memory"; return TALC_ERR_CUDA; }
+  memcpy(sl->hBases.p, bases, total);
+  memcpy(sl->hOffs.p, offsets, (size_t)(n + 1) * 8);
+  ok = (total == 0 || cudaMemcpyAsync(sl->dBases.p, sl->hBases.p, total, cudaMemcpyHostToDevice, s->copyIn) == cudaSuccess) &&
+       cudaMemcpyAsync(sl->dOffs.p, sl->hOffs.p, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s->copyIn) == cudaSuccess &&
+       cudaEventRecord(sl->h2dDone, s->copyIn) == cudaSuccess;
+  if (!ok) { s->err = "talc_stream_submit: host-to-device copy failed"; return TALC_ERR_CUDA; }
+  sl->n = n;
+  sl->totalBases = total;
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    sl->state = 1;
+    s->seqSubmit++;
+  }
+  s->cv.notify_all();
+  return TALC_OK;
+}
+
+uint64_t talc_stream_pending(talc_stream* s) {
+  if (!s) return 0;
+  std::lock_guard<std::mutex> lk(s->mu);
+  return s->seqSubmit - s->seqFetch;
+}
+
+// Result of the oldest batch not yet fetched; blocks until it is complete.  The pointers stay valid until the next
+// call to talc_stream_next / talc_stream_close.  read_stats (may be NULL) receives a pointer to n x {solid span,
+// regions} when the stream was opened with want_read_stats.
+int talc_stream_next(talc_stream* s, const uint8_t** out, const uint64_t** out_offsets, const uint8_t** status, uint32_t* n,
+                     const uint32_t** read_stats, talc_counters* counters) {
+  if (!s) return TALC_ERR_ARG;
+  StreamSlot* sl;
+  {
+    std::unique_lock<std::mutex> lk(s->mu);
+    if (s->seqFetch > 0) {  // release the slot handed out by the previous call
+      StreamSlot* prev = &s->slot[(s->seqFetch - 1) % talc_stream::kSlots];
+      if (prev->state == 3) prev->state = 0;
+    }
+    if (s->seqFetch == s->seqSubmit) {
+      s->cv.notify_all();
+      s->err = "talc_stream_next: nothing submitted";
+      return TALC_ERR_ARG;
+    }
+    sl = &s->slot[s->seqFetch % talc_stream::kSlots];
+    s->cv.notify_all();
+    s->cv.wait(lk, [&] { return sl->state == 2; });
+    sl->state = 3;
+    s->seqFetch++;
+  }
+  if (sl->rc != TALC_OK) {
+    s->err = sl->err;
+    return sl->rc;
+  }
+  cudaSetDevice(s->c->device);
+  if (cudaEventSynchronize(sl->d2hDone) != cudaSuccess) { s->err = "talc_stream_next: copy-out failed"; return TALC_ERR_CUDA; }
+  if (out) *out = (const uint8_t*)sl->hOut.p;
+  if (out_offsets) *out_offsets = (const uint64_t*)sl->hOutOffs.p;
+  if (status) *status = (const uint8_t*)sl->hStatus.p;
+  if (n) *n = sl->n;
+  if (read_stats) *read_stats = s->wantStats ? (const uint32_t*)sl->hStats.p : nullptr;
+  if (counters) *counters = sl->ctr;
+  return TALC_OK;
+}
+
+const char* talc_stream_last_error(talc_stream* s) { return s ? s->err.c_str() : ""; }
+
+void talc_stream_close(talc_stream* s) {
+  if (!s) return;
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->closing = true;
+  }
+  s->cv.notify_all();
+  if (s->worker.joinable()) s->worker.join();
+  cudaSetDevice(s->c->device);
+  cudaStreamSynchronize(s->copyIn);
+  cudaStreamSynchronize(s->copyOut);
+  for (auto& sl : s->slot) {
+    PinBuf* hb[] = {&sl.hBases, &sl.hOffs, &sl.hOut, &sl.hOutOffs, &sl.hStatus, &sl.hStats};
+    for (PinBuf* b : hb) b->release();
+    DevBuf* db[] = {&sl.dBases, &sl.dOffs, &sl.dOut, &sl.dOutOffs, &sl.dStatus, &sl.dStats};
+    for (DevBuf* b : db) b->release();
+    if (sl.h2dDone) cudaEventDestroy(sl.h2dDone);
+    if (sl.d2hDone) cudaEventDestroy(sl.d2hDone);
+  }
+  cudaStreamDestroy(s->copyIn);
+  cudaStreamDestroy(s->copyOut);
+  delete s;
+}
+
+}  // extern "C"

@@ -290,6 +290,7 @@ struct CorrectArgs {
   u32* nOverflow;
   u32* outFull;
   u32* readKcycles;  // optional: per-read elapsed SM cycles / 1024 (tuning aid)
+  u32* readStats;    // optional: per read {span of the final solid regions in k-mers, number of regions} (Read.cpp:418-433)
   CtxView cright, cleft;  // successor tables
   u32 wide;      // worst-case sizing of the X-drop anti-diagonals (align.cuh)
   u32 lastTier;  // no larger arena follows: a read that overflows passes through uncorrected (kReadResource)
@@ -345,6 +346,16 @@ __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) correct_kernel(CorrectAr
       if (lane == 0) mine.reads_overflow += 1;
     }
     if (A.readKcycles && lane == 0) A.readKcycles[r] = (u32)((clock64() - t0) >> 10);
+    if (A.readStats && lane == 0 && st != kReadOverflow) {
+      // outputBasicReadStats (Read.cpp:418-433) reads m_InKmersPositions as correct2 / defineStructure2 left them
+      u32 span = 0, nr = 0;
+      if (st == kReadOk || st == kReadNoStructure || st == kReadResource) {
+        nr = cx.nregs;
+        for (u32 i = 0; i < nr; ++i) span += cx.regs[i].end - cx.regs[i].start + 1;
+      }
+      A.readStats[2 * r] = span;
+      A.readStats[2 * r + 1] = nr;
+    }
     if (st == kReadOverflow) {
       if (lane == 0) {
         A.status[r] = st;
@@ -1100,9 +1111,17 @@ static int prepare_batch(talc_ctx* c, const u8* dBases, const u64* dOffs, u32 n,
   return TALC_OK;
 }
 
+static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const uint64_t* dOffs, uint32_t n, uint64_t totalBases,
+                                     uint8_t* dOut, uint64_t outCapacity, uint64_t* dOutOffs, uint8_t* dStatus,
+                                     talc_counters* counters, u32* dReadStats);
 int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t* dOffs, uint32_t n, uint64_t totalBases,
                               uint8_t* dOut, uint64_t outCapacity, uint64_t* dOutOffs, uint8_t* dStatus,
                               talc_counters* counters) {
+  return correct_batch_device_impl(c, dBases, dOffs, n, totalBases, dOut, outCapacity, dOutOffs, dStatus, counters, nullptr);
+}
+static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const uint64_t* dOffs, uint32_t n, uint64_t totalBases,
+                                     uint8_t* dOut, uint64_t outCapacity, uint64_t* dOutOffs, uint8_t* dStatus,
+                                     talc_counters* counters, u32* dReadStats) {
   if (!c) return TALC_ERR_ARG;
   if (!c->tableReady) { c->err = "no k-mer table loaded"; return TALC_ERR_NO_TABLE; }
   CUDA_TRY(c, cudaSetDevice(c->device));
@@ -1168,6 +1187,7 @@ int talc_correct_batch_device(talc_ctx* c, const uint8_t* dBases, const uint64_t
   A.nOverflow = dNOver;
   A.outFull = dOutFull;
   A.readKcycles = nullptr;
+  A.readStats = dReadStats;
   DevBuf dbgCycles;
   const bool dbg = getenv("TALC_DEBUG_CYCLES") != nullptr;
   if (dbg) {
@@ -1410,3 +1430,6 @@ int talc_test_sort(talc_ctx* c, const int64_t* keys, uint32_t n, uint32_t* perm)
 }
 
 }  // extern "C"
+
+#include "stream.hpp"
+#include "replicate.hpp"
