@@ -56,6 +56,7 @@ def lib():
         L.orc_correct_reads.argtypes = [C.c_void_p, C.POINTER(OrcParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
                                         C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64,
                                         C.POINTER(C.c_double)]
+        L.orc_correct_reads2.argtypes = L.orc_correct_reads.argtypes + [C.c_void_p]
         L.orc_nw.argtypes = [C.c_char_p, C.c_char_p]
         L.orc_lcs.argtypes = [C.c_char_p, C.c_char_p]
         L.orc_overlap.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
@@ -137,6 +138,22 @@ class OracleTable:
         if rc != 0:
             raise RuntimeError("oracle output buffer too small")
         return out[: int(ooff[-1])], ooff, status[:n], json.loads(cj.value.decode()), secs.value
+
+    def read_stats(self, reads: np.ndarray, offsets: np.ndarray, threads: int = 1) -> np.ndarray:
+        """[n, 2] {span of the solid regions, number of regions} per read after correction: the kernel-side columns of
+        the per-read statistics row (Read.cpp:418-433)."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        cap = int(offsets[-1]) * 4 + 4096 * n + 4096
+        out = np.zeros(cap, dtype=np.uint8)
+        ooff = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.uint8)
+        stats = np.zeros((max(n, 1), 2), dtype=np.uint32)
+        secs = C.c_double(0)
+        lib().orc_correct_reads2(self.h, C.byref(self.p), _ptr(reads), _ptr(offsets), n, threads, _ptr(out), cap, _ptr(ooff),
+                                 _ptr(status), None, 0, C.byref(secs), _ptr(stats))
+        return stats[:n]
 
     def stages(self, seq: bytes, max_regions: int = 4096):
         n = max(1, len(seq))

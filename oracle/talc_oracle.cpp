@@ -1517,7 +1517,13 @@ ReadResult correct_read(const Seq& raw, const Table& T, const Params& p, Counter
     len += (unsigned)lastSolid.size();
     checok &= (len == raw.size());
   }
+  auto fill_stats = [&]() {  // Read.cpp:421-424
+    res.stat_regions = (unsigned)regs.size();
+    res.stat_span = 0;
+    for (auto& r : regs) res.stat_span += r.end - r.start + 1;
+  };
   if (!checok) {
+    fill_stats();
     res.status = READ_NO_STRUCTURE;
     C.reads_nostruct++;
     C.bases_out += raw.size();
@@ -1582,6 +1588,7 @@ ReadResult correct_read(const Seq& raw, const Table& T, const Params& p, Counter
   corr += tail;
   res.corrected = corr;
   res.status = READ_OK;
+  fill_stats();
   C.reads_corrected++;
   C.bases_out += corr.size();
   return res;

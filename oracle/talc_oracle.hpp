@@ -142,6 +142,9 @@ enum ReadStatus { READ_OK = 0, READ_NO_SOLID = 1, READ_NO_STRUCTURE = 2, READ_SH
 struct ReadResult {
   ReadStatus status = READ_OK;
   Seq corrected;  // == raw sequence unless status == READ_OK
+  // what outputBasicReadStats (Read.cpp:418-433; call disabled at main.cpp:305) would print for this read:
+  // span and number of m_InKmersPositions as defineStructure2 / correct2 left them
+  unsigned stat_span = 0, stat_regions = 0;
 };
 // optional stage dump for differential debugging of the CUDA path
 struct StageDump {

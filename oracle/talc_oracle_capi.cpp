@@ -88,9 +88,19 @@ uint64_t orc_coverage(void* t, uint32_t K, const char* seq, uint64_t len, uint32
 
 // Batch correction.  bases: concatenated ASCII reads; offsets[n_reads+1].  out must hold out_capacity
 // bytes; out_offsets[n_reads+1].  Returns 0, or -1 if out_capacity is too small.
+int orc_correct_reads2(void* t, const orc_params* q, const char* bases, const uint64_t* offsets, uint32_t n_reads,
+                       int threads, char* out, uint64_t out_capacity, uint64_t* out_offsets, uint8_t* status,
+                       char* counters_json, uint64_t counters_cap, double* seconds, uint32_t* read_stats);
 int orc_correct_reads(void* t, const orc_params* q, const char* bases, const uint64_t* offsets, uint32_t n_reads,
                       int threads, char* out, uint64_t out_capacity, uint64_t* out_offsets, uint8_t* status,
                       char* counters_json, uint64_t counters_cap, double* seconds) {
+  return orc_correct_reads2(t, q, bases, offsets, n_reads, threads, out, out_capacity, out_offsets, status, counters_json,
+                            counters_cap, seconds, nullptr);
+}
+// read_stats (may be null): per read {span of m_InKmersPositions, their number} as Read.cpp:418-433 would print them
+int orc_correct_reads2(void* t, const orc_params* q, const char* bases, const uint64_t* offsets, uint32_t n_reads,
+                       int threads, char* out, uint64_t out_capacity, uint64_t* out_offsets, uint8_t* status,
+                       char* counters_json, uint64_t counters_cap, double* seconds, uint32_t* read_stats) {
   Params p = to_params(q);
   Table* T = (Table*)t;
   if (threads < 1) threads = 1;
@@ -103,6 +113,7 @@ int orc_correct_reads(void* t, const orc_params* q, const char* bases, const uin
     Seq s = to_dna5(std::string(bases + offsets[r], offsets[r + 1] - offsets[r]));
     ReadResult rr = correct_read(s, *T, p, per[omp_get_thread_num()]);
     status[r] = (uint8_t)rr.status;
+    if (read_stats) { read_stats[2 * r] = rr.stat_span; read_stats[2 * r + 1] = rr.stat_regions; }
     results[r].swap(rr.corrected);
   }
   auto t1 = std::chrono::steady_clock::now();

@@ -7,15 +7,26 @@
 //   <prefix>.fa, every read in input order, 70 columns (main.cpp:310, io.cpp:50-75)
 // Exit codes follow main.cpp: 1 on a parse error (:199) or an empty table (:320), 0 otherwise -- including
 // unreadable input (:323).  The work is done on the GPU through the C ABI; there is no CPU path.
-// -t is accepted for compatibility and used for host-side formatting only.  Extension: --gpus N shards
-// the reads over N devices of the box (table replicated device to device).
+// -t is accepted for compatibility and used for host-side FASTA formatting only.
+//
+// Unlike the reference (loadSeqData holds every read, outputSeqData writes them all at the end: main.cpp:219,310) the
+// reads are STREAMED: a reader parses FASTA / FASTQ incrementally into batches (--batch-reads, --batch-bases), each
+// batch goes through a talc_stream (copies, kernels and formatting overlapped) and a writer appends the corrected
+// records in input order.  Host memory is bounded by the batches in flight, whatever the size of the input.
+// Extensions: --gpus N deals the batches round-robin over N devices (table replicated with one NCCL broadcast issued
+// by the library), --tableCache <file>, --readStats (the per-read rows of Read.cpp:418-433 the reference left disabled
+// at main.cpp:305).
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <deque>
 #include <fstream>
 #include <iostream>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -24,8 +35,9 @@
 
 struct Cli {
   std::string reads, dump, junctions, out = "out", queryMode = "memory", tableCache;
-  bool useJunctions = false, reverse = false;
+  bool useJunctions = false, reverse = false, readStats = false;
   int threads = 1, gpus = 1;
+  long batchReads = 131072, batchBases = 256l << 20;
   talc_params p;
   bool haveK = false, haveSR = false;
 };
@@ -69,6 +81,9 @@ static int parse(int argc, const char** argv, Cli& c) {
     else if (a == "-t" || a == "--num_threads") { if (!val(v) || !to_int(v, n) || n < 1) return 1; c.threads = (int)n; }
     else if (a == "-DEBUG_MODE" || a == "--DEBUG_MODE") { if (!val(v)) return 1; }
     else if (a == "-rev" || a == "--reverse") { c.reverse = true; }
+    else if (a == "--readStats") { c.readStats = true; }
+    else if (a == "--batch-reads") { if (!val(v) || !to_int(v, n) || n < 1) return 1; c.batchReads = n; }
+    else if (a == "--batch-bases") { if (!val(v) || !to_int(v, n) || n < 1) return 1; c.batchBases = n; }
     else if (a == "--gpus") { if (!val(v) || !to_int(v, n) || n < 1) return 1; c.gpus = (int)n; }
     else if (a == "--cycle-mode") { if (!val(v) || !to_int(v, n)) return 1; c.p.cycle_mode = (int32_t)n; }
     else if (a.size() > 1 && a[0] == '-') return 1;
@@ -107,73 +122,169 @@ static void write_stats_header(const std::string& path) {  // Read.cpp:394-415
        "nbInCorrReg\tCorrHead?\tCorrHeadLen\tCorrTail?\tCorrTailLen\tCorrlength\tnbInKmers2\n";
 }
 
+// ------------------------------------------------------------------------------------------------ streamed input
 // io.cpp:26-48 (SeqAn readRecords): FASTA or FASTQ by the first byte; ids = header without marker;
-// sequence letters must be ACGTN (either case), anything else is a parse error.
-static bool load_reads(const std::string& path, std::vector<std::string>& ids, std::vector<uint8_t>& bases,
-                       std::vector<uint64_t>& offs) {
-  FILE* f = fopen(path.c_str(), "rb");
-  if (!f) { std::cerr << "ERROR: Could not open file " << path << "\n"; return false; }
-  std::string data;
-  char buf[1 << 16];
-  size_t n;
-  while ((n = fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, n);
-  fclose(f);
-  offs.assign(1, 0);
-  size_t p = 0;
-  const size_t N = data.size();
-  auto line = [&](size_t& b, size_t& e) {  // [b,e) without the terminator; false at end of file
-    if (p >= N) return false;
-    b = p;
-    const void* nl = memchr(data.data() + p, '\n', N - p);
-    e = nl ? (size_t)((const char*)nl - data.data()) : N;
-    p = e + 1;
-    while (e > b && data[e - 1] == '\r') --e;
+// sequence letters must be ACGTN (either case), anything else is a parse error.  The file is read in pieces; a
+// batch ends at a record boundary once it holds --batch-reads reads or --batch-bases bases.
+struct Batch {
+  uint64_t seq = 0;
+  std::vector<std::string> ids;
+  std::vector<uint8_t> bases;
+  std::vector<uint64_t> offs{0};
+};
+
+class ReadParser {
+ public:
+  explicit ReadParser(const std::string& path) : f_(fopen(path.c_str(), "rb")) { buf_.resize(8u << 20); }
+  ~ReadParser() { if (f_) fclose(f_); }
+  bool is_open() const { return f_ != nullptr; }
+  // fills `b` with up to maxReads reads / about maxBases bases; returns false on a parse error.  b.ids.empty()
+  // afterwards means the input is exhausted.
+  bool next_batch(Batch& b, size_t maxReads, size_t maxBases) {
+    b.ids.clear();
+    b.bases.clear();
+    b.offs.assign(1, 0);
+    std::string line;
+    if (pendingHeader_) {  // FASTA: the header that ended the previous batch opens this one
+      b.ids.push_back(header_);
+      pendingHeader_ = false;
+      open_ = true;
+    }
+    while (get_line(line)) {
+      if (first_) {
+        if (line.empty()) continue;
+        if (line[0] == '>') fastq_ = false;
+        else if (line[0] == '@') fastq_ = true;
+        else return false;
+        first_ = false;
+      }
+      if (!fastq_) {
+        if (!line.empty() && line[0] == '>') {
+          if (open_) {
+            b.offs.push_back(b.bases.size());
+            if (b.ids.size() >= maxReads || b.bases.size() >= maxBases) {
+              header_.assign(line, 1, std::string::npos);
+              pendingHeader_ = true;
+              open_ = false;
+              return true;
+            }
+          }
+          b.ids.emplace_back(line, 1, std::string::npos);
+          open_ = true;
+        } else if (!push_seq(b, line)) {
+          std::cout << "ERROR: Unexpected character found" << std::endl;
+          return false;
+        }
+      } else {
+        if (line.empty()) continue;
+        if (line[0] != '@') return false;
+        b.ids.emplace_back(line, 1, std::string::npos);
+        std::string seq, x;
+        if (!get_line(seq) || !push_seq(b, seq)) { std::cout << "ERROR: Unexpected character found" << std::endl; return false; }
+        if (!get_line(x) || !get_line(x)) return false;
+        b.offs.push_back(b.bases.size());
+        if (b.ids.size() >= maxReads || b.bases.size() >= maxBases) return true;
+      }
+    }
+    if (!fastq_ && open_) { b.offs.push_back(b.bases.size()); open_ = false; }
     return true;
-  };
-  auto push_seq = [&](size_t b, size_t e) {
-    for (size_t i = b; i < e; ++i) {
-      const char ch = data[i];
+  }
+
+ private:
+  static bool push_seq(Batch& b, const std::string& s) {
+    for (const char ch : s) {
       switch (ch) {
         case 'A': case 'C': case 'G': case 'T': case 'N': case 'a': case 'c': case 'g': case 't': case 'n':
-          bases.push_back((uint8_t)ch);
+          b.bases.push_back((uint8_t)ch);
           break;
         case ' ': case '\t': break;
         default: return false;
       }
     }
     return true;
-  };
-  size_t b, e;
-  bool first = true, fastq = false, open = false;
-  while (line(b, e)) {
-    if (first) {
-      if (e == b) continue;
-      if (data[b] == '>') fastq = false;
-      else if (data[b] == '@') fastq = true;
-      else return false;
-      first = false;
-    }
-    if (!fastq) {
-      if (e > b && data[b] == '>') {
-        if (open) offs.push_back(bases.size());
-        ids.emplace_back(data, b + 1, e - b - 1);
-        open = true;
-      } else if (!push_seq(b, e)) {
-        std::cout << "ERROR: Unexpected character found" << std::endl;
-        return false;
-      }
-    } else {
-      if (e == b) continue;
-      if (data[b] != '@') return false;
-      ids.emplace_back(data, b + 1, e - b - 1);
-      size_t sb, se, xb, xe;
-      if (!line(sb, se) || !push_seq(sb, se)) { std::cout << "ERROR: Unexpected character found" << std::endl; return false; }
-      if (!line(xb, xe) || !line(xb, xe)) return false;
-      offs.push_back(bases.size());
-    }
   }
-  if (!fastq && open) offs.push_back(bases.size());
-  return true;
+  bool get_line(std::string& out) {  // without the terminator ("\n" or "\r\n"); false at end of file
+    out.clear();
+    bool any = false;
+    for (;;) {
+      if (pos_ == len_) {
+        if (eof_) break;
+        len_ = fread(&buf_[0], 1, buf_.size(), f_);
+        pos_ = 0;
+        if (len_ == 0) { eof_ = true; break; }
+      }
+      any = true;
+      const char* p = &buf_[pos_];
+      const void* nl = memchr(p, '\n', len_ - pos_);
+      if (nl) {
+        const size_t n = (size_t)((const char*)nl - p);
+        out.append(p, n);
+        pos_ += n + 1;
+        while (!out.empty() && out.back() == '\r') out.pop_back();
+        return true;
+      }
+      out.append(p, len_ - pos_);
+      pos_ = len_;
+    }
+    while (!out.empty() && out.back() == '\r') out.pop_back();
+    return any;
+  }
+  FILE* f_;
+  std::string buf_, header_;
+  size_t pos_ = 0, len_ = 0;
+  bool eof_ = false, first_ = true, fastq_ = false, open_ = false, pendingHeader_ = false;
+};
+
+// ids of the batches in flight, handed from the reader to the writer in order
+struct IdQueue {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::shared_ptr<Batch>> q;
+  bool done = false;
+  void push(std::shared_ptr<Batch> b) {
+    { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(b)); }
+    cv.notify_all();
+  }
+  void finish() {
+    { std::lock_guard<std::mutex> lk(mu); done = true; }
+    cv.notify_all();
+  }
+  std::shared_ptr<Batch> pop() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return done || !q.empty(); });
+    if (q.empty()) return nullptr;
+    auto b = q.front();
+    q.pop_front();
+    return b;
+  }
+};
+
+// one corrected batch as 70-column FASTA records (io.cpp:50-75), formatted by up to `threads` workers
+static void format_fasta(const Batch& b, const uint8_t* out, const uint64_t* ooffs, int threads, std::vector<std::string>& parts) {
+  const size_t n = b.ids.size();
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n / 2048 + 1));
+  parts.assign(nt, std::string());
+  auto work = [&](int t) {
+    std::string& buf = parts[t];
+    const size_t r0 = n * t / nt, r1 = n * (t + 1) / nt;
+    buf.reserve((size_t)((ooffs[r1] - ooffs[r0]) * 1.02) + (r1 - r0) * 48 + 64);
+    for (size_t r = r0; r < r1; ++r) {
+      const uint8_t* s = out + ooffs[r];
+      const size_t len = ooffs[r + 1] - ooffs[r];
+      buf += '>';
+      buf += b.ids[r];
+      buf += '\n';
+      if (len == 0) buf += '\n';
+      for (size_t j = 0; j < len; j += 70) {
+        buf.append((const char*)s + j, std::min<size_t>(70, len - j));
+        buf += '\n';
+      }
+    }
+  };
+  if (nt == 1) { work(0); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+  for (auto& x : th) x.join();
 }
 
 int main(int argc, const char** argv) {
@@ -184,22 +295,28 @@ int main(int argc, const char** argv) {
   Cli cli;
   const int pr = parse(argc, argv, cli);
   if (pr == 2) {
-    std::cout << "talc <reads> --SRCounts <dump> [--junctions <dump>] -k <K> [-o <prefix>] [-t <N>] [--gpus <N>] [--tableCache <file>]\n";
+    std::cout << "talc <reads> --SRCounts <dump> [--junctions <dump>] -k <K> [-o <prefix>] [-t <N>] [--gpus <N>] [--tableCache <file>]"
+                 " [--batch-reads <N>] [--batch-bases <N>] [--readStats]\n";
     return 0;
   }
   if (pr != 0) { std::cerr << "talc: PARSE_ERROR\n"; return 1; }
   write_config(cli);
   write_stats_header(cli.out + ".stats_basics.txt");
 
-  std::vector<std::string> ids;
-  std::vector<uint8_t> bases;
-  std::vector<uint64_t> offs;
   std::cout << "[TALC]: Attempting to load sequences." << std::endl;
-  if (!load_reads(cli.reads, ids, bases, offs) || offs.size() != ids.size() + 1) {
+  ReadParser parser(cli.reads);
+  if (!parser.is_open()) {
+    std::cerr << "ERROR: Could not open file " << cli.reads << "\n";
     std::cout << "[TALC]: ISSUE WITH INPUT FILES" << std::endl;
     return 0;  // main.cpp:323 falls off main
   }
-  std::cout << "[TALC]: " << ids.size() << " long read(s) loaded" << std::endl;
+  // the first batch is parsed before the table is built: an input that is not FASTA / FASTQ ends the run here, as in
+  // the reference (which loads every read first)
+  auto first = std::make_shared<Batch>();
+  if (!parser.next_batch(*first, (size_t)cli.batchReads, (size_t)cli.batchBases)) {
+    std::cout << "[TALC]: ISSUE WITH INPUT FILES" << std::endl;
+    return 0;
+  }
 
   std::vector<talc_ctx*> ctx(cli.gpus, nullptr);
   for (int g = 0; g < cli.gpus; ++g) {
@@ -228,83 +345,110 @@ int main(int argc, const char** argv) {
     std::cout << "[TALC]: The de Bruijn Graph is empty...Correction aborted." << std::endl;
     return 1;  // main.cpp:320
   }
-  for (int g = 1; g < cli.gpus; ++g) {
-    if (talc_table_copy(ctx[g], ctx[0]) != 0) { std::cerr << "talc: " << talc_last_error(ctx[g]) << "\n"; return 2; }
+  if (cli.gpus > 1) {
+    double ms = 0;
+    int usedNccl = 0;
+    if (talc_table_replicate(ctx.data(), cli.gpus, &ms, &usedNccl) != 0) {
+      std::cerr << "talc: " << talc_last_error(ctx[0]) << "\n";
+      return 2;
+    }
+    if (usedNccl) std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (one NCCL broadcast, " << ms << " ms)." << std::endl;
+    else std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (peer copies; NCCL not found)." << std::endl;
   }
-
-  // shard contiguous blocks of reads, balanced by bases, over the devices
-  const size_t R = ids.size();
-  std::vector<size_t> cut(cli.gpus + 1, R);
-  cut[0] = 0;
-  {
-    const uint64_t total = offs[R];
-    size_t r = 0;
-    for (int g = 1; g < cli.gpus; ++g) {
-      const uint64_t want = total / cli.gpus * g;
-      while (r < R && offs[r] < want) ++r;
-      cut[g] = r;
+  std::vector<talc_stream*> streams(cli.gpus, nullptr);
+  for (int g = 0; g < cli.gpus; ++g) {
+    if (talc_stream_open(ctx[g], cli.readStats ? 1 : 0, &streams[g]) != 0) {
+      std::cerr << "talc: " << talc_last_error(ctx[g]) << "\n";
+      return 2;
     }
   }
-  std::vector<std::vector<uint8_t>> out(cli.gpus), status(cli.gpus);
-  std::vector<std::vector<uint64_t>> ooffs(cli.gpus);
-  std::vector<int> rcs(cli.gpus, 0);
-  std::vector<std::thread> th;
-  for (int g = 0; g < cli.gpus; ++g) {
-    th.emplace_back([&, g]() {
-      const size_t r0 = cut[g], r1 = cut[g + 1];
-      const uint32_t n = (uint32_t)(r1 - r0);
-      std::vector<uint64_t> lo(n + 1);
-      for (uint32_t i = 0; i <= n; ++i) lo[i] = offs[r0 + i] - offs[r0];
-      out[g].resize(2 * lo[n] + 64ull * n + 4096);
-      ooffs[g].assign(n + 1, 0);
-      status[g].assign(n + 1, 0);
-      rcs[g] = talc_correct_batch(ctx[g], bases.data() + offs[r0], lo.data(), n, out[g].data(), out[g].size(), ooffs[g].data(),
-                                  status[g].data(), nullptr);
-    });
-  }
-  for (auto& t : th) t.join();
-  for (int g = 0; g < cli.gpus; ++g) {
-    if (rcs[g] != 0) { std::cerr << "talc: correction failed on device " << g << ": " << talc_last_error(ctx[g]) << "\n"; return 2; }
-  }
 
-  // failed-read log in input order (the reference's order under -t 1), then the FASTA
-  {
-    std::ofstream lg;
-    bool opened = false;
-    for (int g = 0; g < cli.gpus; ++g) {
-      for (size_t r = cut[g]; r < cut[g + 1]; ++r) {
-        const uint8_t st = status[g][r - cut[g]];
-        const char* msg = st == TALC_READ_NO_STRUCTURE ? "Unable to define convenient structure."
-                          : st == TALC_READ_NO_SOLID   ? "No solid kmer could be found." : nullptr;
+  // ---- writer: corrected records in input order into <o>.fa.partial, renamed when the run is complete; the failed-read
+  // log (input order = the reference's order under -t 1) and the optional stats rows are appended as batches arrive
+  const std::string faTmp = cli.out + ".fa.partial";
+  FILE* fo = fopen(faTmp.c_str(), "wb");
+  if (!fo) { std::cerr << "ERROR: Could not open the file " << cli.out << ".fa\n"; return 0; }
+  IdQueue idq;
+  int writerRc = 0;
+  uint64_t nReads = 0, nResource = 0;
+  std::thread writer([&]() {
+    std::ofstream lg, st;
+    std::vector<std::string> parts;
+    while (auto b = idq.pop()) {
+      talc_stream* s = streams[b->seq % cli.gpus];
+      const uint8_t *out = nullptr, *status = nullptr;
+      const uint64_t* ooffs = nullptr;
+      const uint32_t* stats = nullptr;
+      uint32_t n = 0;
+      if (talc_stream_next(s, &out, &ooffs, &status, &n, &stats, nullptr) != 0 || n != b->ids.size()) {
+        std::cerr << "talc: correction failed on device " << (b->seq % cli.gpus) << ": " << talc_stream_last_error(s) << "\n";
+        writerRc = 2;
+        while (idq.pop()) {}  // keep draining so that the reader does not block for ever
+        return;
+      }
+      for (uint32_t r = 0; r < n; ++r) {
+        const uint8_t v = status[r];
+        const char* msg = v == TALC_READ_NO_STRUCTURE ? "Unable to define convenient structure."
+                          : v == TALC_READ_NO_SOLID   ? "No solid kmer could be found." : nullptr;
         if (msg) {
-          if (!opened) { lg.open(cli.out + ".log", std::ios_base::app); opened = true; }
-          lg << "[Read: " << ids[r] << " ]: " << msg << std::endl;
+          if (!lg.is_open()) lg.open(cli.out + ".log", std::ios_base::app);
+          lg << "[Read: " << b->ids[r] << " ]: " << msg << std::endl;
+        }
+        if (v == TALC_READ_RESOURCE) {
+          ++nResource;
+          std::cerr << "talc: read " << b->ids[r] << " outgrew the scratch arena and is passed through uncorrected\n";
+        }
+        if (cli.readStats && v != TALC_READ_SHORT) {  // outputBasicReadStats, Read.cpp:418-433 (only reads longer than K)
+          if (!st.is_open()) st.open(cli.out + ".stats_basics.txt", std::ios_base::app);
+          const uint64_t rawLen = b->offs[r + 1] - b->offs[r];
+          st << "\n" << b->ids[r] << "\t" << rawLen << "\t" << (stats ? stats[2 * r] : 0) << "\t" << (stats ? stats[2 * r + 1] : 0)
+             << "\t" << (v == TALC_READ_OK ? ooffs[r + 1] - ooffs[r] : 0);
         }
       }
+      format_fasta(*b, out, ooffs, cli.threads, parts);
+      for (const auto& p : parts) fwrite(p.data(), 1, p.size(), fo);
+      nReads += n;
     }
-  }
-  FILE* fo = fopen((cli.out + ".fa").c_str(), "wb");
-  if (!fo) { std::cerr << "ERROR: Could not open the file " << cli.out << ".fa\n"; return 0; }
-  std::string buf;
-  for (int g = 0; g < cli.gpus; ++g) {
-    for (size_t r = cut[g]; r < cut[g + 1]; ++r) {
-      const size_t i = r - cut[g];
-      const uint8_t* s = out[g].data() + ooffs[g][i];
-      const size_t len = ooffs[g][i + 1] - ooffs[g][i];
-      buf.clear();
-      buf += '>';
-      buf += ids[r];
-      buf += '\n';
-      if (len == 0) buf += '\n';
-      for (size_t j = 0; j < len; j += 70) {
-        buf.append((const char*)s + j, std::min<size_t>(70, len - j));
-        buf += '\n';
-      }
-      fwrite(buf.data(), 1, buf.size(), fo);
+  });
+
+  // ---- reader / submitter (this thread): batch b goes to device b mod N; submit blocks while that device's ring of
+  // slots is full, which bounds the memory in flight
+  bool inputOk = true;
+  int submitRc = 0;
+  uint64_t seq = 0;
+  for (std::shared_ptr<Batch> b = first; b && !b->ids.empty();) {
+    b->seq = seq;
+    talc_stream* s = streams[seq % cli.gpus];
+    if (b->offs.size() != b->ids.size() + 1) { inputOk = false; break; }
+    idq.push(b);
+    if (talc_stream_submit(s, b->bases.data(), b->offs.data(), (uint32_t)b->ids.size()) != 0) {
+      std::cerr << "talc: " << talc_stream_last_error(s) << "\n";
+      submitRc = 2;
+      break;
     }
+    std::vector<uint8_t>().swap(b->bases);  // the stream holds its own copy; ids and offsets stay for the writer
+    ++seq;
+    if (writerRc) break;
+    auto nb = std::make_shared<Batch>();
+    if (!parser.next_batch(*nb, (size_t)cli.batchReads, (size_t)cli.batchBases)) { inputOk = false; break; }
+    b = nb;
   }
+  idq.finish();
+  writer.join();
   fclose(fo);
+  for (auto* s : streams) talc_stream_close(s);
   for (auto* c : ctx) talc_ctx_destroy(c);
+  if (submitRc || writerRc) { remove(faTmp.c_str()); return 2; }
+  if (!inputOk) {  // the reference would have failed while loading, before writing anything
+    remove(faTmp.c_str());
+    std::cout << "[TALC]: ISSUE WITH INPUT FILES" << std::endl;
+    return 0;
+  }
+  if (rename(faTmp.c_str(), (cli.out + ".fa").c_str()) != 0) {
+    std::cerr << "ERROR: Could not open the file " << cli.out << ".fa\n";
+    return 0;
+  }
+  std::cout << "[TALC]: " << nReads << " long read(s) processed" << std::endl;
   std::cout << "[TALC]: Looks like we are done now." << std::endl;
   return 0;
 }

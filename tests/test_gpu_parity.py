@@ -358,3 +358,103 @@ def test_cli_is_a_drop_in(api, tmp_path):
     b = open(tmp_path / "cpu.config.txt").read().replace("cpu", "X")
     assert a == b
     assert b"junk" in open(tmp_path / "gpu.log", "rb").read()
+
+
+def _write_case_files(tmp_path, g, fastq=False):
+    import torch
+    from talc_b200 import synth
+    k = int(g["c3_k"][0])
+    synth.write_dump(str(tmp_path / "sr.dump"), torch.from_numpy(g["c3_keys"].astype(np.int64)),
+                     torch.from_numpy(g["c3_counts"].astype(np.int64)), k)
+    synth.write_dump(str(tmp_path / "j.dump"), torch.from_numpy(g["c3_jkeys"].astype(np.int64)),
+                     torch.from_numpy(g["c3_jcounts"].astype(np.int64)), k)
+    reads, off = g["c3_reads"], g["c3_off"]
+    with open(tmp_path / "reads.fa", "wb") as f, open(tmp_path / "reads.fq", "wb") as q:
+        for r in range(len(off) - 1):
+            s = reads[int(off[r]):int(off[r + 1])].tobytes()
+            f.write(b">read_%d\n" % r + s + b"\n")
+            q.write(b"@read_%d\n" % r + s + b"\n+\n" + b"I" * len(s) + b"\n")
+            if r == 2:
+                f.write(b">tiny\nACGTACGT\n>junk\n" + b"ACGT" * 60 + b"\n")
+                q.write(b"@tiny\nACGTACGT\n+\nIIIIIIII\n@junk\n" + b"ACGT" * 60 + b"\n+\n" + b"I" * 240 + b"\n")
+    return k
+
+
+def test_cli_streams_batches_fastq_and_stats_rows(api, tmp_path):
+    """Row f2 / f4: the streamed command line gives the same files whether the input goes through in one batch or in
+    many small ones (--batch-reads 7: batch boundaries, the ring of slots, the in-order writer), FASTQ input equals
+    FASTA input, and --readStats appends the per-read rows of Read.cpp:418-433 (checked against the oracle)."""
+    import os
+    import subprocess
+    from oracle import pyoracle as po
+    from talc_b200 import build
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_case.npz"))
+    k = _write_case_files(tmp_path, g)
+    cli = build.build_cli()
+    common = ["--SRCounts", str(tmp_path / "sr.dump"), "--junctions", str(tmp_path / "j.dump"), "-k", str(k)]
+    run = lambda reads, *a: subprocess.call([cli, str(tmp_path / reads)] + common + list(a), cwd=tmp_path, stdout=subprocess.DEVNULL)
+    assert run("reads.fa", "-o", "one") == 0
+    assert run("reads.fa", "-o", "many", "--batch-reads", "7", "-t", "3") == 0
+    assert run("reads.fq", "-o", "fq", "--batch-reads", "5") == 0
+    assert run("reads.fa", "-o", "stats", "--batch-reads", "11", "--readStats") == 0
+    one = open(tmp_path / "one.fa", "rb").read()
+    assert one.count(b">") == len(g["c3_off"]) - 1 + 2
+    for other in ("many", "fq", "stats"):
+        assert open(tmp_path / (other + ".fa"), "rb").read() == one, other
+        assert open(tmp_path / (other + ".log"), "rb").read() == open(tmp_path / "one.log", "rb").read(), other
+    assert not os.path.exists(tmp_path / "one.fa.partial")
+    # stats rows: header, then "\n" id raw_length span regions corrected_length per read longer than K
+    rows = open(tmp_path / "stats.stats_basics.txt").read().split("\n")
+    assert rows[0].startswith("read_name\traw_length") and rows[1] == ""
+    rows = [r.split("\t") for r in rows[2:]]
+    ot = po.OracleTable(po.make_params(k=k)).build_packed(g["c3_keys"], g["c3_counts"].astype(np.int64), g["c3_jkeys"],
+                                                          g["c3_jcounts"].astype(np.int64))
+    st = ot.read_stats(g["c3_reads"], g["c3_off"], threads=2)
+    by_id = {r[0]: r for r in rows}
+    assert "tiny" not in by_id and by_id["junk"][1:] == ["240", "0", "0", "0"]
+    off, ooff = g["c3_off"], g["c3_ooff"]
+    for r in range(len(off) - 1):
+        row = by_id["read_%d" % r]
+        corr = int(ooff[r + 1] - ooff[r]) if g["c3_status"][r] == 0 else 0
+        assert [int(x) for x in row[1:]] == [int(off[r + 1] - off[r]), int(st[r][0]), int(st[r][1]), corr], r
+
+
+def test_no_cpu_fallback_on_the_gpu_box(api):
+    """With the devices hidden the library must refuse to work, not fall back (run in a child process)."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\nfrom talc_b200 import api\n"
+            "try:\n    api.Talc(api.default_params(21))\n    print('CREATED')\n"
+            "except api.TalcError as e:\n    print('REFUSED', e)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True).stdout
+    assert "REFUSED" in out and "no CPU path" in out
+
+
+def test_stream_api_matches_single_calls(api, case_c1):
+    """talc_stream_*: the same reads cut into uneven batches (one of them empty) come back in submission order with
+    the bytes, status and counters of one talc_correct_batch call."""
+    case = case_c1
+    t = _ctx(api, case)
+    out, off, st, ctr = t.correct(case.reads, case.off)
+    _assert_same(case, out, off, st, ctr)
+    n = len(case.off) - 1
+    cuts = [0, 1, 1, 40, 41, 130, n]
+    s = t.stream(read_stats=True)
+    for a, b in zip(cuts, cuts[1:]):
+        sub = case.reads[int(case.off[a]):int(case.off[b])]
+        s.submit(sub, case.off[a:b + 1] - case.off[a])
+    outs, sts, stats, tot = [], [], [], None
+    for a, b in zip(cuts, cuts[1:]):
+        o, f, x, rs, c = s.next()
+        assert len(x) == b - a and len(f) == b - a + 1 and rs.shape == (b - a, 2)
+        outs.append(o)
+        sts.append(x)
+        stats.append(rs)
+        tot = c if tot is None else {k2: tot[k2] + c[k2] for k2 in c}
+    s.close()
+    assert np.array_equal(np.concatenate(outs), out) and np.array_equal(np.concatenate(sts), st)
+    assert {k2: tot[k2] for k2 in SHARED} == {k2: ctr[k2] for k2 in SHARED}
+    ostats = case.otable.read_stats(case.reads, case.off, threads=4)
+    assert np.array_equal(np.concatenate(stats), ostats)
