@@ -103,6 +103,14 @@ int talc_ctx_set_scratch(talc_ctx* ctx, uint32_t tier1_bytes, uint32_t tier2_byt
 /* Jellyfish `dump -c` text (KMER<ws>COUNT per line), optional junction dump (NULL = none).      */
 int talc_table_load_dump(talc_ctx* ctx, const char* dump_path, const char* junction_path, uint64_t* n_lines,
                          uint64_t* n_kept);
+/* load_dump parses the text ON THE GPU (row f1: file -> pinned staging -> HBM, one flag per byte, line offsets by
+ * stream compaction, one thread per line; entries are inserted straight from device arrays).  load_dump_host is the
+ * threaded host parser of round 1, kept for A/B timing; both build the same table bit for bit.                    */
+int talc_table_load_dump_host(talc_ctx* ctx, const char* dump_path, const char* junction_path, uint64_t* n_lines,
+                              uint64_t* n_kept);
+/* Jellyfish `dump -c` text of packed k-mers (KMER<space>COUNT\n, given order): the inverse of the parser, for tests,
+ * benches and for exporting a table.  Host only.                                                                    */
+int talc_dump_write_packed(const char* path, const uint64_t* keys, const int64_t* counts, uint64_t n, uint32_t K);
 /* same, from packed k-mers in dump-line order; counts as the dump gives them (int)               */
 int talc_table_load_packed(talc_ctx* ctx, const uint64_t* keys, const int64_t* counts, uint64_t n,
                            const uint64_t* jkeys, const int64_t* jcounts, uint64_t nj, int use_junctions,

@@ -54,6 +54,8 @@ def lib():
         L.talc_last_error.argtypes = [vp]
         L.talc_ctx_set_scratch.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
         L.talc_table_load_dump.argtypes = [vp, C.c_char_p, C.c_char_p, u64p, u64p]
+        L.talc_table_load_dump_host.argtypes = [vp, C.c_char_p, C.c_char_p, u64p, u64p]
+        L.talc_dump_write_packed.argtypes = [C.c_char_p, vp, vp, C.c_uint64, C.c_uint32]
         L.talc_table_load_packed.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, C.c_int, u64p]
         L.talc_table_info.argtypes = [vp, u64p, u64p, u64p]
         L.talc_table_alloc.argtypes = [vp, C.c_uint64]
@@ -139,6 +141,13 @@ class Talc:
         nl, nk = C.c_uint64(0), C.c_uint64(0)
         self._check(lib().talc_table_load_dump(self.h, dump.encode(), junctions.encode() if junctions else None,
                                                C.byref(nl), C.byref(nk)), "talc_table_load_dump")
+        return nl.value, nk.value
+
+    def load_dump_host(self, dump: str, junctions: Optional[str] = None):
+        """The round-1 host parser, kept for A/B timing against load_dump (GPU parser)."""
+        nl, nk = C.c_uint64(0), C.c_uint64(0)
+        self._check(lib().talc_table_load_dump_host(self.h, dump.encode(), junctions.encode() if junctions else None,
+                                                    C.byref(nl), C.byref(nk)), "talc_table_load_dump_host")
         return nl.value, nk.value
 
     def load_packed(self, keys, counts, jkeys=None, jcounts=None) -> int:
@@ -276,6 +285,15 @@ class Talc:
         perm = np.zeros(len(keys), dtype=np.uint32)
         self._check(lib().talc_test_sort(self.h, _ptr(keys), len(keys), _ptr(perm)), "talc_test_sort")
         return perm
+
+
+def write_dump(path: str, keys, counts, k: int) -> None:
+    """Jellyfish `dump -c` text from packed k-mers (fast C writer: 49 M lines in seconds)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    rc = lib().talc_dump_write_packed(path.encode(), _ptr(keys), _ptr(counts), len(keys), k)
+    if rc != 0:
+        raise TalcError("talc_dump_write_packed failed (%d)" % rc)
 
 
 def table_copy(dst: Talc, src: Talc) -> None:

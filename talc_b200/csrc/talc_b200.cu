@@ -22,6 +22,7 @@
 
 #include "../../include/talc_b200.h"
 #include "correct.cuh"
+#include "dump_gpu.cuh"
 #include "dump_parse.hpp"
 
 using namespace talc;
@@ -902,28 +903,20 @@ extern "C" int talc_table_load_cache_for(talc_ctx* c, const char* path, const ch
   return load_cache(c, path, true, dump_path, junction_path, n_entries);
 }
 
-// entries: dump order, already filtered to count >= MIN and valid ACGT k-mers of length K
-static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vector<u32>& counts,
-                       const std::vector<u64>& ckeys, const std::vector<u32>& ccols, uint64_t* n_kept) {
-  const u64 n = keys.size();
+// entries on the device in dump-line order (kEmptyKey = no entry on that line); nKept of the nArr slots are occupied.
+// ckeys / ccols: the junction colours already reduced to one final value per k-mer (host arrays)
+static int build_table_device(talc_ctx* c, const u64* dKeys, const u32* dCounts, u64 nArr, u64 nKept, const std::vector<u64>& ckeys,
+                              const std::vector<u32>& ccols, uint64_t* n_kept) {
   u64 cap = 2;
-  while (cap < 2 * n + 2) cap <<= 1;
+  while (cap < 2 * nKept + 2) cap <<= 1;
   int rc = talc_table_alloc(c, cap);
   if (rc) return rc;
   const int blocks = c->sms * 8;
-  u64* dKeys = nullptr;
-  u32* dCounts = nullptr;
-  if (n) {
-    CUDA_TRY(c, cudaMalloc((void**)&dKeys, n * 8));
-    CUDA_TRY(c, cudaMalloc((void**)&dCounts, n * 4));
-    CUDA_TRY(c, cudaMemcpyAsync(dKeys, keys.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(dCounts, counts.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
-  }
   unsigned long long* dN = nullptr;
   CUDA_TRY(c, cudaMalloc((void**)&dN, 16));
   CUDA_TRY(c, cudaMemsetAsync(dN, 0, 16, c->stream));
-  if (n) {
-    table_insert_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap - 1, dKeys, dCounts, n, 0, (u32*)(dN + 1));
+  if (nArr) {
+    table_insert_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap - 1, dKeys, dCounts, nArr, 0, (u32*)(dN + 1));
     CUDA_TRY(c, cudaGetLastError());
   }
   table_finalize_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap, dN);
@@ -945,8 +938,6 @@ static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vec
   CUDA_TRY(c, cudaMemcpyAsync(hN, dN, 16, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   cudaFree(dN);
-  if (dKeys) cudaFree(dKeys);
-  if (dCounts) cudaFree(dCounts);
   if (hN[1]) { c->err = "k-mer table overflowed during the build"; return TALC_ERR_ARG; }
   c->nEntries = hN[0];
   rc = build_ctx_tables(c);
@@ -954,6 +945,24 @@ static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vec
   c->tableReady = true;
   if (n_kept) *n_kept = c->nEntries;
   return TALC_OK;
+}
+// the same from host arrays: dump order, already filtered to count >= MIN and valid ACGT k-mers of length K
+static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vector<u32>& counts,
+                       const std::vector<u64>& ckeys, const std::vector<u32>& ccols, uint64_t* n_kept) {
+  const u64 n = keys.size();
+  u64* dKeys = nullptr;
+  u32* dCounts = nullptr;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (n) {
+    CUDA_TRY(c, cudaMalloc((void**)&dKeys, n * 8));
+    CUDA_TRY(c, cudaMalloc((void**)&dCounts, n * 4));
+    CUDA_TRY(c, cudaMemcpyAsync(dKeys, keys.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(dCounts, counts.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  const int rc = build_table_device(c, dKeys, dCounts, n, n, ckeys, ccols, n_kept);
+  if (dKeys) cudaFree(dKeys);
+  if (dCounts) cudaFree(dCounts);
+  return rc;
 }
 
 static u64 revcomp_kmer(u64 k, u32 K) {
@@ -1016,7 +1025,56 @@ int talc_table_load_packed(talc_ctx* c, const uint64_t* keys, const int64_t* cou
   return build_table(c, k, v, ck, cc, n_kept);
 }
 
+// buildCDBG + decolourRepeatsFromDBG (Jellyfish.cpp:236-295, utils.cpp:658-669) with the text parsed on the GPU
+// (dump_gpu.cuh): the entries never visit the host.  The junction dump (small) is parsed the same way, then reduced to
+// final colours on the host ("last writer wins, forward before reverse complement" is sequential by nature).
 int talc_table_load_dump(talc_ctx* c, const char* dump_path, const char* junction_path, uint64_t* n_lines, uint64_t* n_kept) {
+  if (!c || !dump_path) return TALC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  DeviceDump d;
+  std::string err;
+  if (!parse_dump_gpu(dump_path, c->params.K, c->params.min_count, true, c->sms, c->stream, d, err)) {
+    c->err = err;
+    return TALC_ERR_IO;
+  }
+  if (n_lines) *n_lines = d.tally.lines;
+  std::vector<u64> ck;
+  std::vector<u32> cc;
+  if (junction_path) {
+    DeviceDump j;
+    if (!parse_dump_gpu(junction_path, c->params.K, 0, false, c->sms, c->stream, j, err)) {
+      d.release();
+      c->err = err;
+      return TALC_ERR_IO;
+    }
+    std::vector<u64> jk(j.nLines);
+    std::vector<u32> jv(j.nLines);
+    if (j.nLines) {
+      cudaMemcpy(jk.data(), j.keys, j.nLines * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(jv.data(), j.counts, j.nLines * 4, cudaMemcpyDeviceToHost);
+    }
+    j.release();
+    std::vector<u64> jk2;
+    std::vector<i64> jc2;
+    jk2.reserve(jk.size());
+    jc2.reserve(jk.size());
+    for (size_t i = 0; i < jk.size(); ++i)
+      if (jk[i] != kEmptyKey) { jk2.push_back(jk[i]); jc2.push_back((i64)(i32)jv[i]); }
+    reduce_colours(c->params, jk2.data(), jc2.data(), jk2.size(), true, ck, cc);
+  } else {
+    reduce_colours(c->params, nullptr, nullptr, 0, false, ck, cc);
+  }
+  c->provJunctions = junction_path ? 1u : 0u;
+  file_identity(dump_path, c->provDumpSize, c->provDumpMtime);
+  file_identity(junction_path, c->provJuncSize, c->provJuncMtime);
+  const int rc = build_table_device(c, d.keys, d.counts, d.nLines, d.tally.kept, ck, cc, n_kept);
+  d.release();
+  return rc;
+}
+
+// The round-1 ingest path, kept for A/B timing only (bench.py --time-table-load): threaded host parse of the mapped
+// file (dump_parse.hpp), entries copied to the device afterwards.  Same table, bit for bit.
+int talc_table_load_dump_host(talc_ctx* c, const char* dump_path, const char* junction_path, uint64_t* n_lines, uint64_t* n_kept) {
   if (!c || !dump_path) return TALC_ERR_ARG;
   DumpEntries d;
   std::string err;
@@ -1044,6 +1102,28 @@ int talc_table_load_dump(talc_ctx* c, const char* dump_path, const char* junctio
   file_identity(dump_path, c->provDumpSize, c->provDumpMtime);
   file_identity(junction_path, c->provJuncSize, c->provJuncMtime);
   return build_table(c, d.keys, v, ck, cc, n_kept);
+}
+
+int talc_dump_write_packed(const char* path, const uint64_t* keys, const int64_t* counts, uint64_t n, uint32_t K) {
+  if (!path || (n && (!keys || !counts)) || K < 1 || K > 31) return TALC_ERR_ARG;
+  FILE* f = fopen(path, "wb");
+  if (!f) return TALC_ERR_IO;
+  std::vector<char> buf;
+  buf.reserve((size_t)(1u << 22) + 64);
+  bool ok = true;
+  for (u64 i = 0; i < n && ok; ++i) {
+    char line[64];
+    u32 p = 0;
+    for (u32 j = 0; j < K; ++j) line[p++] = "ACGT"[(keys[i] >> (2 * (K - 1 - j))) & 3ull];
+    line[p++] = ' ';
+    p += (u32)snprintf(line + p, sizeof(line) - p, "%lld", (long long)counts[i]);
+    line[p++] = '\n';
+    buf.insert(buf.end(), line, line + p);
+    if (buf.size() >= (1u << 22)) { ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size(); buf.clear(); }
+  }
+  if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+  ok = (fclose(f) == 0) && ok;
+  return ok ? TALC_OK : TALC_ERR_IO;
 }
 
 int talc_table_lookup(talc_ctx* c, const uint64_t* keys, uint64_t n, uint32_t* counts, uint32_t* colours, uint8_t* found) {

@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
 inputs.  Integer / byte work, so the bar is bit-exact: identical corrected sequences, identical per-read
 status (= identical failed-read log), identical algorithmic counters."""
+import os
+
 import numpy as np
 import pytest
 
@@ -458,3 +460,61 @@ def test_stream_api_matches_single_calls(api, case_c1):
     assert {k2: tot[k2] for k2 in SHARED} == {k2: ctr[k2] for k2 in SHARED}
     ostats = case.otable.read_stats(case.reads, case.off, threads=4)
     assert np.array_equal(np.concatenate(stats), ostats)
+
+
+def test_gpu_dump_parser_semantics(api, case_c3, tmp_path):
+    """Row f1: the dump text is parsed on the GPU.  (1) line semantics of buildCDBG on a hand-made file (first line
+    wins, MIN_COUNT filter, malformed lines, lower case, CR LF, trailing tokens, negative and out-of-range counts,
+    k-mers of the wrong length, no final newline) against the oracle reading the same file; (2) a whole workload written
+    as text builds the table load_packed builds, the host parser of round 1 builds the same one, and the reads
+    correct to the oracle's bytes."""
+    from oracle import pyoracle as po
+    k = 5
+    text = ("ACGTA 5\nACGTA 9\nCCCCC 7\r\nGGGGA 1\n  TTTTT\t3 trailing tokens\nbad_line\n\nAAAAA 4\nTACGT 6\nacgtc 8\n"
+            "ACG 9\nACGTAC 9\nACGTN 9\nGGGGG x9\nGGGGT -1\nGGGTT 99999999999\nGGTTT +12\nGTTTT 12abc\nCATCA 2")
+    (tmp_path / "d.dump").write_text(text)
+    (tmp_path / "j.dump").write_text("ACGTA 2\nTACGT 4\nACGTA 3\nAAAAA 5\nCCCCC 10000\nACGTC 0\njunk\nCATCA 17\n")
+    t = api.Talc(api.default_params(k))
+    nl, nk = t.load_dump(str(tmp_path / "d.dump"), str(tmp_path / "j.dump"))
+    h = api.Talc(api.default_params(k))
+    assert h.load_dump_host(str(tmp_path / "d.dump"), str(tmp_path / "j.dump")) == (nl, nk)
+    ot = po.OracleTable(po.make_params(k=k)).load_dump(str(tmp_path / "d.dump"), str(tmp_path / "j.dump"))
+    # the reference's map also holds 'ACG', 'ACGTAC' and 'ACGTN' (no length or alphabet check, Jellyfish.cpp:262): keys
+    # that no 5-mer of a read can ever equal; the 2-bit table drops them
+    assert nk == ot.size() - 3 == 10
+    from itertools import product
+    allk = ["".join(x) for x in product("ACGT", repeat=k)]
+    keys = np.array([sum("ACGT".index(ch) << (2 * (k - 1 - i)) for i, ch in enumerate(s_)) for s_ in allk], dtype=np.uint64)
+    cnt, col, found = t.lookup(keys)
+    cnt2, col2, found2 = h.lookup(keys)
+    assert np.array_equal(cnt, cnt2) and np.array_equal(col, col2) and np.array_equal(found, found2)
+    for i, s_ in enumerate(allk):
+        f, c, l = ot.lookup(s_)
+        assert (bool(found[i]), int(cnt[i]), int(col[i])) == (f, c, l), s_
+    assert int(found.sum()) == nk
+    # (2) a real workload through text
+    case = case_c3
+    api.write_dump(str(tmp_path / "sr.dump"), case.keys, case.counts, case.cfg.k)
+    api.write_dump(str(tmp_path / "jj.dump"), case.jkeys, case.jcounts, case.cfg.k)
+    a = api.Talc(api.default_params(case.cfg.k))
+    nl, nk = a.load_dump(str(tmp_path / "sr.dump"), str(tmp_path / "jj.dump"))
+    b = _ctx(api, case)
+    assert nl == len(case.keys) and nk == b.table_info()["entries"] == case.otable.size()
+    rng = np.random.default_rng(5)
+    probe = np.concatenate([case.keys[rng.integers(0, len(case.keys), 20000)], rng.integers(0, 1 << 42, 2000).astype(np.uint64)])
+    for x, y in zip(a.lookup(probe), b.lookup(probe)):
+        assert np.array_equal(x, y)
+    out, off, st, ctr = a.correct(case.reads, case.off)
+    _assert_same(case, out, off, st, ctr)
+    # the cache written from this table is refused for other inputs and accepted for the same ones
+    a.table_save(str(tmp_path / "t.bin"))
+    c2 = api.Talc(api.default_params(case.cfg.k))
+    assert c2.table_load_cache_for(str(tmp_path / "t.bin"), str(tmp_path / "sr.dump"), str(tmp_path / "jj.dump")) == nk
+    with pytest.raises(api.TalcError):
+        c2.table_load_cache_for(str(tmp_path / "t.bin"), str(tmp_path / "sr.dump"), None)
+    with pytest.raises(api.TalcError):
+        c2.table_load_cache_for(str(tmp_path / "t.bin"), str(tmp_path / "jj.dump"), str(tmp_path / "jj.dump"))
+    with open(tmp_path / "t.bin", "r+b") as f:  # truncated file
+        f.truncate(os.path.getsize(tmp_path / "t.bin") - 16)
+    with pytest.raises(api.TalcError):
+        c2.table_load_cache(str(tmp_path / "t.bin"))
