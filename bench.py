@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--batch-reads", type=int, default=131072, help="reads per step and per rank")
     ap.add_argument("--cpu-sample-reads", type=int, default=16384, help="reads of the bounded CPU sample (about 10-30 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-table-load", action="store_true", help="skip the table-load timings (text dump on GPU / host parser / cache)")
+    ap.add_argument("--cli-clock", type=int, default=0, metavar="READS",
+                    help="also time the `talc` command line end to end (process start -> .fa closed) on READS reads, "
+                         "from the text dump and from --tableCache (SURVEY 8d second clock)")
     return ap.parse_args()
 
 
@@ -195,23 +199,13 @@ def run_gpu(args, rank, world, local_rank):
     info = ctx.table_info()
     t_bcast_ms = 0.0
     if world > 1:
-        # replicate: one NCCL broadcast of the raw slot array over NVLink, then each rank seals its copy
-        meta = torch.tensor([info["capacity"], info["entries"]], dtype=torch.int64, device=dev)
-        dist.broadcast(meta, 0)
-        cap, nent = int(meta[0]), int(meta[1])
-        staging = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
+        # replicate: ONE ncclBroadcast of the raw slot array over NVLink, issued by the library itself
+        # (talc_table_broadcast); torch.distributed only carries the 128-byte NCCL id to the other ranks
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
-            ctx.table_export_device(staging)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.broadcast(staging, 0)
-        e1.record()
-        torch.cuda.synchronize()
-        t_bcast_ms = e0.elapsed_time(e1)
-        if rank != 0:
-            ctx.table_import_device(staging, cap, nent)
-        del staging
+            uid.copy_(torch.from_numpy(api.nccl_unique_id()))
+        dist.broadcast(uid, 0)
+        t_bcast_ms = ctx.table_broadcast(uid.cpu().numpy(), rank, world, 0)
         info = ctx.table_info()
     # this rank's reads: batch_reads per step, a different slice every step (and every rank)
     nsteps = args.warmup + args.steps + 1  # +1 slice for the e2e leg warm-up
@@ -219,6 +213,7 @@ def run_gpu(args, rank, world, local_rank):
     reads, roff = synth.make_reads(cfg, tr, B * nsteps, dev, seed_offset=3 + 17 * rank)
     cpu_keys = (keys, counts, jk, jc)
     tr_keep = tr if world > 1 else None
+    tr_cli = tr if args.cli_clock else None
     del tr
     t_gen = time.time() - t0
     roff = roff.to(torch.int64)
@@ -278,19 +273,35 @@ def run_gpu(args, rank, world, local_rank):
     for i in range(3):  # three pinned input batches, cycled (a different slice every step, bounded pinned memory)
         r, o, nb = batch(args.warmup + i)
         pinned.append((r.cpu().pin_memory().numpy(), o.cpu().numpy().astype(np.uint64), nb))
-    ctx.correct(pinned[2][0], pinned[2][1], host_out, host_ooff, host_st)  # warm-up of the host path
+    # the call a user of a multi-batch job makes: talc_stream_submit / talc_stream_next (pinned ring of slots, copies
+    # of batch i+1 and i-1 overlapped with the kernels of batch i); every step's result is read back on the host
+    stream = ctx.stream()
+    stream.submit(pinned[2][0], pinned[2][1])  # warm-up of the host path (allocates the slots)
+    stream.submit(pinned[1][0], pinned[1][1])
+    stream.next(copy=False)
+    stream.next(copy=False)
     e2e_bases, h2d, d2h, e2e_dev_ms = 0, 0, 0, 0.0
     barrier()
     w0 = time.perf_counter()
+    fetched = 0
     for s_ in range(args.steps):
         hr, ho, nb = pinned[s_ % 3]
-        out, ooff, st, c = ctx.correct(hr, ho, host_out, host_ooff, host_st)
-        e2e_dev_ms += c["ms_total"]
+        stream.submit(hr, ho)
         e2e_bases += nb
         h2d = nb + 8 * (B + 1)
+        if s_ - fetched >= 2:
+            out, ooff, st, _, c = stream.next(copy=False)
+            e2e_dev_ms += c["ms_total"]
+            d2h = int(ooff[-1]) + 8 * (B + 1) + B
+            fetched += 1
+    while fetched < args.steps:
+        out, ooff, st, _, c = stream.next(copy=False)
+        e2e_dev_ms += c["ms_total"]
         d2h = int(ooff[-1]) + 8 * (B + 1) + B
+        fetched += 1
     barrier()
     e2e_wall_ms = (time.perf_counter() - w0) * 1e3
+    stream.close()
     emax = torch.tensor([e2e_wall_ms], dtype=torch.float64, device=dev)
     etot = torch.tensor([float(e2e_bases)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -351,7 +362,8 @@ def run_gpu(args, rank, world, local_rank):
                                                  "algorithmic_bytes_per_launch": cov_bytes,
                                                  "frac": cov_bytes / 1e9 / (cov_ms / 1e3) / peak}},
                 "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": args.steps, "clock": "host wall clock around talc_correct_batch, max over ranks",
+                        "steps": args.steps, "clock": "host wall clock around all steps through talc_stream_submit / talc_stream_next "
+                                 "(host buffers in, pinned host results out, every result fetched), max over ranks",
                         "wall_ms": float(emax), "device_event_ms": e2e_dev_ms},
                 "replica_parity": replica_parity,
                 # stage-4 integer work: DP cell updates of the reference algorithm per second of correct_kernel
@@ -365,6 +377,10 @@ def run_gpu(args, rank, world, local_rank):
                                                      "cells_nw", "cells_lcs", "cells_ovl", "cells_xdrop", "gaps", "gaps_bridged",
                                                      "reads_second_tier", "reads_ok", "reads")},
                 "cpu_baseline": None}
+        if world == 1 and not args.no_table_load:
+            line["table_load"] = table_load_timings(api, cfg, cpu_keys, use_j)
+        if world == 1 and args.cli_clock:
+            line["cli_clock"] = cli_clock(args, cfg, cpu_keys, use_j, tr_cli, dev)
         rnd = random_sector_peaks(ctx)
         line["roofline"].update(rnd)
         if rnd.get("peak_random"):
@@ -383,6 +399,77 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def table_load_timings(api, cfg, cpu_keys, use_j):
+    """Row f1: seconds to get from the Jellyfish text dump of this workload to a sealed table in HBM -- parsed on the
+    GPU (talc_table_load_dump), by the threaded host parser of round 1 (talc_table_load_dump_host), and from the
+    binary cache (talc_table_load_cache_for)."""
+    import tempfile
+    import numpy as np
+    keys, counts, jk, jc = cpu_keys
+    d = tempfile.mkdtemp(prefix="talc_bench_")
+    dump, jdump, cache = os.path.join(d, "sr.dump"), os.path.join(d, "j.dump"), os.path.join(d, "table.bin")
+    t0 = time.time()
+    api.write_dump(dump, keys.cpu().numpy().astype(np.uint64), counts.cpu().numpy(), cfg.k)
+    if use_j:
+        api.write_dump(jdump, jk.cpu().numpy().astype(np.uint64), jc.cpu().numpy(), cfg.k)
+    t_write = time.time() - t0
+    res = {"dump_bytes": os.path.getsize(dump), "dump_lines": int(keys.numel()), "write_dump_s": round(t_write, 2)}
+    j = jdump if use_j else None
+    for name, fn in (("gpu_parser_s", "load_dump"), ("host_parser_s", "load_dump_host")):
+        t = api.Talc(api.default_params(cfg.k))
+        t0 = time.time()
+        nl, nk = getattr(t, fn)(dump, j)
+        res[name] = round(time.time() - t0, 2)
+        res["entries_kept"] = nk
+        if name == "gpu_parser_s":
+            t0 = time.time()
+            t.table_save(cache)
+            res["cache_write_s"] = round(time.time() - t0, 2)
+        t.close()
+    t = api.Talc(api.default_params(cfg.k))
+    t0 = time.time()
+    t.table_load_cache_for(cache, dump, j)
+    res["cache_load_s"] = round(time.time() - t0, 2)
+    t.close()
+    for f in (dump, jdump, cache):
+        if os.path.exists(f):
+            os.remove(f)
+    os.rmdir(d)
+    return res
+
+
+def cli_clock(args, cfg, cpu_keys, use_j, tr, dev):
+    """SURVEY 8d second clock: the `talc` command line, process start -> .fa closed, on `--cli-clock` reads of this
+    workload: table from the text dump, then from --tableCache."""
+    import tempfile
+    import numpy as np
+    from talc_b200 import api, build, synth
+    keys, counts, jk, jc = cpu_keys
+    d = tempfile.mkdtemp(prefix="talc_cli_")
+    dump, jdump = os.path.join(d, "sr.dump"), os.path.join(d, "j.dump")
+    api.write_dump(dump, keys.cpu().numpy().astype(np.uint64), counts.cpu().numpy(), cfg.k)
+    if use_j:
+        api.write_dump(jdump, jk.cpu().numpy().astype(np.uint64), jc.cpu().numpy(), cfg.k)
+    reads, roff = synth.make_reads(cfg, tr, args.cli_clock, dev, seed_offset=3)
+    synth.write_fasta(os.path.join(d, "reads.fa"), reads, roff)
+    bases = int(roff[-1])
+    cli = build.build_cli()
+    common = [cli, "reads.fa", "--SRCounts", "sr.dump", "-k", str(cfg.k), "-t", str(min(16, os.cpu_count() or 1))] + \
+             (["--junctions", "j.dump"] if use_j else [])
+    res = {"reads": args.cli_clock, "bases": bases, "fasta_bytes": os.path.getsize(os.path.join(d, "reads.fa"))}
+    for name, extra in (("text_dump", ["-o", "a"]), ("cache_cold", ["-o", "b", "--tableCache", "t.bin"]),
+                        ("cache_warm", ["-o", "c", "--tableCache", "t.bin"])):
+        t0 = time.time()
+        rc = subprocess.call(common + extra, cwd=d, stdout=subprocess.DEVNULL)
+        secs = time.time() - t0
+        res[name] = {"rc": rc, "seconds": round(secs, 2), "mbp_per_s": round(bases / 1e6 / secs, 1)}
+    import hashlib
+    res["fa_identical"] = len({hashlib.sha256(open(os.path.join(d, x + ".fa"), "rb").read()).hexdigest() for x in "abc"}) == 1
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+    return res
 
 
 def random_sector_peaks(ctx):
