@@ -108,6 +108,15 @@ int talc_table_load_dump(talc_ctx* ctx, const char* dump_path, const char* junct
  * threaded host parser of round 1, kept for A/B timing; both build the same table bit for bit.                    */
 int talc_table_load_dump_host(talc_ctx* ctx, const char* dump_path, const char* junction_path, uint64_t* n_lines,
                               uint64_t* n_kept);
+/* Row f3 -- the table counted on the GPU straight from short-read files, replacing `jellyfish count` + `jellyfish dump -c`
+ * (README.md:33-55 of the reference) and the text round trip: NON-canonical counts of every window of K consecutive
+ * ACGT letters (either case) of every read of every file (paired-end: pass both files); FASTQ with four lines per
+ * record or FASTA with one sequence line per record.  The sealed table holds the k-mers with count >= MIN_COUNT, i.e.
+ * what buildCDBG keeps of the dump (Jellyfish.cpp:260); junction colours are applied as for a dump (NULL = none).
+ * expected_distinct sizes the counting table like jellyfish's -s (0 = derived from the file sizes); TALC_ERR_CAPACITY
+ * when it was too small.  n_kmers = occurrences counted, n_distinct = distinct k-mers seen, n_kept = entries kept.   */
+int talc_table_count_reads(talc_ctx* ctx, const char* const* paths, int n_paths, uint64_t expected_distinct,
+                           const char* junction_path_or_null, uint64_t* n_kmers, uint64_t* n_distinct, uint64_t* n_kept);
 /* Jellyfish `dump -c` text of packed k-mers (KMER<space>COUNT\n, given order): the inverse of the parser, for tests,
  * benches and for exporting a table.  Host only.                                                                    */
 int talc_dump_write_packed(const char* path, const uint64_t* keys, const int64_t* counts, uint64_t n, uint32_t K);

@@ -56,6 +56,7 @@ def lib():
         L.talc_table_load_dump.argtypes = [vp, C.c_char_p, C.c_char_p, u64p, u64p]
         L.talc_table_load_dump_host.argtypes = [vp, C.c_char_p, C.c_char_p, u64p, u64p]
         L.talc_dump_write_packed.argtypes = [C.c_char_p, vp, vp, C.c_uint64, C.c_uint32]
+        L.talc_table_count_reads.argtypes = [vp, C.POINTER(C.c_char_p), C.c_int, C.c_uint64, C.c_char_p, u64p, u64p, u64p]
         L.talc_table_load_packed.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, C.c_int, u64p]
         L.talc_table_info.argtypes = [vp, u64p, u64p, u64p]
         L.talc_table_alloc.argtypes = [vp, C.c_uint64]
@@ -149,6 +150,16 @@ class Talc:
         self._check(lib().talc_table_load_dump_host(self.h, dump.encode(), junctions.encode() if junctions else None,
                                                     C.byref(nl), C.byref(nk)), "talc_table_load_dump_host")
         return nl.value, nk.value
+
+    def count_reads(self, paths, expected_distinct: int = 0, junctions: Optional[str] = None):
+        """Row f3: build the table by counting k-mers of short-read FASTQ/FASTA files on the GPU.
+        Returns (k-mer occurrences, distinct k-mers, entries kept)."""
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        a, b, d = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(lib().talc_table_count_reads(self.h, arr, len(paths), expected_distinct,
+                                                 junctions.encode() if junctions else None, C.byref(a), C.byref(b),
+                                                 C.byref(d)), "talc_table_count_reads")
+        return a.value, b.value, d.value
 
     def load_packed(self, keys, counts, jkeys=None, jcounts=None) -> int:
         keys = np.ascontiguousarray(keys, dtype=np.uint64)

@@ -22,6 +22,7 @@
 
 #include "../../include/talc_b200.h"
 #include "correct.cuh"
+#include "count_gpu.cuh"
 #include "dump_gpu.cuh"
 #include "dump_parse.hpp"
 
@@ -903,22 +904,12 @@ extern "C" int talc_table_load_cache_for(talc_ctx* c, const char* path, const ch
   return load_cache(c, path, true, dump_path, junction_path, n_entries);
 }
 
-// entries on the device in dump-line order (kEmptyKey = no entry on that line); nKept of the nArr slots are occupied.
-// ckeys / ccols: the junction colours already reduced to one final value per k-mer (host arrays)
-static int build_table_device(talc_ctx* c, const u64* dKeys, const u32* dCounts, u64 nArr, u64 nKept, const std::vector<u64>& ckeys,
-                              const std::vector<u32>& ccols, uint64_t* n_kept) {
-  u64 cap = 2;
-  while (cap < 2 * nKept + 2) cap <<= 1;
-  int rc = talc_table_alloc(c, cap);
-  if (rc) return rc;
+// common tail of every build: strip the line indices, apply the reduced junction colours + homopolymer resets, check
+// the overflow flag at dN[1], derive the successor tables
+static int finish_table(talc_ctx* c, unsigned long long* dN, const std::vector<u64>& ckeys, const std::vector<u32>& ccols,
+                        uint64_t* n_kept) {
   const int blocks = c->sms * 8;
-  unsigned long long* dN = nullptr;
-  CUDA_TRY(c, cudaMalloc((void**)&dN, 16));
-  CUDA_TRY(c, cudaMemsetAsync(dN, 0, 16, c->stream));
-  if (nArr) {
-    table_insert_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap - 1, dKeys, dCounts, nArr, 0, (u32*)(dN + 1));
-    CUDA_TRY(c, cudaGetLastError());
-  }
+  const u64 cap = c->capacity;
   table_finalize_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap, dN);
   CUDA_TRY(c, cudaGetLastError());
   if (!ckeys.empty()) {
@@ -937,14 +928,33 @@ static int build_table_device(talc_ctx* c, const u64* dKeys, const u32* dCounts,
   unsigned long long hN[2] = {0, 0};
   CUDA_TRY(c, cudaMemcpyAsync(hN, dN, 16, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  cudaFree(dN);
   if (hN[1]) { c->err = "k-mer table overflowed during the build"; return TALC_ERR_ARG; }
   c->nEntries = hN[0];
-  rc = build_ctx_tables(c);
+  const int rc = build_ctx_tables(c);
   if (rc) return rc;
   c->tableReady = true;
   if (n_kept) *n_kept = c->nEntries;
   return TALC_OK;
+}
+// entries on the device in dump-line order (kEmptyKey = no entry on that line); nKept of the nArr slots are occupied.
+// ckeys / ccols: the junction colours already reduced to one final value per k-mer (host arrays)
+static int build_table_device(talc_ctx* c, const u64* dKeys, const u32* dCounts, u64 nArr, u64 nKept, const std::vector<u64>& ckeys,
+                              const std::vector<u32>& ccols, uint64_t* n_kept) {
+  u64 cap = 2;
+  while (cap < 2 * nKept + 2) cap <<= 1;
+  int rc = talc_table_alloc(c, cap);
+  if (rc) return rc;
+  const int blocks = c->sms * 8;
+  unsigned long long* dN = nullptr;
+  CUDA_TRY(c, cudaMalloc((void**)&dN, 16));
+  CUDA_TRY(c, cudaMemsetAsync(dN, 0, 16, c->stream));
+  if (nArr) {
+    table_insert_kernel<<<blocks, 256, 0, c->stream>>>(c->slots, cap - 1, dKeys, dCounts, nArr, 0, (u32*)(dN + 1));
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  const int rc2 = finish_table(c, dN, ckeys, ccols, n_kept);
+  cudaFree(dN);
+  return rc2;
 }
 // the same from host arrays: dump order, already filtered to count >= MIN and valid ACGT k-mers of length K
 static int build_table(talc_ctx* c, const std::vector<u64>& keys, const std::vector<u32>& counts,
@@ -1102,6 +1112,148 @@ int talc_table_load_dump_host(talc_ctx* c, const char* dump_path, const char* ju
   file_identity(dump_path, c->provDumpSize, c->provDumpMtime);
   file_identity(junction_path, c->provJuncSize, c->provJuncMtime);
   return build_table(c, d.keys, v, ck, cc, n_kept);
+}
+
+// ---------------------------------------------------------------------------------- row f3: count k-mers from short reads
+static int junction_colours_gpu(talc_ctx* c, const char* junction_path, std::vector<u64>& ck, std::vector<u32>& cc) {
+  std::string err;
+  if (!junction_path) { reduce_colours(c->params, nullptr, nullptr, 0, false, ck, cc); return TALC_OK; }
+  DeviceDump j;
+  if (!parse_dump_gpu(junction_path, c->params.K, 0, false, c->sms, c->stream, j, err)) { c->err = err; return TALC_ERR_IO; }
+  std::vector<u64> jk(j.nLines);
+  std::vector<u32> jv(j.nLines);
+  if (j.nLines) {
+    cudaMemcpy(jk.data(), j.keys, j.nLines * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(jv.data(), j.counts, j.nLines * 4, cudaMemcpyDeviceToHost);
+  }
+  j.release();
+  std::vector<u64> jk2;
+  std::vector<i64> jc2;
+  for (size_t i = 0; i < jk.size(); ++i)
+    if (jk[i] != kEmptyKey) { jk2.push_back(jk[i]); jc2.push_back((i64)(i32)jv[i]); }
+  reduce_colours(c->params, jk2.data(), jc2.data(), jk2.size(), true, ck, cc);
+  return TALC_OK;
+}
+
+int talc_table_count_reads(talc_ctx* c, const char* const* paths, int n_paths, uint64_t expected_distinct, const char* junction_path,
+                           uint64_t* n_kmers, uint64_t* n_distinct, uint64_t* n_kept) {
+  if (!c || !paths || n_paths < 1) return TALC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const u32 K = c->params.K;
+  if (expected_distinct == 0) {  // no hint (jellyfish's -s): one distinct k-mer per 4 bytes of input is generous
+    for (int i = 0; i < n_paths; ++i) {
+      struct stat st;
+      if (stat(paths[i], &st) == 0) expected_distinct += (u64)st.st_size / 4;
+    }
+    if (expected_distinct < (1u << 20)) expected_distinct = 1u << 20;
+  }
+  u64 cap = 2;
+  while (cap < 2 * expected_distinct + 2) cap <<= 1;
+  const int blocks = c->sms * 8;
+  Slot* big = nullptr;
+  CUDA_TRY(c, cudaMalloc((void**)&big, cap * sizeof(Slot)));
+  count_fill_empty_kernel<<<blocks, 256, 0, c->stream>>>(big, cap);
+  const size_t piece = 64u << 20;
+  char *pin = nullptr, *dText = nullptr;
+  u8* dFlag = nullptr;
+  u64* dStarts = nullptr;
+  unsigned long long* dNum = nullptr;  // [0] line count / select count, [1] k-mer occurrences, [2] fail flag, [3] distinct, [4] kept
+  void* dTmp = nullptr;
+  size_t tmpBytes = 0;
+  int rc = TALC_OK;
+  auto fail = [&](int code, const std::string& msg) { rc = code; c->err = msg; };
+  if (cudaHostAlloc((void**)&pin, piece, cudaHostAllocDefault) != cudaSuccess || cudaMalloc((void**)&dText, 2 * piece + 16) != cudaSuccess ||
+      cudaMalloc((void**)&dFlag, 2 * piece) != cudaSuccess || cudaMalloc((void**)&dStarts, (2 * piece / 2 + 2) * 8) != cudaSuccess ||
+      cudaMalloc((void**)&dNum, 64) != cudaSuccess)
+    fail(TALC_ERR_CUDA, "talc_table_count_reads: out of memory");
+  if (rc == TALC_OK) {
+    cudaMemsetAsync(dNum, 0, 64, c->stream);
+    thrust::counting_iterator<u64> pos0(0);
+    cub::DeviceSelect::Flagged(nullptr, tmpBytes, pos0, dFlag, dStarts, (u64*)dNum, (int)(2 * piece), c->stream);
+    if (cudaMalloc(&dTmp, tmpBytes + 16) != cudaSuccess) fail(TALC_ERR_CUDA, "talc_table_count_reads: out of memory");
+  }
+  for (int fi = 0; fi < n_paths && rc == TALC_OK; ++fi) {
+    FILE* f = fopen(paths[fi], "rb");
+    if (!f) { fail(TALC_ERR_IO, std::string("cannot open ") + paths[fi]); break; }
+    u64 carry = 0;  // bytes of an incomplete record at the front of dText
+    u32 period = 0;
+    bool eof = false;
+    while (!eof && rc == TALC_OK) {
+      size_t n = fread(pin, 1, piece, f);
+      eof = n < piece;
+      if (n == 0 && carry == 0) break;
+      if (period == 0) {
+        size_t q = 0;
+        while (q < n && (pin[q] == '\n' || pin[q] == '\r')) ++q;
+        if (q < n && pin[q] == '@') period = 4;
+        else if (q < n && pin[q] == '>') period = 2;
+        else { fail(TALC_ERR_IO, std::string(paths[fi]) + " is neither FASTQ nor FASTA"); break; }
+        if (q) { memmove(pin, pin + q, n - q); n -= q; }
+      }
+      if (n && cudaMemcpyAsync(dText + carry, pin, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { fail(TALC_ERR_CUDA, "copy failed"); break; }
+      const u64 size = carry + n;
+      cudaMemsetAsync(dNum, 0, 8, c->stream);
+      line_flag_kernel<<<blocks, 256, 0, c->stream>>>(dText, size, dFlag, dNum);
+      u64 nLines = 0;
+      cudaMemcpyAsync(&nLines, dNum, 8, cudaMemcpyDeviceToHost, c->stream);
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) { fail(TALC_ERR_CUDA, "line scan failed"); break; }
+      if (nLines > piece) { fail(TALC_ERR_IO, std::string(paths[fi]) + ": lines of fewer than two bytes on average -- not a read file"); break; }
+      thrust::counting_iterator<u64> pos(0);
+      size_t tb = tmpBytes;
+      cub::DeviceSelect::Flagged(dTmp, tb, pos, dFlag, dStarts, (u64*)dNum, (int)size, c->stream);
+      // lines that are complete: all of them at the end of the file, else all but the last (which may be cut); records
+      // that are complete: a multiple of `period` lines
+      u64 usable = eof ? nLines : (nLines ? nLines - 1 : 0);
+      usable -= usable % period;
+      u64 cut = size;
+      if (usable < nLines) {
+        cudaMemcpyAsync(&cut, dStarts + usable, 8, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { fail(TALC_ERR_CUDA, "line scan failed"); break; }
+      }
+      if (usable) {
+        count_kmers_kernel<<<blocks, 256, 0, c->stream>>>(dText, cut, dStarts, usable, period, K, big, cap - 1, dNum + 1, (u32*)(dNum + 2));
+        if (cudaGetLastError() != cudaSuccess) { fail(TALC_ERR_CUDA, "count kernel launch failed"); break; }
+      }
+      carry = size - cut;
+      if (carry > piece) { fail(TALC_ERR_IO, std::string("a record of ") + paths[fi] + " is longer than 64 MiB"); break; }
+      if (carry) cudaMemcpyAsync(dText, dText + cut, carry, cudaMemcpyDeviceToDevice, c->stream);  // cut >= carry: no overlap
+      if (eof) break;
+    }
+    fclose(f);
+  }
+  unsigned long long h[5] = {0, 0, 0, 0, 0};
+  if (rc == TALC_OK) {
+    count_tally_kernel<<<blocks, 256, 0, c->stream>>>(big, cap, c->params.min_count, dNum + 3, dNum + 4);
+    cudaMemcpyAsync(h, dNum, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) fail(TALC_ERR_CUDA, std::string("k-mer counting failed: ") + cudaGetErrorString(cudaGetLastError()));
+    else if (h[2]) fail(TALC_ERR_CAPACITY, "the counting table is full: raise expected_distinct (jellyfish's -s)");
+  }
+  if (rc == TALC_OK) {
+    if (n_kmers) *n_kmers = h[1];
+    if (n_distinct) *n_distinct = h[3];
+    u64 fcap = 2;
+    while (fcap < 2 * h[4] + 2) fcap <<= 1;
+    rc = talc_table_alloc(c, fcap);
+    if (rc == TALC_OK) {
+      cudaMemsetAsync(dNum, 0, 64, c->stream);
+      count_rehash_kernel<<<blocks, 256, 0, c->stream>>>(big, cap, c->params.min_count, c->slots, fcap - 1, (u32*)(dNum + 1));
+      std::vector<u64> ck;
+      std::vector<u32> cc;
+      rc = junction_colours_gpu(c, junction_path, ck, cc);
+      c->provJunctions = junction_path ? 1u : 0u;
+      c->provDumpSize = c->provDumpMtime = 0;
+      file_identity(junction_path, c->provJuncSize, c->provJuncMtime);
+      if (rc == TALC_OK) rc = finish_table(c, dNum, ck, cc, n_kept);
+    }
+  }
+  if (pin) cudaFreeHost(pin);
+  if (dText) cudaFree(dText);
+  if (dFlag) cudaFree(dFlag);
+  if (dStarts) cudaFree(dStarts);
+  if (dNum) cudaFree(dNum);
+  if (dTmp) cudaFree(dTmp);
+  cudaFree(big);
+  return rc;
 }
 
 int talc_dump_write_packed(const char* path, const uint64_t* keys, const int64_t* counts, uint64_t n, uint32_t K) {

@@ -518,3 +518,69 @@ def test_gpu_dump_parser_semantics(api, case_c3, tmp_path):
         f.truncate(os.path.getsize(tmp_path / "t.bin") - 16)
     with pytest.raises(api.TalcError):
         c2.table_load_cache(str(tmp_path / "t.bin"))
+
+
+def test_gpu_kmer_counting_from_short_reads(api, case_c1, tmp_path):
+    """Row f3: talc_table_count_reads counts the k-mers of short-read files on the GPU and builds the table `jellyfish
+    count | jellyfish dump -c | buildCDBG` would have built: checked against the numpy restatement of the counting rule
+    (oracle/kmer_count.py), against the dump route (counts written as text, parsed, filtered), and end to end."""
+    from oracle import kmer_count as kc
+    case = case_c1
+    k = case.cfg.k
+    rng = np.random.default_rng(11)
+    tb = case.w.t_bases.numpy()
+    toff = case.w.t_off.numpy()
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def short_reads(n):
+        out = []
+        for _ in range(n):
+            t = int(rng.integers(0, len(toff) - 1))
+            a, b = int(toff[t]), int(toff[t + 1])
+            L = int(rng.integers(30, 151))
+            p = int(rng.integers(a, max(a + 1, b - L)))
+            s = letters[tb[p:min(b, p + L)]].copy()
+            for q in np.nonzero(rng.random(len(s)) < 0.01)[0]:
+                s[q] = letters[int(rng.integers(0, 4))]
+            r = rng.random()
+            if r < 0.05 and len(s) > 5:
+                s[int(rng.integers(0, len(s)))] = ord("N")
+            elif r < 0.10:
+                s = np.frombuffer(s.tobytes().lower(), dtype=np.uint8).copy()
+            out.append(s.tobytes())
+        out.append(b"ACGT")                    # shorter than K
+        out.append(b"A" * 70)                  # homopolymer: 70-K+1 occurrences of one k-mer
+        return out
+
+    r1, r2 = short_reads(30000), short_reads(20000)
+    with open(tmp_path / "sr_1.fq", "wb") as f:
+        for i, s_ in enumerate(r1):
+            f.write(b"@r%d/1\n" % i + s_ + b"\n+\n" + b"I" * len(s_) + b"\n")
+    with open(tmp_path / "sr_2.fa", "wb") as f:
+        for i, s_ in enumerate(r2):
+            f.write(b">r%d/2\r\n" % i + s_ + b"\r\n")
+    okeys, ocounts, occ = kc.count_kmers(kc.read_sequences(str(tmp_path / "sr_1.fq")) + kc.read_sequences(str(tmp_path / "sr_2.fa")), k)
+    assert occ > 2_000_000 and len(okeys) > 100_000
+    t = api.Talc(api.default_params(k))
+    n_kmers, n_distinct, n_kept = t.count_reads([str(tmp_path / "sr_1.fq"), str(tmp_path / "sr_2.fa")])
+    keep = ocounts >= 2
+    assert (n_kmers, n_distinct, n_kept) == (occ, len(okeys), int(keep.sum()))
+    cnt, col, found = t.lookup(okeys)
+    assert np.array_equal(found.astype(bool), keep)
+    assert np.array_equal(cnt[keep], ocounts[keep].astype(np.uint32)) and not cnt[~keep].any() and not col.any()
+    # the dump route: the same counts as text -> parser -> MIN_COUNT filter
+    api.write_dump(str(tmp_path / "sr.dump"), okeys, ocounts, k)
+    d = api.Talc(api.default_params(k))
+    assert d.load_dump(str(tmp_path / "sr.dump")) == (len(okeys), n_kept)
+    probe = np.concatenate([okeys[::7], rng.integers(0, 1 << 42, 3000).astype(np.uint64)])
+    for x, y in zip(t.lookup(probe), d.lookup(probe)):
+        assert np.array_equal(x, y)
+    # too small a counting table is an error, not a silent loss
+    with pytest.raises(api.TalcError):
+        api.Talc(api.default_params(k)).count_reads([str(tmp_path / "sr_1.fq")], expected_distinct=1000)
+    # end to end: long reads corrected with the counted table == with the table from the dump of the same counts
+    sub_r, sub_o = case.reads[: int(case.off[60])], case.off[:61]
+    a = t.correct(sub_r, sub_o)
+    b = d.correct(sub_r, sub_o)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[3]["gaps"] == b[3]["gaps"] and a[3]["lookups_walk"] == b[3]["lookups_walk"]
