@@ -73,6 +73,7 @@ typedef struct talc_counters {
   uint64_t bases_out, reads_ok, reads_overflow;
   /* filled by the host side of the call */
   uint64_t reads, bases_in, reads_second_tier, kernel_launches;
+  uint64_t rounds;   /* control / walk kernel rounds of the call (0 in monolithic mode) */
   double ms_h2d, ms_coverage, ms_correct, ms_correct_tier2, ms_gather, ms_d2h, ms_total;
 } talc_counters;
 
@@ -98,6 +99,12 @@ const char* talc_last_error(talc_ctx* ctx);   /* ctx may be NULL: last create er
 
 /* scratch sizing (optional): bytes per thread for the first and second tier, warps (= reads in flight) of the second tier */
 int talc_ctx_set_scratch(talc_ctx* ctx, uint32_t tier1_bytes, uint32_t tier2_bytes, uint32_t tier2_threads);
+
+/* execution shape of the correction kernels; 0 keeps a value.  split_walk: 1 (default) = reads are suspendable programs
+ * whose long graph walks run in a separate lane-per-trail kernel (csrc/walk.cuh), 2 = one monolithic kernel per batch
+ * (the round-1 shape, kept for A/B measurements).  Results are identical (tests/test_gpu_parity.py).  read_contexts =
+ * reads in flight in split mode (each owns a first-tier arena), walk_step_cap = steps per frontier and round.  */
+int talc_ctx_set_exec(talc_ctx* ctx, uint32_t split_walk, uint32_t read_contexts, uint32_t walk_step_cap);
 
 /* ---- k-mer table (main.cpp:231-232) -------------------------------------------------------- */
 /* Jellyfish `dump -c` text (KMER<ws>COUNT per line), optional junction dump (NULL = none).      */

@@ -23,7 +23,7 @@ class TalcParams(C.Structure):
 COUNTER_U64 = ["lookups_seg", "lookups_deg", "lookups_walk", "steps_inner", "steps_border", "frontier_sum", "cells_nw",
                "cells_lcs", "cells_ovl", "cells_xdrop", "gaps", "gaps_bridged", "gap_attempts", "borders",
                "borders_corrected", "ev_gardening", "ev_bridge", "ev_edge", "ev_cycle", "bases_out", "reads_ok",
-               "reads_overflow", "reads", "bases_in", "reads_second_tier", "kernel_launches"]
+               "reads_overflow", "reads", "bases_in", "reads_second_tier", "kernel_launches", "rounds"]
 COUNTER_F64 = ["ms_h2d", "ms_coverage", "ms_correct", "ms_correct_tier2", "ms_gather", "ms_d2h", "ms_total"]
 
 
@@ -53,6 +53,7 @@ def lib():
         L.talc_last_error.restype = C.c_char_p
         L.talc_last_error.argtypes = [vp]
         L.talc_ctx_set_scratch.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.talc_ctx_set_exec.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
         L.talc_table_load_dump.argtypes = [vp, C.c_char_p, C.c_char_p, u64p, u64p]
         L.talc_table_load_dump_host.argtypes = [vp, C.c_char_p, C.c_char_p, u64p, u64p]
         L.talc_dump_write_packed.argtypes = [C.c_char_p, vp, vp, C.c_uint64, C.c_uint32]
@@ -136,6 +137,10 @@ class Talc:
 
     def set_scratch(self, tier1_bytes=0, tier2_bytes=0, tier2_threads=0):
         self._check(lib().talc_ctx_set_scratch(self.h, tier1_bytes, tier2_bytes, tier2_threads), "talc_ctx_set_scratch")
+
+    def set_exec(self, split_walk=0, read_contexts=0, walk_step_cap=0):
+        """split_walk: 1 = suspendable reads + walk kernel (default), 2 = monolithic kernel; 0 keeps a value."""
+        self._check(lib().talc_ctx_set_exec(self.h, split_walk, read_contexts, walk_step_cap), "talc_ctx_set_exec")
 
     # ---- table
     def load_dump(self, dump: str, junctions: Optional[str] = None):

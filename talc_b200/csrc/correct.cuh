@@ -139,6 +139,44 @@ class Corrector {
   Trail* nxt;
   u32 nCur, nNxt, maxT;
 
+  // --- resumable control flow.  The per-read program (run -> search_bridge / search_edge) is a state machine whose
+  // loop variables live in these frames, so a read can be suspended where a long walk starts -- the walk then runs in
+  // its own kernel (walk.cuh), one trail per lane next to the trails of other reads -- and resumed afterwards from
+  // its context in HBM.  Without splitWalk (host emulation, tuning builds) nothing ever yields.
+  enum : u8 { kStepFalse = 0, kStepTrue = 1, kStepYield = 2 };
+  static const u32 kInlineWalkSteps = 6;  // steps a warp still takes by itself before it hands the frontier over
+  struct WalkReq {  // what the walk kernel needs besides cur[] / the slots, and what it hands back (step)
+    const AnchorRec* aims;
+    u32 nAims, step, pathMax, border;
+  };
+  struct RunFrame {
+    u32 pc, reg;
+    int attempt;
+    bool success;
+  };
+  struct BridgeFrame {
+    u32 pc, s, limit, mk0, whichStart, gapLen, pathMax, step;
+    u32 maxBridges, maxKeep, nBr, nBrSeq;
+    RefView ref;
+    void* br;      // BridgeRec[maxBridges]
+    u64* brSeq;
+    i32 runScore;
+    double runMd;
+    bool runHave, found;
+  };
+  struct EdgeFrame {
+    u32 pc, s, limit, mk0, whichStart, pathMax, step;
+    int xdrop;
+    RefView ref;
+    EdgeBest bestLong, bestShort;
+  };
+  WalkReq wq;
+  RunFrame fr;
+  BridgeFrame fb;
+  EdgeFrame fe;
+  ReadJob job_;
+  u32 splitWalk;  // 1: hand long walks to the walk kernel (yield), 0: walk inline
+
   TALC_HD u32 K() const { return P.K; }
 
   // ------------------------------------------------------------------ prediction intervals from the per-context tables
@@ -628,6 +666,9 @@ class Corrector {
   }
 
 
+  // a frontier the fast path (and the walk kernel, walk.cuh) can take: every trail in its own lane of a group
+  TALC_HD bool walk_eligible(u32 nAims) const { return !(nCur == 0 || nCur > 7 || nCur > P.max_branches || nAims > 32); }
+
   // ------------------------------------------------------------------ single-trail fast path
   // The frontier holds one trail for ~96% of all steps (oracle counters).  While it does, and the step
   // is an ordinary one -- exactly one admissible successor, no aim reached, no cycle, no pruning point --
@@ -635,8 +676,10 @@ class Corrector {
   // run *before* the step, and the general code below redoes that step in full; the two are therefore
   // interchangeable step by step and the result cannot depend on which one ran.
   // border == false: oneMoreStep (Explorer.cpp:546-612); border == true: oneMoreStepInTheDark (:615-687).
-  TALC_HDN void fast_walk_scalar(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border) {
-    if (nCur != 1) return;
+  // maxSteps bounds the run; returns true when the run ended on that bound (the trail was still walking)
+  TALC_HDN bool fast_walk_scalar(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border, u32 maxSteps) {
+    if (nCur != 1) return false;
+    bool capped = false;
     const u32 k = P.K;
     const bool right = dirRight;
     Trail tr = cur[0];
@@ -656,6 +699,7 @@ class Corrector {
     u64 cw = w[cwIdx];
     while (st < pathMax) {
       if (border && ((st + 1) % kCheckInterval == 0)) break;  // scoreEdges is due after this step
+      if (nSteps >= maxSteps) { capped = true; break; }
       const u32 plen = k + st;
       u32 cnt[4], col[4];
       NextProbe probe;
@@ -725,6 +769,7 @@ class Corrector {
         ctr->lookups_walk += 4ull * nSteps;
       }
     }
+    return capped;
   }
 
 
@@ -739,9 +784,10 @@ class Corrector {
   // order (child t of trail t), nothing is scored or pruned (frontier <= MAX_NB_COMPETING_PATHS and <= 7, so
   // `complex` is false and gardening cannot trigger), and the step only appends one base per trail.  Any other
   // kind of step ends the run *before* the step; the general code then takes that step in full.
-  __device__ __noinline__ void fast_walk(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border) {
+  __device__ __noinline__ bool fast_walk(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border, u32 maxSteps) {
     const u32 nT = nCur;
-    if (nT == 0 || nT > 7 || nT > P.max_branches || nAims > 32) return;
+    if (!walk_eligible(nAims)) return false;
+    bool capped = false;
     const u32 lane = threadIdx.x & 31u;
     const u64 myAim = (!border && lane < nAims) ? aims[lane].kmer : ~0ull;  // ~0 is not a k-mer (<= 60 bits)
     const bool act = lane < nT;  // lane t owns trail t: ONE bucket of the successor table answers its whole step
@@ -765,6 +811,7 @@ class Corrector {
 #pragma unroll 1
     while (st < pathMax) {
       if (untilCheck == 0) break;  // border: (st + 1) % kCheckInterval == 0, scoreEdges is due after this step
+      if (nSteps >= maxSteps) { capped = true; break; }
       const u32 plen = k + st;
       // ---- the four successors of every trail: one sector per trail
       int child = -1;
@@ -845,6 +892,7 @@ class Corrector {
         ctr->lookups_walk += 4ull * nSteps * nT;
       }
     }
+    return capped;
   }
   // more than one successor in the graph: the exact tagging rules decide (rare on the fast path, kept out of line)
   __device__ __noinline__ int pick_single_child(const u32 c4[4], u32 cm, u32 count) {
@@ -861,8 +909,8 @@ class Corrector {
     return n == 1 ? child : -1;
   }
 #else
-  inline void fast_walk(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border) {
-    fast_walk_scalar(step, pathMax, aims, nAims, border);
+  inline bool fast_walk(u32& step, u32 pathMax, const AnchorRec* aims, u32 nAims, bool border, u32 maxSteps) {
+    return fast_walk_scalar(step, pathMax, aims, nAims, border, maxSteps);
   }
 #endif
 
@@ -1018,55 +1066,110 @@ class Corrector {
     return false;
   }
 
-  TALC_HDN bool search_bridge(Piece& weakOut) {
+  // One call runs the search until it ends (kStepTrue: weakOut holds the accepted bridge, kStepFalse: none / scratch
+  // overflow, see the arenas) or until a long walk is handed over (kStepYield: call again after the walk).
+  // fb.pc == 0 starts a new search.
+  TALC_HDN u8 search_bridge(Piece& weakOut) {
     const u32 k = K();
     const AnchorRec* anchors = dirRight ? ancL : ancR;
     const u32 nAnch = dirRight ? nAncL : nAncR;
     const AnchorRec* aims = dirRight ? ancR : ancL;
     const u32 nAims = dirRight ? nAncR : nAncL;
-    u32 limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
-    bool found = false;
-    const u32 mk0 = scratch.mark();
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1  // at most 5 start anchors: unrolled, the whole search would be in the binary five times
-#endif
-    for (u32 s = 0; s < limit && !found; ++s) {
-      scratch.release(mk0);
-      if (ctr) ctr->gap_attempts++;
-      const u32 whichStart = anchors[s].pos;
-      u32 gapLen = 0;
-      if (dirRight & (whichStart + k < R.start)) gapLen = R.start - (whichStart + k);
-      else if (!dirRight & (L.end + k < whichStart)) gapLen = whichStart - (L.end + k);
-      const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(3 * k));
-      RefView ref;
-      ref.w = rdw;
-      ref.lg = rdlg;
-      if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = R.end + k - whichStart; }
-      else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k - L.start; }
-      if (!setup_search(pathMax)) return false;
-      if (!push_root(anchors[s])) return false;
-      // bridges: metadata for all, sequences only for running-best record setters
-      // the reference puts no cap on recorded bridges: the caps grow with the arena (second tier: ~50 000 bridges)
-      const u32 capShare = (scratch.cap - scratch.top) / 16u;
-      u32 maxBridges = capShare / (u32)sizeof(BridgeRec);
-      if (maxBridges < 1024u) maxBridges = 1024u;
-      u32 maxKeep = capShare / (slotWords * 8u);
-      if (maxKeep < 32u) maxKeep = 32u;
-      if (maxKeep > maxBridges) maxKeep = maxBridges;
-      BridgeRec* br = (BridgeRec*)scratch.alloc(maxBridges * sizeof(BridgeRec));
-      u64* brSeq = (u64*)scratch.alloc(maxKeep * slotWords * 8);
-      if (!br || !brSeq) return false;
-      u32 nBr = 0, nBrSeq = 0;
-      i32 runScore = 0;
-      double runMd = 0;
-      bool runHave = false;
+    for (;;) {
+      switch (fb.pc) {
+        case 0: {
+          fb.limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
+          fb.found = false;
+          fb.mk0 = scratch.mark();
+          fb.s = 0;
+          fb.pc = 1;
+          break;
+        }
+        case 1: {  // next start anchor (Explorer.cpp:905: at most 5, until one is accepted)
+          if (!(fb.s < fb.limit && !fb.found)) {
+            scratch.release(fb.mk0);
+            fb.pc = 0;
+            return fb.found ? kStepTrue : kStepFalse;
+          }
+          scratch.release(fb.mk0);
+          if (ctr) ctr->gap_attempts++;
+          const u32 whichStart = anchors[fb.s].pos;
+          u32 gapLen = 0;
+          if (dirRight & (whichStart + k < R.start)) gapLen = R.start - (whichStart + k);
+          else if (!dirRight & (L.end + k < whichStart)) gapLen = whichStart - (L.end + k);
+          fb.whichStart = whichStart;
+          fb.gapLen = gapLen;
+          fb.pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(3 * k));
+          RefView ref;
+          ref.w = rdw;
+          ref.lg = rdlg;
+          if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = R.end + k - whichStart; }
+          else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k - L.start; }
+          fb.ref = ref;
+          if (!setup_search(fb.pathMax)) { fb.pc = 0; return kStepFalse; }
+          if (!push_root(anchors[fb.s])) { fb.pc = 0; return kStepFalse; }
+          // bridges: metadata for all, sequences only for running-best record setters
+          // the reference puts no cap on recorded bridges: the caps grow with the arena (second tier: ~50 000 bridges)
+          const u32 capShare = (scratch.cap - scratch.top) / 16u;
+          u32 maxBridges = capShare / (u32)sizeof(BridgeRec);
+          if (maxBridges < 1024u) maxBridges = 1024u;
+          u32 maxKeep = capShare / (slotWords * 8u);
+          if (maxKeep < 32u) maxKeep = 32u;
+          if (maxKeep > maxBridges) maxKeep = maxBridges;
+          fb.maxBridges = maxBridges;
+          fb.maxKeep = maxKeep;
+          fb.br = scratch.alloc(maxBridges * sizeof(BridgeRec));
+          fb.brSeq = (u64*)scratch.alloc(maxKeep * slotWords * 8);
+          if (!fb.br || !fb.brSeq) { fb.pc = 0; return kStepFalse; }
+          fb.nBr = fb.nBrSeq = 0;
+          fb.runScore = 0;
+          fb.runMd = 0;
+          fb.runHave = false;
+          fb.step = 0;
+          fb.pc = 2;
+          break;
+        }
+        case 2: {  // loop head of Explorer.cpp:940
+          if (!((nCur > 0) & (nCur <= kMaxInnerPaths) & (fb.step < fb.pathMax))) { fb.pc = 4; break; }
+          const bool capped = fast_walk(fb.step, fb.pathMax, aims, nAims, false, splitWalk ? kInlineWalkSteps : ~0u);
+          fb.pc = 3;
+          if (capped && splitWalk) {  // still walking: the walk kernel carries on from cur[] and hands fb.step back in wq
+            wq.aims = aims;
+            wq.nAims = nAims;
+            wq.step = fb.step;
+            wq.pathMax = fb.pathMax;
+            wq.border = 0;
+            return kStepYield;
+          }
+          break;
+        }
+        case 3: {
+          if (!(fb.step < fb.pathMax)) { fb.pc = 4; break; }
+          if (!bridge_general_step(aims, nAims)) { fb.pc = 0; return kStepFalse; }
+          fb.pc = 2;
+          break;
+        }
+        default: {  // case 4: the attempt is over
+          finish_bridge_attempt(weakOut);
+          if (scratch.overflow || keep.overflow) { fb.pc = 0; return kStepFalse; }
+          ++fb.s;
+          fb.pc = 1;
+          break;
+        }
+      }
+    }
+  }
 
-      u32 step = 0;
-      const SeqView refv = view_of(ref);
-      while ((nCur > 0) & (nCur <= kMaxInnerPaths) & (step < pathMax)) {
-        fast_walk(step, pathMax, aims, nAims, false);
-        if (!(step < pathMax)) break;
-        // ---- oneMoreStep, Explorer.cpp:546-612
+  // ---- oneMoreStep, Explorer.cpp:546-612 (one synchronous expansion of the frontier, then pruning if due)
+  TALC_HDN bool bridge_general_step(const AnchorRec* aims, u32 nAims) {
+    const u32 k = K();
+    const RefView ref = fb.ref;
+    const SeqView refv = view_of(ref);
+    BridgeRec* br = (BridgeRec*)fb.br;
+    u64* brSeq = fb.brSeq;
+    const u32 whichStart = fb.whichStart;
+    u32 step = fb.step;
+    {
         const u32 plen = k + step;  // every trail of the frontier has this length
         if (ctr) { ctr->steps_inner++; ctr->frontier_sum += nCur; }
         nNxt = 0;
@@ -1126,7 +1229,7 @@ class Corrector {
             if (aim) {
               // recordBridge (:1097) + scoreSequence + cutAnchors evaluated now; inputs are final
               if (ctr) ctr->ev_bridge++;
-              if (nBr >= maxBridges) { scratch.overflow = 1; return false; }
+              if (fb.nBr >= fb.maxBridges) { scratch.overflow = 1; return false; }
               BridgeRec b;
               const u32 clen = plen + 1;
               b.fullLen = clen;
@@ -1146,18 +1249,18 @@ class Corrector {
                 else b.ok = false;
               } else b.ok = false;
               b.seqSlot = -1;
-              if (!runHave || fold_better(b.score, b.md, runScore, runMd)) {
-                runHave = true;
-                runScore = b.score;
-                runMd = b.md;
-                if (nBrSeq >= maxKeep) { scratch.overflow = 1; return false; }
-                u64* dst = brSeq + (u64)nBrSeq * slotWords;
+              if (!fb.runHave || fold_better(b.score, b.md, fb.runScore, fb.runMd)) {
+                fb.runHave = true;
+                fb.runScore = b.score;
+                fb.runMd = b.md;
+                if (fb.nBrSeq >= fb.maxKeep) { scratch.overflow = 1; return false; }
+                u64* dst = brSeq + (u64)fb.nBrSeq * slotWords;
                 const u64* src = slot_ptr(ch.slot);
                 TALC_ROLLED
                 for (u32 wi = 0; wi < (clen + 31) / 32; ++wi) dst[wi] = src[wi];
-                b.seqSlot = (i32)nBrSeq++;
+                b.seqSlot = (i32)fb.nBrSeq++;
               }
-              br[nBr++] = b;
+              br[fb.nBr++] = b;
               if (clen > ref.len) drop = true;  // Q10: otherwise the trail keeps exploring
             }
             if (drop) {
@@ -1171,6 +1274,7 @@ class Corrector {
           if (!parentSlotTaken) slot_free(par.slot);
         }
         ++step;
+        fb.step = step;
         if ((nNxt > P.max_branches) & (step % kCheckInterval == 0)) {
           // scoreBridges, Explorer.cpp:689-706: reference truncated to K+step+WINDOW (walk order)
           u32 bound = k + step + P.window;
@@ -1214,8 +1318,16 @@ class Corrector {
           adopt_all();
         }
         if (scratch.overflow) return false;
-      }
-      // release frontier slots (the attempt is over)
+    }
+    return true;
+  }
+
+  // Explorer.cpp:945-982: best recorded bridge of the attempt, acceptance test, corrected weak sequence
+  TALC_HDN void finish_bridge_attempt(Piece& weakOut) {
+    const u32 k = K();
+    BridgeRec* br = (BridgeRec*)fb.br;
+    const u64* brSeq = fb.brSeq;
+    const u32 nBr = fb.nBr;
       if (nBr > 0) {
         // Q9: if cutAnchors rejected some bridges the survivors are the FIRST nOk entries
         u32 nOk = 0;
@@ -1239,9 +1351,9 @@ class Corrector {
             R.start = B.rightAnchor;
             // corrected weak sequence = path without its two anchors, in read orientation
             u8* dst = (u8*)keep.alloc(bestLen ? bestLen : 1);
-            if (!dst) return false;
+            if (!dst) return;
             if (bestLen > 0) {
-              if (B.seqSlot < 0) { scratch.overflow = 1; return false; }  // cannot happen: see fold argument
+              if (B.seqSlot < 0) { scratch.overflow = 1; return; }  // cannot happen: see fold argument
               const u64* w = brSeq + (u64)B.seqSlot * slotWords;
               PathView pv; pv.w = w; pv.len = B.fullLen;
               TALC_ROLLED
@@ -1252,13 +1364,10 @@ class Corrector {
             }
             weakOut.off = (u32)(dst - keep.base);
             weakOut.len = (i32)bestLen;
-            found = true;
+            fb.found = true;
           }
         }
       }
-    }
-    scratch.release(mk0);
-    return found;
   }
 
   // ------------------------------------------------------------------ border search
@@ -1395,49 +1504,91 @@ class Corrector {
     return true;
   }
 
-  // Explorer::searchEdge, Explorer.cpp:992-1081
-  TALC_HDN bool search_edge(Piece& weakOut) {
+  // Explorer::searchEdge, Explorer.cpp:992-1081.  Resumable like search_bridge (fe.pc == 0 starts a new search).
+  TALC_HDN u8 search_edge(Piece& weakOut) {
     const u32 k = K();
     const AnchorRec* anchors = dirRight ? ancL : ancR;
     const u32 nAnch = dirRight ? nAncL : nAncR;
-    const u32 limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
-    // running bests of m_longPaths / m_shortPaths across all anchors
-    u32 maxGap = 0;
-    TALC_ROLLED
-    for (u32 s = 0; s < limit; ++s) {
-      const u32 g = (location == 0) ? anchors[s].pos : (rd.len - (anchors[s].pos + k));
-      maxGap = g > maxGap ? g : maxGap;
+    for (;;) {
+      switch (fe.pc) {
+        case 0: {
+          fe.limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
+          // running bests of m_longPaths / m_shortPaths across all anchors
+          u32 maxGap = 0;
+          TALC_ROLLED
+          for (u32 s = 0; s < fe.limit; ++s) {
+            const u32 g = (location == 0) ? anchors[s].pos : (rd.len - (anchors[s].pos + k));
+            maxGap = g > maxGap ? g : maxGap;
+          }
+          const u32 maxPath = (u32)(i32)(1.2 * (double)maxGap + (double)(2 * k));
+          const u32 bestWords = (k + maxPath + 2 + 31) / 32 + 1;
+          fe.bestLong.have = fe.bestShort.have = false;
+          fe.bestLong.seq = (u64*)scratch.alloc(bestWords * 8);
+          fe.bestShort.seq = (u64*)scratch.alloc(bestWords * 8);
+          if (!fe.bestLong.seq || !fe.bestShort.seq) return kStepFalse;
+          fe.mk0 = scratch.mark();
+          fe.s = 0;
+          fe.pc = 1;
+          break;
+        }
+        case 1: {  // next start anchor: EVERY anchor is searched (Explorer.cpp:1028)
+          if (!(fe.s < fe.limit)) {
+            fe.pc = 0;
+            return finish_edge_search(weakOut) ? kStepTrue : kStepFalse;
+          }
+          scratch.release(fe.mk0);
+          fe.xdrop = (int)((int)kCheckInterval * 0.3 + 1);  // Q15: 2
+          const u32 whichStart = anchors[fe.s].pos;
+          const u32 gapLen = (location == 0) ? whichStart : (rd.len - (whichStart + k));
+          fe.whichStart = whichStart;
+          fe.pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(2 * k));
+          RefView ref;
+          ref.w = rdw;
+          ref.lg = rdlg;
+          if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = rd.len - whichStart; }
+          else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k; }
+          fe.ref = ref;
+          if (!setup_search(fe.pathMax)) { fe.pc = 0; return kStepFalse; }
+          if (!push_root(anchors[fe.s])) { fe.pc = 0; return kStepFalse; }
+          fe.step = 0;
+          fe.pc = 2;
+          break;
+        }
+        case 2: {  // loop head of Explorer.cpp:1055
+          if (!((nCur > 0) & (nCur <= kMaxInnerPaths) & (fe.step < fe.pathMax))) { ++fe.s; fe.pc = 1; break; }
+          const bool capped = fast_walk(fe.step, fe.pathMax, nullptr, 0, true, splitWalk ? kInlineWalkSteps : ~0u);
+          fe.pc = 3;
+          if (capped && splitWalk) {
+            wq.aims = nullptr;
+            wq.nAims = 0;
+            wq.step = fe.step;
+            wq.pathMax = fe.pathMax;
+            wq.border = 1;
+            return kStepYield;
+          }
+          break;
+        }
+        default: {  // case 3
+          if (!(fe.step < fe.pathMax)) { ++fe.s; fe.pc = 1; break; }
+          if (!edge_general_step()) { fe.pc = 0; return kStepFalse; }
+          fe.pc = 2;
+          break;
+        }
+      }
     }
-    const u32 maxPath = (u32)(i32)(1.2 * (double)maxGap + (double)(2 * k));
-    const u32 bestWords = (k + maxPath + 2 + 31) / 32 + 1;
-    EdgeBest bestLong, bestShort;
-    bestLong.have = bestShort.have = false;
-    bestLong.seq = (u64*)scratch.alloc(bestWords * 8);
-    bestShort.seq = (u64*)scratch.alloc(bestWords * 8);
-    if (!bestLong.seq || !bestShort.seq) return false;
-    const u32 mk0 = scratch.mark();
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (u32 s = 0; s < limit; ++s) {
-      scratch.release(mk0);
-      int xdrop = (int)((int)kCheckInterval * 0.3 + 1);  // Q15: 2
-      const u32 whichStart = anchors[s].pos;
-      const u32 gapLen = (location == 0) ? whichStart : (rd.len - (whichStart + k));
-      const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(2 * k));
-      RefView ref;
-      ref.w = rdw;
-      ref.lg = rdlg;
-      if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = rd.len - whichStart; }
-      else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k; }
-      const SeqView refv = view_of(ref);
-      if (!setup_search(pathMax)) return false;
-      if (!push_root(anchors[s])) return false;
-      u32 step = 0;
-      while ((nCur > 0) & (nCur <= kMaxInnerPaths) & (step < pathMax)) {
-        fast_walk(step, pathMax, nullptr, 0, true);
-        if (!(step < pathMax)) break;
-        // ---- oneMoreStepInTheDark, Explorer.cpp:615-687
+  }
+
+  // ---- oneMoreStepInTheDark, Explorer.cpp:615-687
+  TALC_HDN bool edge_general_step() {
+    const u32 k = K();
+    const RefView ref = fe.ref;
+    const SeqView refv = view_of(ref);
+    const u32 whichStart = fe.whichStart, pathMax = fe.pathMax;
+    EdgeBest& bestLong = fe.bestLong;
+    EdgeBest& bestShort = fe.bestShort;
+    int xdrop = fe.xdrop;
+    u32 step = fe.step;
+    {
         const u32 plen = k + step;
         if (ctr) { ctr->steps_border++; ctr->frontier_sum += nCur; }
         nNxt = 0;
@@ -1500,8 +1651,10 @@ class Corrector {
           if (!parentSlotTaken) slot_free(par.slot);
         }
         ++step;
+        fe.step = step;
         if ((step % kCheckInterval == 0) || (nNxt >= kMaxBorderPaths)) {
           if (!score_edges(xdrop, k + step, ref, whichStart, bestLong, bestShort)) return false;
+          fe.xdrop = xdrop;
           if (nNxt > 5) {
             const u32 mkg = scratch.mark();
             u32* kept = (u32*)scratch.alloc((nNxt + P.max_branches + 1) * 4);
@@ -1516,8 +1669,15 @@ class Corrector {
         } else
           adopt_all();
         if (scratch.overflow) return false;
-      }
     }
+    return true;
+  }
+
+  // sortOutBestBorder (Explorer.cpp:310-329) + the acceptance test of :1063-1076
+  TALC_HDN bool finish_edge_search(Piece& weakOut) {
+    const u32 k = K();
+    const EdgeBest& bestLong = fe.bestLong;
+    const EdgeBest& bestShort = fe.bestShort;
     bool found = false;
     if (bestLong.have || bestShort.have) {
       const EdgeBest& W = bestLong.have ? bestLong : bestShort;  // sortOutBestBorder, :310-329
@@ -1556,8 +1716,141 @@ class Corrector {
   }
 
   // ------------------------------------------------------------------ per-read driver (main.cpp:258-296)
-  // Returns the status; on kReadOk the pieces describe the corrected read.
-  TALC_HDN u8 run(const ReadJob& job) {
+  // start() sets the read up and runs it; resume() continues after a yield (the walk kernel has advanced cur[] and
+  // wq.step).  Both return a ReadStatus, or kReadYield when the read waits for the walk kernel.  On kReadOk the
+  // pieces describe the corrected read.
+  TALC_HDN u8 start(const ReadJob& job) {
+    job_ = job;
+    fr.pc = 0;
+    fb.pc = 0;
+    fe.pc = 0;
+    return resume();
+  }
+  TALC_HDN u8 run(const ReadJob& job) {  // never yields: the walk is taken inline (host emulation, tuning builds)
+    splitWalk = 0;
+    return start(job);
+  }
+  // what the walk kernel (or its host stand-in) reports back
+  TALC_HD void walk_done(u32 step) {
+    if (location == 1) fb.step = step;
+    else fe.step = step;
+  }
+  TALC_HDN u8 resume() {
+    const u32 k = K();
+    for (;;) {
+      switch (fr.pc) {
+        case 0: {
+          const u8 st = prepare_read();
+          if (st != kReadOk) return st;
+          fr.reg = 0;
+          fr.pc = 1;
+          break;
+        }
+        case 1: {  // Read::correct2 (Read.cpp:336-386): the gaps in order
+          if (!(fr.reg + 1 < nregs)) { fr.pc = 5; break; }
+          if (ctr) ctr->gaps++;
+          fr.success = false;
+          fr.attempt = 0;
+          fr.pc = 2;
+          break;
+        }
+        case 2: {  // RIGHT-ward attempt, then LEFT-ward on failure (Read.cpp:350-355)
+          if (!(fr.attempt < 2 && !fr.success)) { fr.pc = 4; break; }
+          // initializeINNER (Explorer.cpp:228-243)
+          scratch.release(0);
+          location = 1;
+          dirRight = (fr.attempt == 0);
+          L = regs[fr.reg];
+          R = regs[fr.reg + 1];
+          weakLen = R.start - (L.end + k);
+          if (!build_anchors(true) || !build_anchors(false)) return kReadOverflow;
+          fb.pc = 0;
+          fr.pc = 3;
+          break;
+        }
+        case 3: {
+          Piece w;
+          const u8 r = search_bridge(w);
+          if (r == kStepYield) return kReadYield;
+          fr.success = (r == kStepTrue);
+          if (scratch.overflow || keep.overflow) return kReadOverflow;
+          if (fr.success) gapPiece[fr.reg] = w;
+          ++fr.attempt;
+          fr.pc = 2;
+          break;
+        }
+        case 4: {
+          if (fr.success && ctr) ctr->gaps_bridged++;
+          regs[fr.reg] = L;  // updateINNER (Read.cpp:294-303)
+          regs[fr.reg + 1] = R;
+          ++fr.reg;
+          fr.pc = 1;
+          break;
+        }
+        case 5: {  // HEAD (Read.cpp:361-367); region 0's start is untouched by the inner gaps
+          const u32 headLen = headRaw;
+          if (!(headPresent && headLen <= kBorderMaxLen)) { fr.pc = 7; break; }
+          if (ctr) ctr->borders++;
+          scratch.release(0);
+          location = 0;
+          dirRight = false;
+          L.start = L.end = 0;
+          R = regs[0];
+          weakLen = R.start;
+          nAncL = 0;
+          if (!build_anchors(false)) return kReadOverflow;
+          fe.pc = 0;
+          fr.pc = 6;
+          break;
+        }
+        case 6: {
+          Piece w;
+          const u8 r = search_edge(w);
+          if (r == kStepYield) return kReadYield;
+          if (scratch.overflow || keep.overflow) return kReadOverflow;
+          if (r == kStepTrue) {
+            if (ctr) ctr->borders_corrected++;
+            regs[0] = R;  // updateHEAD (Read.cpp:305-311)
+            headPiece = w;
+          }
+          fr.pc = 7;
+          break;
+        }
+        case 7: {  // TAIL (Read.cpp:368-374)
+          const u32 tailLen = tailRaw;
+          if (!(tailPresent && tailLen <= kBorderMaxLen)) return kReadOk;
+          if (ctr) ctr->borders++;
+          scratch.release(0);
+          location = 2;
+          dirRight = true;
+          R.start = R.end = 0;
+          L = regs[nregs - 1];
+          weakLen = rd.len - (L.end + k);
+          nAncR = 0;
+          if (!build_anchors(true)) return kReadOverflow;
+          fe.pc = 0;
+          fr.pc = 8;
+          break;
+        }
+        default: {  // case 8
+          Piece w;
+          const u8 r = search_edge(w);
+          if (r == kStepYield) return kReadYield;
+          if (scratch.overflow || keep.overflow) return kReadOverflow;
+          if (r == kStepTrue) {
+            if (ctr) ctr->borders_corrected++;
+            regs[nregs - 1] = L;  // updateTAIL (Read.cpp:313-318)
+            tailPiece = w;
+          }
+          return kReadOk;
+        }
+      }
+    }
+  }
+
+  // everything of main.cpp:258-296 that precedes correct2: packing, the reCoverage gate, defineStructure2
+  TALC_HDN u8 prepare_read() {
+    const ReadJob& job = job_;
     rd = job.rd;
     cov = job.cov;
     wide = job.wide;
@@ -1615,70 +1908,6 @@ class Corrector {
     for (u32 i = 0; i + 1 < nregs; ++i) gapPiece[i].len = -1;
     headPiece.len = tailPiece.len = -1;
     complexRegion = false;
-    // Read::correct2 (Read.cpp:336-386)
-    TALC_ROLLED
-    for (u32 reg = 0; reg + 1 < nregs; ++reg) {
-      if (ctr) ctr->gaps++;
-      bool success = false;
-      TALC_ROLLED
-      for (int attempt = 0; attempt < 2 && !success; ++attempt) {
-        // initializeINNER (Explorer.cpp:228-243)
-        scratch.release(0);
-        location = 1;
-        dirRight = (attempt == 0);
-        L = regs[reg];
-        R = regs[reg + 1];
-        weakLen = R.start - (L.end + k);
-        if (!build_anchors(true) || !build_anchors(false)) return kReadOverflow;
-        Piece w;
-        success = search_bridge(w);
-        if (scratch.overflow || keep.overflow) return kReadOverflow;
-        if (success) gapPiece[reg] = w;
-      }
-      if (success && ctr) ctr->gaps_bridged++;
-      regs[reg] = L;  // updateINNER (Read.cpp:294-303)
-      regs[reg + 1] = R;
-    }
-    const u32 headLen = headRaw;  // region 0's start is untouched by the inner gaps
-    if (headPresent && headLen <= kBorderMaxLen) {
-      if (ctr) ctr->borders++;
-      scratch.release(0);
-      location = 0;
-      dirRight = false;
-      L.start = L.end = 0;
-      R = regs[0];
-      weakLen = R.start;
-      nAncL = 0;
-      if (!build_anchors(false)) return kReadOverflow;
-      Piece w;
-      const bool ok = search_edge(w);
-      if (scratch.overflow || keep.overflow) return kReadOverflow;
-      if (ok) {
-        if (ctr) ctr->borders_corrected++;
-        regs[0] = R;  // updateHEAD (Read.cpp:305-311)
-        headPiece = w;
-      }
-    }
-    const u32 tailLen = tailRaw;
-    if (tailPresent && tailLen <= kBorderMaxLen) {
-      if (ctr) ctr->borders++;
-      scratch.release(0);
-      location = 2;
-      dirRight = true;
-      R.start = R.end = 0;
-      L = regs[nregs - 1];
-      weakLen = rd.len - (L.end + k);
-      nAncR = 0;
-      if (!build_anchors(true)) return kReadOverflow;
-      Piece w;
-      const bool ok = search_edge(w);
-      if (scratch.overflow || keep.overflow) return kReadOverflow;
-      if (ok) {
-        if (ctr) ctr->borders_corrected++;
-        regs[nregs - 1] = L;  // updateTAIL (Read.cpp:313-318)
-        tailPiece = w;
-      }
-    }
     return kReadOk;
   }
 

@@ -71,7 +71,8 @@ enum ReadStatus : u8 {
   kReadNoStructure = 2,  // "Unable to define convenient structure."
   kReadShort = 3,        // len <= K : untouched, not logged
   kReadResource = 4,     // not in the reference: the read exhausted even the last scratch tier and passes through uncorrected
-  kReadOverflow = 250    // internal: scratch arena too small, re-run with a larger arena
+  kReadOverflow = 250,   // internal: scratch arena too small, re-run with a larger arena
+  kReadYield = 251       // internal: the read waits for the walk kernel (its context stays in HBM)
 };
 
 // Dna5 code of an input character (SeqAn char -> Dna5): ACGT either case, U -> T, else N(4).

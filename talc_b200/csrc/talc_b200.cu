@@ -14,6 +14,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cub/cub.cuh>
 #include <string>
 #include <thread>
@@ -22,6 +23,7 @@
 
 #include "../../include/talc_b200.h"
 #include "correct.cuh"
+#include "walk.cuh"
 #include "count_gpu.cuh"
 #include "dump_gpu.cuh"
 #include "dump_parse.hpp"
@@ -397,6 +399,176 @@ __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) correct_kernel(CorrectAr
   }
 }
 
+// ---- the same per-read program, suspendable: read contexts live in HBM, a round of control_kernel runs every ready
+// context until its read is done (the context then takes the next read of the queue) or until it yields a long walk
+// to walk_kernel (walk.cuh); walk_kernel advances the frontiers and hands the contexts back.  Rounds alternate until
+// every read of the batch is done (host loop in run_split_rounds).
+struct RoundArgs {
+  CorrectArgs A;
+  ReadCtx* ctxs;
+  const u32* readyList;
+  const u32* nReady;
+  u32* walkList;
+  u32* nWalk;
+  u32* taskCursor;
+  u32* finished;  // reads of this pass that are done (corrected, failed, or deferred to the next tier)
+};
+
+__global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) control_kernel(RoundArgs R) {
+  __shared__ Corrector cxs[TALC_WARPS_PER_BLOCK];
+  __shared__ Counters mines[TALC_WARPS_PER_BLOCK];
+  const CorrectArgs& A = R.A;
+  const u32 lane = threadIdx.x & 31;
+  const u32 wib = (threadIdx.x >> 5) % TALC_WARPS_PER_BLOCK;
+  Corrector& cx = cxs[wib];
+  Counters& mine = mines[wib];
+  const u32 nReady = *R.nReady;
+  for (;;) {
+    u32 qi = 0;
+    if (lane == 0) qi = atomicAdd(R.taskCursor, 1u);
+    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if (qi >= nReady) break;
+    const u32 id = R.readyList[qi];
+    ReadCtx* rc = R.ctxs + id;
+    u8* const myArena = A.arenas + (u64)id * (u64)A.arenaBytes;
+    __syncwarp();
+    u32 r = rc->read;
+    u8 st = kReadYield;
+    bool have = false;
+    if (r != kCtxFree) {  // resume a suspended read from its context
+      {
+        const u32* src = (const u32*)&rc->cx;
+        u32* dst = (u32*)&cx;
+        for (u32 i = lane; i < sizeof(Corrector) / 4; i += 32) dst[i] = src[i];
+        const u32* s2 = (const u32*)&rc->ctr;
+        u32* d2 = (u32*)&mine;
+        for (u32 i = lane; i < sizeof(Counters) / 4; i += 32) d2[i] = s2[i];
+      }
+      __syncwarp();
+      cx.ctr = &mine;
+      cx.walk_done(cx.wq.step);
+      __syncwarp();
+      st = cx.resume();
+      __syncwarp();
+      have = true;
+    }
+    for (;;) {
+      if (have) {
+        if (st == kReadYield) {  // suspend: context back to HBM, frontier to the walk kernel
+          __syncwarp();
+          {
+            const u32* src = (const u32*)&cx;
+            u32* dst = (u32*)&rc->cx;
+            for (u32 i = lane; i < sizeof(Corrector) / 4; i += 32) dst[i] = src[i];
+            const u32* s2 = (const u32*)&mine;
+            u32* d2 = (u32*)&rc->ctr;
+            for (u32 i = lane; i < sizeof(Counters) / 4; i += 32) d2[i] = s2[i];
+          }
+          if (lane == 0) {
+            rc->read = r;
+            const u32 pos = atomicAdd(R.nWalk, 1u);
+            R.walkList[pos] = id;
+          }
+          __syncwarp();
+          break;
+        }
+        // ---- the read is done: same epilogue as correct_kernel
+        if (st == kReadOverflow && A.lastTier) {
+          st = kReadResource;
+          if (lane == 0) mine.reads_overflow += 1;
+        }
+        if (A.readStats && lane == 0 && st != kReadOverflow) {
+          u32 span = 0, nr = 0;
+          if (st == kReadOk || st == kReadNoStructure || st == kReadResource) {
+            nr = cx.nregs;
+            for (u32 i = 0; i < nr; ++i) span += cx.regs[i].end - cx.regs[i].start + 1;
+          }
+          A.readStats[2 * r] = span;
+          A.readStats[2 * r + 1] = nr;
+        }
+        if (st == kReadOverflow) {
+          if (lane == 0) {
+            A.status[r] = st;
+            const u32 slot = atomicAdd(A.nOverflow, 1u);
+            A.overflowList[slot] = r;
+          }
+        } else {
+          const u32 rlen = (u32)(A.offs[r + 1] - A.offs[r]);
+          const u32 olen = (st == kReadOk) ? cx.corrected_length() : rlen;
+          unsigned long long pos = 0;
+          if (lane == 0) pos = atomicAdd(A.outCursor, (unsigned long long)olen);
+          pos = __shfl_sync(0xffffffffu, pos, 0);
+          if (pos + olen <= A.outCap) {
+            u8* dst = A.outArena + pos;
+            if (st == kReadOk) cx.emit(dst, lane, 32);
+            else {
+              const u8* src = A.bases + A.offs[r];
+              for (u32 i = lane; i < rlen; i += 32) dst[i] = code_char(base_code(src[i]));
+            }
+          } else if (lane == 0) {
+            atomicExch(A.outFull, 1u);
+          }
+          if (lane == 0) {
+            A.outPos[r] = pos;
+            A.outLen[r] = olen;
+            A.status[r] = st;
+            mine.cells_nw += cx.dps.cells_nw;
+            mine.cells_lcs += cx.dps.cells_lcs;
+            mine.cells_ovl += cx.dps.cells_ovl;
+            mine.cells_xdrop += cx.dps.cells_xdrop;
+            mine.bases_out += olen;
+            if (st == kReadOk) mine.reads_ok += 1;
+            for (int i = 0; i < kNumCounters; ++i) {
+              const u64 v = ((const u64*)&mine)[i];
+              if (v) atomicAdd(A.counters + i, (unsigned long long)v);
+            }
+          }
+        }
+        if (lane == 0) atomicAdd(R.finished, 1u);
+        __syncwarp();
+      }
+      // ---- this context takes the next read of the queue (most expensive first)
+      u32 wi = 0;
+      if (lane == 0) wi = atomicAdd(A.workCounter, 1u);
+      wi = __shfl_sync(0xffffffffu, wi, 0);
+      if (wi >= A.nOrder) {
+        if (lane == 0) rc->read = kCtxFree;
+        __syncwarp();
+        break;
+      }
+      r = A.order[wi];
+      __syncwarp();
+      cx.T = A.tv;
+      cx.CR = A.cright;
+      cx.CL = A.cleft;
+      cx.P = A.P;
+      cx.tabs = A.tabs;
+      cx.splitWalk = 1;
+      for (int i = 0; i < kNumCounters; ++i) ((u64*)&mine)[i] = 0;
+      cx.ctr = &mine;
+      ReadJob job;
+      job.rd.s = A.bases + A.offs[r];
+      job.rd.len = (u32)(A.offs[r + 1] - A.offs[r]);
+      job.cov = A.cov + A.kmerOff[r];
+      job.arena = myArena;
+      job.arena_bytes = A.arenaBytes;
+      job.wide = A.wide != 0;
+      __syncwarp();
+      st = cx.start(job);
+      __syncwarp();
+      have = true;
+    }
+  }
+}
+__global__ void ctx_init_kernel(ReadCtx* ctxs, u32 nCtx, u32* readyList, u32* nReady) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nCtx) {
+    ctxs[i].read = kCtxFree;
+    readyList[i] = i;
+  }
+  if (i == 0) *nReady = nCtx;
+}
+
 // corrected reads from allocation order into input order; one warp per read, 16-byte chunks
 __global__ void gather_kernel(const u8* __restrict__ arena, const u64* __restrict__ pos, const u32* __restrict__ len,
                               const u64* __restrict__ outOff, u32 n, u8* __restrict__ out) {
@@ -573,10 +745,14 @@ struct talc_ctx {
   u32 tier2Bytes = 64u << 20;
   u32 tier2Warps = 128;
   u32 blocksPerSm = TALC_MIN_BLOCKS;
+  u32 splitWalk = 0;       // 1: suspendable reads + walk kernel (rounds), 0: one monolithic correct_kernel launch
+  u32 nCtxTier1 = 16384;   // read contexts in flight (each with a tier-1 arena)
+  u32 walkStepCap = 48;    // steps a frontier may take per round of the walk kernel (bounds the round's tail)
+  u64 lastRounds = 0;
   double* modelTabs = nullptr;  // 3 x kModelTabN doubles
   // cached device buffers
   DevBuf bases, offs, kmerOff, nk, cov, order, sortKey, sortKeyOut, sortVal, cubTmp, arenas, outArena, outPos, outLen,
-      outLen64, status, outOffs, out, misc, overflowList;
+      outLen64, status, outOffs, out, misc, overflowList, readCtxs, roundLists;
 };
 
 static const u32 kModelTabN = 16384;
@@ -677,6 +853,9 @@ int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out) {
                                                                   c->modelTabs + 2 * kModelTabN);
   cudaStreamSynchronize(c->stream);
   if (const char* e2 = getenv("TALC_BLOCKS_PER_SM")) c->blocksPerSm = (u32)std::max(1, atoi(e2));
+  if (const char* e2 = getenv("TALC_SPLIT")) c->splitWalk = atoi(e2) != 0;
+  if (const char* e2 = getenv("TALC_CTX")) c->nCtxTier1 = (u32)std::max(4, atoi(e2));
+  if (const char* e2 = getenv("TALC_WALK_CAP")) c->walkStepCap = (u32)std::max(1, atoi(e2));
   *out = c;
   return TALC_OK;
 }
@@ -690,7 +869,7 @@ void talc_ctx_destroy(talc_ctx* c) {
   if (c->modelTabs) cudaFree(c->modelTabs);
   DevBuf* bufs[] = {&c->bases, &c->offs, &c->kmerOff, &c->nk, &c->cov, &c->order, &c->sortKey, &c->sortKeyOut, &c->sortVal,
                     &c->cubTmp, &c->arenas, &c->outArena, &c->outPos, &c->outLen, &c->outLen64, &c->status, &c->outOffs,
-                    &c->out, &c->misc, &c->overflowList};
+                    &c->out, &c->misc, &c->overflowList, &c->readCtxs, &c->roundLists};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
@@ -702,6 +881,16 @@ int talc_ctx_set_scratch(talc_ctx* c, uint32_t tier1_bytes, uint32_t tier2_bytes
   if (tier1_bytes) c->tier1Bytes = (tier1_bytes + 255u) & ~255u;
   if (tier2_bytes) c->tier2Bytes = (tier2_bytes + 255u) & ~255u;
   if (tier2_threads) c->tier2Warps = (tier2_threads + 3u) & ~3u;
+  return TALC_OK;
+}
+
+// execution shape of the correction (0 keeps a value): split_walk 1 = suspendable reads + walk kernel, 2 = one
+// monolithic kernel (the round-1 shape, kept for A/B measurements); read_contexts in flight; steps per walk round
+int talc_ctx_set_exec(talc_ctx* c, uint32_t split_walk, uint32_t read_contexts, uint32_t walk_step_cap) {
+  if (!c) return TALC_ERR_ARG;
+  if (split_walk) c->splitWalk = split_walk == 1 ? 1u : 0u;
+  if (read_contexts) c->nCtxTier1 = read_contexts < 4 ? 4 : read_contexts;
+  if (walk_step_cap) c->walkStepCap = walk_step_cap;
   return TALC_OK;
 }
 
@@ -1301,6 +1490,67 @@ int talc_table_lookup(talc_ctx* c, const uint64_t* keys, uint64_t n, uint32_t* c
   return TALC_OK;
 }
 
+// One pass of the correction over the reads of A.order (tier 1: the whole batch; tier 2: the reads whose arena was too
+// small).  Split mode alternates control_kernel and walk_kernel until every read of the pass is done; the host only
+// enqueues rounds and polls one counter every few rounds.  nCtx contexts are in flight, each with its own arena.
+static int run_pass(talc_ctx* c, CorrectArgs& A, u32 nCtx, u64* launches) {
+  const u32 n = A.nOrder;
+  if (!c->splitWalk) {
+    u32 blocks = (nCtx + 3) / 4;
+    correct_kernel<<<blocks, 128, 0, c->stream>>>(A);
+    CUDA_TRY(c, cudaGetLastError());
+    if (launches) *launches += 1;
+    return TALC_OK;
+  }
+  CUDA_TRY(c, c->readCtxs.reserve((size_t)nCtx * sizeof(ReadCtx)));
+  CUDA_TRY(c, c->roundLists.reserve((size_t)nCtx * 8 + 256));
+  ReadCtx* ctxs = (ReadCtx*)c->readCtxs.p;
+  u32* dCnt = (u32*)c->roundLists.p;  // [0] nReady, [1] nWalk, [2] taskCursor, [3] finished
+  u32* readyList = dCnt + 64;
+  u32* walkList = readyList + nCtx;
+  CUDA_TRY(c, cudaMemsetAsync(dCnt, 0, 256, c->stream));
+  ctx_init_kernel<<<(nCtx + 255) / 256, 256, 0, c->stream>>>(ctxs, nCtx, readyList, dCnt);
+  CUDA_TRY(c, cudaGetLastError());
+  RoundArgs R;
+  R.A = A;
+  R.ctxs = ctxs;
+  R.readyList = readyList;
+  R.nReady = dCnt;
+  R.walkList = walkList;
+  R.nWalk = dCnt + 1;
+  R.taskCursor = dCnt + 2;
+  R.finished = dCnt + 3;
+  u32 ctlBlocks = (u32)c->sms * c->blocksPerSm;
+  if (ctlBlocks * 4 > nCtx) ctlBlocks = (nCtx + 3) / 4;
+  u32 walkBlocks = (u32)c->sms * 4;
+  if (walkBlocks * 32 > nCtx) walkBlocks = (nCtx + 31) / 32;
+  u64 rounds = 0;
+  u32 hFinished = 0;
+  u32 chunk = 8;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    for (u32 i = 0; i < chunk; ++i) {
+      CUDA_TRY(c, cudaMemsetAsync(dCnt + 1, 0, 8, c->stream));  // nWalk, taskCursor
+      control_kernel<<<ctlBlocks, 128, 0, c->stream>>>(R);
+      CUDA_TRY(c, cudaMemsetAsync(dCnt, 0, 4, c->stream));      // nReady
+      walk_kernel<<<walkBlocks, 256, 0, c->stream>>>(ctxs, walkList, dCnt + 1, readyList, dCnt, c->walkStepCap);
+    }
+    rounds += chunk;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(&hFinished, dCnt + 3, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (hFinished >= n) break;
+    if (chunk < 64) chunk *= 2;
+    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 600.0) {
+      c->err = "correction rounds did not terminate within 600 s (" + std::to_string(hFinished) + " of " + std::to_string(n) + " reads done)";
+      return TALC_ERR_CUDA;
+    }
+  }
+  c->lastRounds += rounds;
+  if (launches) *launches += 2 * rounds + 1;
+  return TALC_OK;
+}
+
 // ---------------------------------------------------------------------------------- correction
 // shared front end: k-mer offsets, length-sorted order, coverage.  d_bases/d_offs on device.
 static int prepare_batch(talc_ctx* c, const u8* dBases, const u64* dOffs, u32 n, u64 totalBases, u64& totalKmers) {
@@ -1368,12 +1618,12 @@ static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const u
   int rc = prepare_batch(c, dBases, dOffs, n, totalBases, totalKmers);
   if (rc) return rc;
 
-  // launch geometry: 128-thread blocks (4 warps = 4 reads in flight per block), a multiple of the SM count,
-  // no more warps than there are reads
+  // launch geometry.  Monolithic mode: 128-thread blocks (4 warps = 4 reads in flight per block), a multiple of the
+  // SM count, no more warps than there are reads.  Split mode: nCtx read contexts in flight, each with its own arena.
   u32 blocksPerSm = c->blocksPerSm;
   u32 blocks = (u32)c->sms * blocksPerSm;
   while (blocks > (u32)c->sms && (u64)(blocks - c->sms) * 4 >= n) blocks -= c->sms;
-  const u64 nWarps = (u64)blocks * 4;
+  const u64 nWarps = c->splitWalk ? (u64)std::min<u32>(n, c->nCtxTier1) : (u64)blocks * 4;
   const u64 outArenaCap = 2 * totalBases + (u64)n * 64 + 4096;
   CUDA_TRY(c, c->arenas.reserve(std::max<size_t>((size_t)nWarps * c->tier1Bytes, (size_t)c->tier2Warps * c->tier2Bytes)));
   CUDA_TRY(c, c->outArena.reserve(outArenaCap));
@@ -1429,13 +1679,16 @@ static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const u
   }
   A.wide = 1;
   A.lastTier = 0;
-  correct_kernel<<<blocks, 128, 0, c->stream>>>(A);
-  CUDA_TRY(c, cudaGetLastError());
+  u64 launches = 3;
+  c->lastRounds = 0;
+  {
+    const int rcp = run_pass(c, A, (u32)nWarps, &launches);
+    if (rcp) return rcp;
+  }
   CUDA_TRY(c, cudaEventRecord(c->ev[3], c->stream));
   u32 hOver = 0;
   CUDA_TRY(c, cudaMemcpyAsync(&hOver, dNOver, 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  u64 launches = 4;
   if (hOver > 0) {
     // second tier: only the reads whose first-tier slice was too small, worst-case buffer sizing
     CUDA_TRY(c, cudaMemsetAsync(dWork, 0, 8, c->stream));  // workCounter and nOverflow
@@ -1447,10 +1700,8 @@ static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const u
     B.nOrder = hOver;
     B.arenaBytes = c->tier2Bytes;
     B.lastTier = 1;
-    u32 b2 = std::max<u32>(1, std::min<u32>(c->tier2Warps / 4, (hOver + 3) / 4));
-    correct_kernel<<<b2, 128, 0, c->stream>>>(B);
-    CUDA_TRY(c, cudaGetLastError());
-    launches++;
+    const int rcp = run_pass(c, B, std::max<u32>(1, std::min<u32>(c->tier2Warps, hOver)), &launches);
+    if (rcp) return rcp;
   }
   CUDA_TRY(c, cudaEventRecord(c->ev[4], c->stream));
   // input order: exclusive scan of the lengths, then gather
@@ -1501,6 +1752,7 @@ static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const u
     counters->bases_in = totalBases;
     counters->reads_second_tier = hOver;
     counters->kernel_launches = launches + 3;
+    counters->rounds = c->lastRounds;
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); counters->ms_coverage = ms;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); counters->ms_correct = ms;

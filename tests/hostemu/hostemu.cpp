@@ -93,6 +93,8 @@ void* emu_table_build(const emu_params* q, const uint64_t* keys, const int64_t* 
 }
 void emu_table_free(void* t) { delete (EmuTable*)t; }
 
+static uint64_t g_yields = 0;
+uint64_t emu_yields() { return g_yields; }
 int emu_correct_reads(void* tab, const emu_params* q, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
                       uint32_t arena_bytes, int wide, uint8_t* out, uint64_t out_capacity, uint64_t* out_offsets,
                       uint8_t* status, uint64_t* counters /* kNumCounters */) {
@@ -135,8 +137,23 @@ int emu_correct_reads(void* tab, const emu_params* q, const uint8_t* bases, cons
     job.cov = cov.data();
     job.arena = arena.data();
     job.arena_bytes = arena_bytes;
-    job.wide = wide != 0;
-    u8 st = cx->run(job);
+    job.wide = (wide & 1) != 0;
+    u8 st;
+    if (wide & 2) {
+      // split mode: the read yields where a long walk starts; the "walk kernel" is the scalar fast path run to its end,
+      // then the read resumes from its frames -- the suspend / resume protocol of the device, on one thread
+      cx->splitWalk = 1;
+      st = cx->start(job);
+      while (st == kReadYield) {
+        ++g_yields;
+        u32 step = cx->wq.step;
+        cx->fast_walk_scalar(step, cx->wq.pathMax, cx->wq.aims, cx->wq.nAims, cx->wq.border != 0, ~0u);
+        cx->walk_done(step);
+        st = cx->resume();
+      }
+    } else {
+      st = cx->run(job);
+    }
     mine.cells_nw += cx->dps.cells_nw;
     mine.cells_lcs += cx->dps.cells_lcs;
     mine.cells_ovl += cx->dps.cells_ovl;

@@ -47,6 +47,7 @@ def lib():
         L.emu_table_free.argtypes = [C.c_void_p]
         L.emu_correct_reads.argtypes = [C.c_void_p, C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                         C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_yields.restype = C.c_uint64
         L.emu_nw.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
         L.emu_lcs.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
         L.emu_overlap.argtypes = [C.c_char_p, C.c_char_p]
@@ -91,7 +92,7 @@ class EmuTable:
         except Exception:
             pass
 
-    def correct(self, reads, offsets, arena_bytes=48 * 1024, wide=False):
+    def correct(self, reads, offsets, arena_bytes=48 * 1024, wide=False, split=False):
         reads = np.ascontiguousarray(reads, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
@@ -100,7 +101,7 @@ class EmuTable:
         ooff = np.zeros(n + 1, dtype=np.uint64)
         status = np.zeros(max(n, 1), dtype=np.uint8)
         ctr = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
-        rc = lib().emu_correct_reads(self.h, C.byref(self.p), _ptr(reads), _ptr(offsets), n, arena_bytes, 1 if wide else 0,
+        rc = lib().emu_correct_reads(self.h, C.byref(self.p), _ptr(reads), _ptr(offsets), n, arena_bytes, (1 if wide else 0) | (2 if split else 0),
                                      _ptr(out), cap, _ptr(ooff), _ptr(status), _ptr(ctr))
         if rc != 0:
             raise RuntimeError("emu output buffer too small")

@@ -584,3 +584,25 @@ def test_gpu_kmer_counting_from_short_reads(api, case_c1, tmp_path):
     b = d.correct(sub_r, sub_o)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert a[3]["gaps"] == b[3]["gaps"] and a[3]["lookups_walk"] == b[3]["lookups_walk"]
+
+
+@pytest.mark.parametrize("shape", [(2, 0, 0), (1, 5, 1), (1, 64, 7), (1, 0, 0)])
+def test_execution_shapes_give_identical_results(api, case_c1, case_c5, case_c3, shape):
+    """The suspendable per-read program + lane-per-trail walk kernel (split_walk = 1) against the monolithic kernel
+    (split_walk = 2) and the oracle: bytes, status and every algorithmic counter, whatever the number of read contexts
+    in flight (5: every context is reused dozens of times) and wherever the walk rounds are cut (cap 1: a frontier
+    comes back after every single step)."""
+    for case in (case_c1, case_c5, case_c3):
+        t = _ctx(api, case)
+        t.set_exec(*shape)
+        out, off, st, ctr = t.correct(case.reads, case.off)
+        _assert_same(case, out, off, st, ctr)
+        if shape[0]:
+            assert (ctr["rounds"] > 0) == (shape[0] == 1)
+    # a tiny first tier pushes reads through the second tier in split mode as well
+    t = _ctx(api, case_c1)
+    t.set_exec(*shape)
+    t.set_scratch(tier1_bytes=6 * 1024)
+    out, off, st, ctr = t.correct(case_c1.reads, case_c1.off)
+    assert ctr["reads_second_tier"] > 0
+    _assert_same(case_c1, out, off, st, ctr)

@@ -160,3 +160,28 @@ def test_tagging_matches_oracle_exhaustively():
             for i in range(4):
                 if t1[i] != 1:
                     assert d1[i] == d2[i]
+
+
+def test_suspend_and_resume_is_result_neutral(case_c5):
+    """The per-read program as a resumable state machine (correct.cuh frames): a read that yields at every long walk
+    and is resumed from its saved frames gives the bytes, status and counters of the run that never yields."""
+    import pyemu
+    from oracle import pyoracle as po
+    g = np.load(GOLD)
+    for name in ("c1", "c3", "c5"):
+        k = int(g[name + "_k"][0])
+        usej = len(g[name + "_jkeys"]) > 0
+        et = pyemu.EmuTable(pyemu.params_from(po.make_params(k=k)), g[name + "_keys"], g[name + "_counts"].astype(np.int64),
+                            g[name + "_jkeys"] if usej else None, g[name + "_jcounts"].astype(np.int64) if usej else None)
+        y0 = pyemu.lib().emu_yields()
+        a = et.correct(g[name + "_reads"], g[name + "_off"], arena_bytes=1 << 20, wide=True, split=True)
+        assert pyemu.lib().emu_yields() > y0, "the split run must actually yield"
+        b = et.correct(g[name + "_reads"], g[name + "_off"], arena_bytes=1 << 20, wide=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+        assert np.array_equal(a[0], g[name + "_out"]) and np.array_equal(a[2], g[name + "_status"])
+    case = case_c5
+    et = pyemu.EmuTable(pyemu.params_from(case.op), case.keys, case.counts)
+    out, off, st, ctr = et.correct(case.reads, case.off, arena_bytes=4 << 20, wide=True, split=True)
+    assert np.array_equal(st, case.o_status) and np.array_equal(off, case.o_off) and np.array_equal(out, case.o_out)
+    for k2 in ("lookups_walk", "steps_inner", "steps_border", "cells_xdrop", "ev_gardening", "ev_cycle"):
+        assert ctr[k2] == case.o_ctr[k2], k2
