@@ -1,0 +1,54 @@
+#!/bin/bash
+# One GPU slot, everything that needs hardware (round 2): tests, A/B of the two execution shapes, bench, ncu.
+# usage (on the box, from the repo root): bash tools/r2_gpu_session.sh [stage ...]   stages: tests ab bench ncu race
+# Every stage writes under gpurun_out/ and never stops the ones after it.
+mkdir -p gpurun_out
+STAGES="${@:-tests ab bench}"
+for S in $STAGES; do
+case $S in
+tests)
+  timeout 2400 python -m pytest tests -m gpu -q --timeout 1500 -x > gpurun_out/r2_tests.log 2>&1
+  echo "== tests: $(tail -1 gpurun_out/r2_tests.log)"
+  grep -E "^(FAILED|ERROR)|Error|assert" gpurun_out/r2_tests.log | head -20
+  ;;
+ab)
+  # the two execution shapes on a mid-size workload (40 000 reads of config 2 at scale 0.02, table fits L2) and on
+  # config 5; TALC_SPLIT / TALC_CTX / TALC_WALK_CAP select the shape
+  for cfg in 2 5; do
+    for shape in "0 16384 48" "1 16384 48" "1 16384 16" "1 32768 48" "1 8192 128"; do
+      set -- $shape
+      TALC_PROFILE_CONFIG=$cfg TALC_SPLIT=$1 TALC_CTX=$2 TALC_WALK_CAP=$3 timeout 600 python tools/profile_case.py 40000 2 \
+        2>&1 | tail -1 | sed "s/^/cfg$cfg split=$1 ctx=$2 cap=$3: /"
+    done
+  done > gpurun_out/r2_ab.log 2>&1
+  cat gpurun_out/r2_ab.log
+  ;;
+bench)
+  TALC_SPLIT=0 timeout 900 python bench.py --steps 3 --warmup 3 --no-table-load > gpurun_out/r2_bench_mono.json 2> gpurun_out/r2_bench_mono.err
+  echo "== mono: $(python -c "import json;d=json.load(open('gpurun_out/r2_bench_mono.json'));print(d['value'],d['e2e']['value'],d.get('parity'))" 2>&1)"
+  TALC_SPLIT=1 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_split.json 2> gpurun_out/r2_bench_split.err
+  echo "== split: $(python -c "import json;d=json.load(open('gpurun_out/r2_bench_split.json'));print(d['value'],d['e2e']['value'],d.get('parity'),d.get('table_load'),d['roofline'].get('peak_random'),d['roofline'].get('peak_random_dependent'))" 2>&1)"
+  tail -2 gpurun_out/r2_bench_split.err
+  ;;
+ncu)
+  K='regex:^(correct_kernel|control_kernel|walk_kernel|coverage_kernel|gather_kernel|kmer_count_kernel|len_to_u64_kernel|cost_key_kernel|ctx_init_kernel|table_.*|ctx_.*|model_tabs_kernel|random_sector_kernel.*)$'
+  ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 4000 --csv --log-file gpurun_out/r2_launches.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-table-load > gpurun_out/r2_ncu_launch.log 2>&1
+  grep -c . gpurun_out/r2_launches.csv
+  for kern in control_kernel walk_kernel; do
+    TALC_PROFILE_CONFIG=2 ncu --set full --import-source on --clock-control none -k regex:$kern -s 40 -c 1 -o gpurun_out/r2_$kern -f \
+      python tools/profile_case.py 40000 1 > gpurun_out/r2_ncu_$kern.log 2>&1
+  done
+  ls -la gpurun_out/*.ncu-rep
+  ;;
+race)
+  # compute-sanitizer racecheck + memcheck of a tiny batch through both execution shapes
+  for sp in 0 1; do
+    TALC_SPLIT=$sp timeout 1200 compute-sanitizer --tool racecheck --print-limit 5 python tools/profile_case.py 24 1 > gpurun_out/r2_racecheck_split$sp.log 2>&1
+    tail -3 gpurun_out/r2_racecheck_split$sp.log
+    TALC_SPLIT=$sp timeout 1200 compute-sanitizer --tool memcheck --print-limit 5 python tools/profile_case.py 200 1 > gpurun_out/r2_memcheck_split$sp.log 2>&1
+    tail -3 gpurun_out/r2_memcheck_split$sp.log
+  done
+  ;;
+esac
+done
