@@ -170,6 +170,12 @@ class Corrector {
     RefView ref;
     EdgeBest bestLong, bestShort;
   };
+  // A suspended read also gives its warp back when it has run for pauseBudget SM cycles since it was resumed (host
+  // emulation: general steps): the control kernel works in rounds, and one read with a 500-base border would
+  // otherwise hold a whole round for as long as its X-drop extensions take.  wq.border == 2 marks such a pause: the
+  // walk kernel passes the context straight on.
+  long long tResume;
+  u32 pauseBudget, pauseCount;
   WalkReq wq;
   RunFrame fr;
   BridgeFrame fb;
@@ -666,6 +672,20 @@ class Corrector {
   }
 
 
+  TALC_HD bool should_pause() {
+    if (!splitWalk || !pauseBudget) return false;
+#if defined(__CUDA_ARCH__)
+    const int mine = (clock64() - tResume) > (long long)pauseBudget ? 1 : 0;
+    return __shfl_sync(0xffffffffu, mine, 0) != 0;  // one decision per warp
+#else
+    return (++pauseCount % pauseBudget) == 0;
+#endif
+  }
+  TALC_HD void mark_resumed() {
+#if defined(__CUDA_ARCH__)
+    tResume = clock64();
+#endif
+  }
   // a frontier the fast path (and the walk kernel, walk.cuh) can take: every trail in its own lane of a group
   TALC_HD bool walk_eligible(u32 nAims) const { return !(nCur == 0 || nCur > 7 || nCur > P.max_branches || nAims > 32); }
 
@@ -1147,6 +1167,11 @@ class Corrector {
           if (!(fb.step < fb.pathMax)) { fb.pc = 4; break; }
           if (!bridge_general_step(aims, nAims)) { fb.pc = 0; return kStepFalse; }
           fb.pc = 2;
+          if (should_pause()) {
+            wq.step = fb.step;
+            wq.border = 2;
+            return kStepYield;
+          }
           break;
         }
         default: {  // case 4: the attempt is over
@@ -1572,6 +1597,11 @@ class Corrector {
           if (!(fe.step < fe.pathMax)) { ++fe.s; fe.pc = 1; break; }
           if (!edge_general_step()) { fe.pc = 0; return kStepFalse; }
           fe.pc = 2;
+          if (should_pause()) {
+            wq.step = fe.step;
+            wq.border = 2;
+            return kStepYield;
+          }
           break;
         }
       }
@@ -1721,6 +1751,8 @@ class Corrector {
   // pieces describe the corrected read.
   TALC_HDN u8 start(const ReadJob& job) {
     job_ = job;
+    pauseCount = 0;
+    mark_resumed();
     fr.pc = 0;
     fb.pc = 0;
     fe.pc = 0;
@@ -1728,6 +1760,7 @@ class Corrector {
   }
   TALC_HDN u8 run(const ReadJob& job) {  // never yields: the walk is taken inline (host emulation, tuning builds)
     splitWalk = 0;
+    pauseBudget = 0;
     return start(job);
   }
   // what the walk kernel (or its host stand-in) reports back

@@ -297,6 +297,7 @@ struct CorrectArgs {
   u32* readStats;    // optional: per read {span of the final solid regions in k-mers, number of regions} (Read.cpp:418-433)
   CtxView cright, cleft;  // successor tables
   u32 wide;      // worst-case sizing of the X-drop anti-diagonals (align.cuh)
+  u32 pauseCycles;  // split mode: SM cycles a read may run per round before it gives its warp back (0 = no limit)
   u32 lastTier;  // no larger arena follows: a read that overflows passes through uncorrected (kReadResource)
 };
 
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) control_kernel(RoundArgs
       __syncwarp();
       cx.ctr = &mine;
       cx.walk_done(cx.wq.step);
+      cx.mark_resumed();
       __syncwarp();
       st = cx.resume();
       __syncwarp();
@@ -544,6 +546,7 @@ __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) control_kernel(RoundArgs
       cx.P = A.P;
       cx.tabs = A.tabs;
       cx.splitWalk = 1;
+      cx.pauseBudget = A.pauseCycles;
       for (int i = 0; i < kNumCounters; ++i) ((u64*)&mine)[i] = 0;
       cx.ctr = &mine;
       ReadJob job;
@@ -748,6 +751,7 @@ struct talc_ctx {
   u32 splitWalk = 0;       // 1: suspendable reads + walk kernel (rounds), 0: one monolithic correct_kernel launch
   u32 nCtxTier1 = 16384;   // read contexts in flight (each with a tier-1 arena)
   u32 walkStepCap = 48;    // steps a frontier may take per round of the walk kernel (bounds the round's tail)
+  u32 pauseCycles = 200000;  // SM cycles (~100 us) a read may run per round of the control kernel
   u64 lastRounds = 0;
   double* modelTabs = nullptr;  // 3 x kModelTabN doubles
   // cached device buffers
@@ -856,6 +860,7 @@ int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out) {
   if (const char* e2 = getenv("TALC_SPLIT")) c->splitWalk = atoi(e2) != 0;
   if (const char* e2 = getenv("TALC_CTX")) c->nCtxTier1 = (u32)std::max(4, atoi(e2));
   if (const char* e2 = getenv("TALC_WALK_CAP")) c->walkStepCap = (u32)std::max(1, atoi(e2));
+  if (const char* e2 = getenv("TALC_PAUSE_CYCLES")) c->pauseCycles = (u32)std::max(0, atoi(e2));
   *out = c;
   return TALC_OK;
 }
@@ -1524,28 +1529,50 @@ static int run_pass(talc_ctx* c, CorrectArgs& A, u32 nCtx, u64* launches) {
   if (ctlBlocks * 4 > nCtx) ctlBlocks = (nCtx + 3) / 4;
   u32 walkBlocks = (u32)c->sms * 4;
   if (walkBlocks * 32 > nCtx) walkBlocks = (nCtx + 31) / 32;
-  u64 rounds = 0;
-  u32 hFinished = 0;
-  u32 chunk = 8;
-  const auto t0 = std::chrono::steady_clock::now();
-  for (;;) {
+  // a chunk of rounds is captured once into a CUDA graph (4 nodes per round) and replayed: the host enqueues one graph
+  // and reads one counter per chunk instead of driving every launch
+  const u32 chunk = 16;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool captured = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  if (captured) {
     for (u32 i = 0; i < chunk; ++i) {
-      CUDA_TRY(c, cudaMemsetAsync(dCnt + 1, 0, 8, c->stream));  // nWalk, taskCursor
+      cudaMemsetAsync(dCnt + 1, 0, 8, c->stream);  // nWalk, taskCursor
       control_kernel<<<ctlBlocks, 128, 0, c->stream>>>(R);
-      CUDA_TRY(c, cudaMemsetAsync(dCnt, 0, 4, c->stream));      // nReady
+      cudaMemsetAsync(dCnt, 0, 4, c->stream);      // nReady
       walk_kernel<<<walkBlocks, 256, 0, c->stream>>>(ctxs, walkList, dCnt + 1, readyList, dCnt, c->walkStepCap);
     }
+    captured = cudaStreamEndCapture(c->stream, &graph) == cudaSuccess && graph != nullptr &&
+               cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+  }
+  if (!captured) {
+    if (graph) cudaGraphDestroy(graph);
+    c->err = std::string("cannot capture the correction rounds into a CUDA graph: ") + cudaGetErrorString(cudaGetLastError());
+    return TALC_ERR_CUDA;
+  }
+  u64 rounds = 0;
+  u32 hFinished = 0;
+  int rc = TALC_OK;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    if (cudaGraphLaunch(exec, c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(&hFinished, dCnt + 3, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      c->err = std::string("correction rounds failed: ") + cudaGetErrorString(cudaGetLastError());
+      rc = TALC_ERR_CUDA;
+      break;
+    }
     rounds += chunk;
-    CUDA_TRY(c, cudaGetLastError());
-    CUDA_TRY(c, cudaMemcpyAsync(&hFinished, dCnt + 3, 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (hFinished >= n) break;
-    if (chunk < 64) chunk *= 2;
     if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 600.0) {
       c->err = "correction rounds did not terminate within 600 s (" + std::to_string(hFinished) + " of " + std::to_string(n) + " reads done)";
-      return TALC_ERR_CUDA;
+      rc = TALC_ERR_CUDA;
+      break;
     }
   }
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  if (rc) return rc;
   c->lastRounds += rounds;
   if (launches) *launches += 2 * rounds + 1;
   return TALC_OK;
@@ -1679,6 +1706,7 @@ static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const u
   }
   A.wide = 1;
   A.lastTier = 0;
+  A.pauseCycles = c->pauseCycles;
   u64 launches = 3;
   c->lastRounds = 0;
   {

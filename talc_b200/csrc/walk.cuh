@@ -57,6 +57,13 @@ __global__ void __launch_bounds__(256) walk_kernel(ReadCtx* __restrict__ ctxs, c
     const u32 id = walkList[j];
     ReadCtx* rc = ctxs + id;
     Corrector& cx = rc->cx;  // in HBM; every lane of the group reads the same words
+    if (cx.wq.border == 2) {  // a pause, not a walk (Corrector::should_pause): straight back to the control kernel
+      if (gl == 0) {
+        const u32 pos = atomicAdd(nReady, 1u);
+        readyList[pos] = id;
+      }
+      continue;
+    }
     const u32 nT = cx.nCur;
     const bool act = gl < nT;
     const Params P = cx.P;

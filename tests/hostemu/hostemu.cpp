@@ -138,16 +138,19 @@ int emu_correct_reads(void* tab, const emu_params* q, const uint8_t* bases, cons
     job.arena = arena.data();
     job.arena_bytes = arena_bytes;
     job.wide = (wide & 1) != 0;
+    cx->pauseBudget = 0;
     u8 st;
     if (wide & 2) {
       // split mode: the read yields where a long walk starts; the "walk kernel" is the scalar fast path run to its end,
       // then the read resumes from its frames -- the suspend / resume protocol of the device, on one thread
       cx->splitWalk = 1;
+      cx->pauseBudget = (wide >> 8) & 0xFF;  // host: pause after every n-th general step (0 = never)
       st = cx->start(job);
       while (st == kReadYield) {
         ++g_yields;
         u32 step = cx->wq.step;
-        cx->fast_walk_scalar(step, cx->wq.pathMax, cx->wq.aims, cx->wq.nAims, cx->wq.border != 0, ~0u);
+        if (cx->wq.border != 2)  // 2 = a pause, nothing to walk
+          cx->fast_walk_scalar(step, cx->wq.pathMax, cx->wq.aims, cx->wq.nAims, cx->wq.border != 0, ~0u);
         cx->walk_done(step);
         st = cx->resume();
       }

@@ -177,11 +177,13 @@ def test_suspend_and_resume_is_result_neutral(case_c5):
         a = et.correct(g[name + "_reads"], g[name + "_off"], arena_bytes=1 << 20, wide=True, split=True)
         assert pyemu.lib().emu_yields() > y0, "the split run must actually yield"
         b = et.correct(g[name + "_reads"], g[name + "_off"], arena_bytes=1 << 20, wide=True)
+        c = et.correct(g[name + "_reads"], g[name + "_off"], arena_bytes=1 << 20, wide=True, split=True, pause_every=1)
+        assert np.array_equal(c[0], b[0]) and np.array_equal(c[2], b[2]) and c[3] == b[3]  # paused after every general step
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
         assert np.array_equal(a[0], g[name + "_out"]) and np.array_equal(a[2], g[name + "_status"])
     case = case_c5
     et = pyemu.EmuTable(pyemu.params_from(case.op), case.keys, case.counts)
-    out, off, st, ctr = et.correct(case.reads, case.off, arena_bytes=4 << 20, wide=True, split=True)
+    out, off, st, ctr = et.correct(case.reads, case.off, arena_bytes=4 << 20, wide=True, split=True, pause_every=3)
     assert np.array_equal(st, case.o_status) and np.array_equal(off, case.o_off) and np.array_equal(out, case.o_out)
     for k2 in ("lookups_walk", "steps_inner", "steps_border", "cells_xdrop", "ev_gardening", "ev_cycle"):
         assert ctr[k2] == case.o_ctr[k2], k2
