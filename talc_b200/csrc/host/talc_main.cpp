@@ -420,13 +420,13 @@ int main(int argc, const char** argv) {
     b->seq = seq;
     talc_stream* s = streams[seq % cli.gpus];
     if (b->offs.size() != b->ids.size() + 1) { inputOk = false; break; }
-    idq.push(b);
     if (talc_stream_submit(s, b->bases.data(), b->offs.data(), (uint32_t)b->ids.size()) != 0) {
       std::cerr << "talc: " << talc_stream_last_error(s) << "\n";
       submitRc = 2;
       break;
     }
     std::vector<uint8_t>().swap(b->bases);  // the stream holds its own copy; ids and offsets stay for the writer
+    idq.push(b);                            // only now: the writer fetches what has been submitted
     ++seq;
     if (writerRc) break;
     auto nb = std::make_shared<Batch>();

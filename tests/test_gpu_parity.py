@@ -444,17 +444,29 @@ def test_stream_api_matches_single_calls(api, case_c1):
     n = len(case.off) - 1
     cuts = [0, 1, 1, 40, 41, 130, n]
     s = t.stream(read_stats=True)
-    for a, b in zip(cuts, cuts[1:]):
-        sub = case.reads[int(case.off[a]):int(case.off[b])]
-        s.submit(sub, case.off[a:b + 1] - case.off[a])
     outs, sts, stats, tot = [], [], [], None
-    for a, b in zip(cuts, cuts[1:]):
+    spans = list(zip(cuts, cuts[1:]))
+
+    def fetch(a, b):
+        nonlocal tot
         o, f, x, rs, c = s.next()
         assert len(x) == b - a and len(f) == b - a + 1 and rs.shape == (b - a, 2)
         outs.append(o)
         sts.append(x)
         stats.append(rs)
         tot = c if tot is None else {k2: tot[k2] + c[k2] for k2 in c}
+
+    fetched = 0
+    for i, (a, b) in enumerate(spans):  # at most three batches in flight: the ring has four slots
+        sub = case.reads[int(case.off[a]):int(case.off[b])]
+        s.submit(sub, case.off[a:b + 1] - case.off[a])
+        if i - fetched >= 2:
+            fetch(*spans[fetched])
+            fetched += 1
+    assert s.pending() == len(spans) - fetched
+    while fetched < len(spans):
+        fetch(*spans[fetched])
+        fetched += 1
     s.close()
     assert np.array_equal(np.concatenate(outs), out) and np.array_equal(np.concatenate(sts), st)
     assert {k2: tot[k2] for k2 in SHARED} == {k2: ctr[k2] for k2 in SHARED}
