@@ -7,7 +7,7 @@ STAGES="${@:-tests ab bench}"
 for S in $STAGES; do
 case $S in
 tests)
-  timeout 2400 python -m pytest tests -m gpu -q --timeout 1500 -x > gpurun_out/r2_tests.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --durations=30 > gpurun_out/r2_tests.log 2>&1
   echo "== tests: $(tail -1 gpurun_out/r2_tests.log)"
   grep -E "^(FAILED|ERROR)|Error|assert" gpurun_out/r2_tests.log | head -20
   ;;
