@@ -144,7 +144,6 @@ class Corrector {
   // its own kernel (walk.cuh), one trail per lane next to the trails of other reads -- and resumed afterwards from
   // its context in HBM.  Without splitWalk (host emulation, tuning builds) nothing ever yields.
   enum : u8 { kStepFalse = 0, kStepTrue = 1, kStepYield = 2 };
-  static const u32 kInlineWalkSteps = 6;  // steps a warp still takes by itself before it hands the frontier over
   struct WalkReq {  // what the walk kernel needs besides cur[] / the slots, and what it hands back (step)
     const AnchorRec* aims;
     u32 nAims, step, pathMax, border;
@@ -176,6 +175,7 @@ class Corrector {
   // walk kernel passes the context straight on.
   long long tResume;
   u32 pauseBudget, pauseCount;
+  u32 inlineInner, inlineBorder;  // ordinary steps a warp still takes by itself before it hands the frontier over
   WalkReq wq;
   RunFrame fr;
   BridgeFrame fb;
@@ -1151,7 +1151,7 @@ class Corrector {
         }
         case 2: {  // loop head of Explorer.cpp:940
           if (!((nCur > 0) & (nCur <= kMaxInnerPaths) & (fb.step < fb.pathMax))) { fb.pc = 4; break; }
-          const bool capped = fast_walk(fb.step, fb.pathMax, aims, nAims, false, splitWalk ? kInlineWalkSteps : ~0u);
+          const bool capped = fast_walk(fb.step, fb.pathMax, aims, nAims, false, splitWalk ? inlineInner : ~0u);
           fb.pc = 3;
           if (capped && splitWalk) {  // still walking: the walk kernel carries on from cur[] and hands fb.step back in wq
             wq.aims = aims;
@@ -1581,7 +1581,7 @@ class Corrector {
         }
         case 2: {  // loop head of Explorer.cpp:1055
           if (!((nCur > 0) & (nCur <= kMaxInnerPaths) & (fe.step < fe.pathMax))) { ++fe.s; fe.pc = 1; break; }
-          const bool capped = fast_walk(fe.step, fe.pathMax, nullptr, 0, true, splitWalk ? kInlineWalkSteps : ~0u);
+          const bool capped = fast_walk(fe.step, fe.pathMax, nullptr, 0, true, splitWalk ? inlineBorder : ~0u);
           fe.pc = 3;
           if (capped && splitWalk) {
             wq.aims = nullptr;

@@ -297,6 +297,7 @@ struct CorrectArgs {
   u32* readStats;    // optional: per read {span of the final solid regions in k-mers, number of regions} (Read.cpp:418-433)
   CtxView cright, cleft;  // successor tables
   u32 wide;      // worst-case sizing of the X-drop anti-diagonals (align.cuh)
+  u32 inlineInner, inlineBorder;  // split mode: ordinary steps taken inside control_kernel before a frontier is handed over
   u32 pauseCycles;  // split mode: SM cycles a read may run per round before it gives its warp back (0 = no limit)
   u32 lastTier;  // no larger arena follows: a read that overflows passes through uncorrected (kReadResource)
 };
@@ -547,6 +548,8 @@ __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) control_kernel(RoundArgs
       cx.tabs = A.tabs;
       cx.splitWalk = 1;
       cx.pauseBudget = A.pauseCycles;
+      cx.inlineInner = A.inlineInner;
+      cx.inlineBorder = A.inlineBorder;
       for (int i = 0; i < kNumCounters; ++i) ((u64*)&mine)[i] = 0;
       cx.ctr = &mine;
       ReadJob job;
@@ -752,6 +755,7 @@ struct talc_ctx {
   u32 nCtxTier1 = 16384;   // read contexts in flight (each with a tier-1 arena)
   u32 walkStepCap = 48;    // steps a frontier may take per round of the walk kernel (bounds the round's tail)
   u32 pauseCycles = 200000;  // SM cycles (~100 us) a read may run per round of the control kernel
+  u32 inlineInner = 6, inlineBorder = 6;
   u64 lastRounds = 0;
   double* modelTabs = nullptr;  // 3 x kModelTabN doubles
   // cached device buffers
@@ -861,6 +865,8 @@ int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out) {
   if (const char* e2 = getenv("TALC_CTX")) c->nCtxTier1 = (u32)std::max(4, atoi(e2));
   if (const char* e2 = getenv("TALC_WALK_CAP")) c->walkStepCap = (u32)std::max(1, atoi(e2));
   if (const char* e2 = getenv("TALC_PAUSE_CYCLES")) c->pauseCycles = (u32)std::max(0, atoi(e2));
+  if (const char* e2 = getenv("TALC_INLINE_INNER")) c->inlineInner = (u32)std::max(0, atoi(e2));
+  if (const char* e2 = getenv("TALC_INLINE_BORDER")) c->inlineBorder = (u32)std::max(0, atoi(e2));
   *out = c;
   return TALC_OK;
 }
@@ -1529,6 +1535,41 @@ static int run_pass(talc_ctx* c, CorrectArgs& A, u32 nCtx, u64* launches) {
   if (ctlBlocks * 4 > nCtx) ctlBlocks = (nCtx + 3) / 4;
   u32 walkBlocks = (u32)c->sms * 4;
   if (walkBlocks * 32 > nCtx) walkBlocks = (nCtx + 31) / 32;
+  if (getenv("TALC_ROUND_DEBUG")) {  // tuning aid: every round timed and counted on its own (no graph)
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    double tc = 0, tw = 0;
+    u64 rounds = 0, sumReady = 0, sumWalk = 0;
+    u32 h[4];
+    for (;;) {
+      u32 hr = 0;
+      cudaMemcpyAsync(&hr, dCnt, 4, cudaMemcpyDeviceToHost, c->stream);
+      cudaMemsetAsync(dCnt + 1, 0, 8, c->stream);
+      cudaEventRecord(e0, c->stream);
+      control_kernel<<<ctlBlocks, 128, 0, c->stream>>>(R);
+      cudaEventRecord(e1, c->stream);
+      cudaMemsetAsync(dCnt, 0, 4, c->stream);
+      walk_kernel<<<walkBlocks, 256, 0, c->stream>>>(ctxs, walkList, dCnt + 1, readyList, dCnt, c->walkStepCap);
+      cudaEventRecord(e2, c->stream);
+      cudaMemcpyAsync(h, dCnt, 16, cudaMemcpyDeviceToHost, c->stream);
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, e0, e1);
+      cudaEventElapsedTime(&b, e1, e2);
+      tc += a; tw += b; ++rounds; sumReady += hr; sumWalk += h[1];
+      if (rounds <= 40 || (rounds % 200) == 0 || h[3] >= n)
+        fprintf(stderr, "[round %llu] ready %u -> control %.3f ms -> walk %u -> %.3f ms ; finished %u / %u\n",
+                (unsigned long long)rounds, hr, a, h[1], b, h[3], n);
+      if (h[3] >= n) break;
+      if (rounds > 2000000) break;
+    }
+    fprintf(stderr, "[rounds] %llu rounds: control %.1f ms, walk %.1f ms; tasks %llu (%.1f per round), walks %llu\n",
+            (unsigned long long)rounds, tc, tw, (unsigned long long)sumReady, (double)sumReady / rounds, (unsigned long long)sumWalk);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    c->lastRounds += rounds;
+    if (launches) *launches += 2 * rounds + 1;
+    return TALC_OK;
+  }
   // a chunk of rounds is captured once into a CUDA graph (4 nodes per round) and replayed: the host enqueues one graph
   // and reads one counter per chunk instead of driving every launch
   const u32 chunk = 16;
@@ -1707,6 +1748,8 @@ static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const u
   A.wide = 1;
   A.lastTier = 0;
   A.pauseCycles = c->pauseCycles;
+  A.inlineInner = c->inlineInner;
+  A.inlineBorder = c->inlineBorder;
   u64 launches = 3;
   c->lastRounds = 0;
   {

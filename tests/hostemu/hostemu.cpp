@@ -144,6 +144,7 @@ int emu_correct_reads(void* tab, const emu_params* q, const uint8_t* bases, cons
       // split mode: the read yields where a long walk starts; the "walk kernel" is the scalar fast path run to its end,
       // then the read resumes from its frames -- the suspend / resume protocol of the device, on one thread
       cx->splitWalk = 1;
+      cx->inlineInner = cx->inlineBorder = 6;
       cx->pauseBudget = (wide >> 8) & 0xFF;  // host: pause after every n-th general step (0 = never)
       st = cx->start(job);
       while (st == kReadYield) {

@@ -21,4 +21,4 @@ d_ooff = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
 d_st = torch.zeros(n, dtype=torch.uint8, device="cuda")
 for _ in range(iters):
     ctr = t.correct_device(d_reads, d_off, total, d_out, d_ooff, d_st)
-print("reads %d bases %d ms_correct %.1f ms_cov %.2f Mbp/s %.1f" % (n, total, ctr["ms_correct"], ctr["ms_coverage"], total / 1e3 / ctr["ms_total"]))
+print("reads %d bases %d ms_correct %.1f ms_cov %.2f Mbp/s %.1f rounds %d launches %d" % (n, total, ctr["ms_correct"], ctr["ms_coverage"], total / 1e3 / ctr["ms_total"], ctr["rounds"], ctr["kernel_launches"]))

@@ -41,6 +41,18 @@ ncu)
   done
   ls -la gpurun_out/*.ncu-rep
   ;;
+rounds)
+  # per-round timing of the split shape (TALC_ROUND_DEBUG) on the two profile workloads, a few shapes
+  for cfg in 2 5; do
+    for shape in "16384 48 6 6 200000" "16384 48 0 6 200000" "32768 160 0 6 200000" "32768 160 0 6 1000000" "32768 160 0 6 0"; do
+      set -- $shape
+      echo "=== cfg$cfg ctx=$1 cap=$2 inlineInner=$3 inlineBorder=$4 pause=$5"
+      TALC_ROUND_DEBUG=1 TALC_PROFILE_CONFIG=$cfg TALC_SPLIT=1 TALC_CTX=$1 TALC_WALK_CAP=$2 TALC_INLINE_INNER=$3 TALC_INLINE_BORDER=$4 TALC_PAUSE_CYCLES=$5 \
+        timeout 600 python tools/profile_case.py 40000 1 2>&1 | grep -E "round|reads" | awk 'NR<=45 || /rounds\]/ || /reads/ || NR%10==0' | tail -80
+    done
+  done > gpurun_out/r2_rounds.log 2>&1
+  grep -E "===|rounds\]|^reads" gpurun_out/r2_rounds.log
+  ;;
 race)
   # compute-sanitizer racecheck + memcheck of a tiny batch through both execution shapes
   for sp in 0 1; do
