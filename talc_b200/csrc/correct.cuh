@@ -20,6 +20,11 @@
 #include "stdsort.cuh"
 #include "table.cuh"
 
+// the bodies of the general steps: real calls (TALC_HDN) or inlined into their one caller per kernel (TALC_HD)
+#ifndef TALC_STEPFN
+#define TALC_STEPFN TALC_HDN
+#endif
+
 namespace talc {
 
 struct Counters {
@@ -1186,7 +1191,7 @@ class Corrector {
   }
 
   // ---- oneMoreStep, Explorer.cpp:546-612 (one synchronous expansion of the frontier, then pruning if due)
-  TALC_HDN bool bridge_general_step(const AnchorRec* aims, u32 nAims) {
+  TALC_STEPFN bool bridge_general_step(const AnchorRec* aims, u32 nAims) {
     const u32 k = K();
     const RefView ref = fb.ref;
     const SeqView refv = view_of(ref);
@@ -1348,7 +1353,7 @@ class Corrector {
   }
 
   // Explorer.cpp:945-982: best recorded bridge of the attempt, acceptance test, corrected weak sequence
-  TALC_HDN void finish_bridge_attempt(Piece& weakOut) {
+  TALC_STEPFN void finish_bridge_attempt(Piece& weakOut) {
     const u32 k = K();
     BridgeRec* br = (BridgeRec*)fb.br;
     const u64* brSeq = fb.brSeq;
@@ -1609,7 +1614,7 @@ class Corrector {
   }
 
   // ---- oneMoreStepInTheDark, Explorer.cpp:615-687
-  TALC_HDN bool edge_general_step() {
+  TALC_STEPFN bool edge_general_step() {
     const u32 k = K();
     const RefView ref = fe.ref;
     const SeqView refv = view_of(ref);
@@ -1704,7 +1709,7 @@ class Corrector {
   }
 
   // sortOutBestBorder (Explorer.cpp:310-329) + the acceptance test of :1063-1076
-  TALC_HDN bool finish_edge_search(Piece& weakOut) {
+  TALC_STEPFN bool finish_edge_search(Piece& weakOut) {
     const u32 k = K();
     const EdgeBest& bestLong = fe.bestLong;
     const EdgeBest& bestShort = fe.bestShort;
@@ -1743,6 +1748,188 @@ class Corrector {
       }
     }
     return found;
+  }
+
+  // ------------------------------------------------------------------ straight-line drivers (monolithic kernel, host)
+  // The same searches without the suspend points: plain loops around the same step functions.  The monolithic kernel
+  // (and the host emulation's default path) run these; the state machines above exist for reads that are suspended.
+  TALC_HDN bool search_bridge_mono(Piece& weakOut) {
+    const u32 k = K();
+    const AnchorRec* anchors = dirRight ? ancL : ancR;
+    const u32 nAnch = dirRight ? nAncL : nAncR;
+    const AnchorRec* aims = dirRight ? ancR : ancL;
+    const u32 nAims = dirRight ? nAncR : nAncL;
+    const u32 limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
+    fb.found = false;
+    const u32 mk0 = scratch.mark();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1  // at most 5 start anchors: unrolled, the whole search would be in the binary five times
+#endif
+    for (u32 s = 0; s < limit && !fb.found; ++s) {
+      scratch.release(mk0);
+      if (ctr) ctr->gap_attempts++;
+      const u32 whichStart = anchors[s].pos;
+      u32 gapLen = 0;
+      if (dirRight & (whichStart + k < R.start)) gapLen = R.start - (whichStart + k);
+      else if (!dirRight & (L.end + k < whichStart)) gapLen = whichStart - (L.end + k);
+      const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(3 * k));
+      fb.whichStart = whichStart;
+      fb.gapLen = gapLen;
+      fb.pathMax = pathMax;
+      RefView ref;
+      ref.w = rdw;
+      ref.lg = rdlg;
+      if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = R.end + k - whichStart; }
+      else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k - L.start; }
+      fb.ref = ref;
+      if (!setup_search(pathMax)) return false;
+      if (!push_root(anchors[s])) return false;
+      const u32 capShare = (scratch.cap - scratch.top) / 16u;
+      u32 maxBridges = capShare / (u32)sizeof(BridgeRec);
+      if (maxBridges < 1024u) maxBridges = 1024u;
+      u32 maxKeep = capShare / (slotWords * 8u);
+      if (maxKeep < 32u) maxKeep = 32u;
+      if (maxKeep > maxBridges) maxKeep = maxBridges;
+      fb.maxBridges = maxBridges;
+      fb.maxKeep = maxKeep;
+      fb.br = scratch.alloc(maxBridges * sizeof(BridgeRec));
+      fb.brSeq = (u64*)scratch.alloc(maxKeep * slotWords * 8);
+      if (!fb.br || !fb.brSeq) return false;
+      fb.nBr = fb.nBrSeq = 0;
+      fb.runScore = 0;
+      fb.runMd = 0;
+      fb.runHave = false;
+      fb.step = 0;
+      while ((nCur > 0) & (nCur <= kMaxInnerPaths) & (fb.step < pathMax)) {
+        fast_walk(fb.step, pathMax, aims, nAims, false, ~0u);
+        if (!(fb.step < pathMax)) break;
+        if (!bridge_general_step(aims, nAims)) return false;
+      }
+      finish_bridge_attempt(weakOut);
+      if (scratch.overflow || keep.overflow) return false;
+    }
+    scratch.release(mk0);
+    return fb.found;
+  }
+
+  TALC_HDN bool search_edge_mono(Piece& weakOut) {
+    const u32 k = K();
+    const AnchorRec* anchors = dirRight ? ancL : ancR;
+    const u32 nAnch = dirRight ? nAncL : nAncR;
+    const u32 limit = nAnch < kMaxStartAnchors ? nAnch : (u32)kMaxStartAnchors;
+    u32 maxGap = 0;
+    TALC_ROLLED
+    for (u32 s = 0; s < limit; ++s) {
+      const u32 g = (location == 0) ? anchors[s].pos : (rd.len - (anchors[s].pos + k));
+      maxGap = g > maxGap ? g : maxGap;
+    }
+    const u32 maxPath = (u32)(i32)(1.2 * (double)maxGap + (double)(2 * k));
+    const u32 bestWords = (k + maxPath + 2 + 31) / 32 + 1;
+    fe.bestLong.have = fe.bestShort.have = false;
+    fe.bestLong.seq = (u64*)scratch.alloc(bestWords * 8);
+    fe.bestShort.seq = (u64*)scratch.alloc(bestWords * 8);
+    if (!fe.bestLong.seq || !fe.bestShort.seq) return false;
+    const u32 mk0 = scratch.mark();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (u32 s = 0; s < limit; ++s) {
+      scratch.release(mk0);
+      fe.xdrop = (int)((int)kCheckInterval * 0.3 + 1);  // Q15: 2
+      const u32 whichStart = anchors[s].pos;
+      const u32 gapLen = (location == 0) ? whichStart : (rd.len - (whichStart + k));
+      const u32 pathMax = (u32)(i32)(1.2 * (double)gapLen + (double)(2 * k));
+      fe.whichStart = whichStart;
+      fe.pathMax = pathMax;
+      RefView ref;
+      ref.w = rdw;
+      ref.lg = rdlg;
+      if (dirRight) { ref.start = (i32)whichStart; ref.step = 1; ref.len = rd.len - whichStart; }
+      else { ref.start = (i32)(whichStart + k - 1); ref.step = -1; ref.len = whichStart + k; }
+      fe.ref = ref;
+      if (!setup_search(pathMax)) return false;
+      if (!push_root(anchors[s])) return false;
+      fe.step = 0;
+      while ((nCur > 0) & (nCur <= kMaxInnerPaths) & (fe.step < pathMax)) {
+        fast_walk(fe.step, pathMax, nullptr, 0, true, ~0u);
+        if (!(fe.step < pathMax)) break;
+        if (!edge_general_step()) return false;
+      }
+    }
+    return finish_edge_search(weakOut);
+  }
+
+  // Read::correct2 (Read.cpp:336-386) as plain loops
+  TALC_HDN u8 run_mono(const ReadJob& job) {
+    job_ = job;
+    splitWalk = 0;
+    pauseBudget = 0;
+    const u32 k = K();
+    {
+      const u8 st = prepare_read();
+      if (st != kReadOk) return st;
+    }
+    TALC_ROLLED
+    for (u32 reg = 0; reg + 1 < nregs; ++reg) {
+      if (ctr) ctr->gaps++;
+      bool success = false;
+      TALC_ROLLED
+      for (int attempt = 0; attempt < 2 && !success; ++attempt) {
+        scratch.release(0);  // initializeINNER (Explorer.cpp:228-243)
+        location = 1;
+        dirRight = (attempt == 0);
+        L = regs[reg];
+        R = regs[reg + 1];
+        weakLen = R.start - (L.end + k);
+        if (!build_anchors(true) || !build_anchors(false)) return kReadOverflow;
+        Piece w;
+        success = search_bridge_mono(w);
+        if (scratch.overflow || keep.overflow) return kReadOverflow;
+        if (success) gapPiece[reg] = w;
+      }
+      if (success && ctr) ctr->gaps_bridged++;
+      regs[reg] = L;  // updateINNER (Read.cpp:294-303)
+      regs[reg + 1] = R;
+    }
+    if (headPresent && headRaw <= kBorderMaxLen) {
+      if (ctr) ctr->borders++;
+      scratch.release(0);
+      location = 0;
+      dirRight = false;
+      L.start = L.end = 0;
+      R = regs[0];
+      weakLen = R.start;
+      nAncL = 0;
+      if (!build_anchors(false)) return kReadOverflow;
+      Piece w;
+      const bool ok = search_edge_mono(w);
+      if (scratch.overflow || keep.overflow) return kReadOverflow;
+      if (ok) {
+        if (ctr) ctr->borders_corrected++;
+        regs[0] = R;  // updateHEAD (Read.cpp:305-311)
+        headPiece = w;
+      }
+    }
+    if (tailPresent && tailRaw <= kBorderMaxLen) {
+      if (ctr) ctr->borders++;
+      scratch.release(0);
+      location = 2;
+      dirRight = true;
+      R.start = R.end = 0;
+      L = regs[nregs - 1];
+      weakLen = rd.len - (L.end + k);
+      nAncR = 0;
+      if (!build_anchors(true)) return kReadOverflow;
+      Piece w;
+      const bool ok = search_edge_mono(w);
+      if (scratch.overflow || keep.overflow) return kReadOverflow;
+      if (ok) {
+        if (ctr) ctr->borders_corrected++;
+        regs[nregs - 1] = L;  // updateTAIL (Read.cpp:313-318)
+        tailPiece = w;
+      }
+    }
+    return kReadOk;
   }
 
   // ------------------------------------------------------------------ per-read driver (main.cpp:258-296)

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) correct_kernel(CorrectAr
     job.wide = A.wide != 0;
     __syncwarp();
     const long long t0 = clock64();
-    u8 st = cx.run(job);
+    u8 st = cx.run_mono(job);
     __syncwarp();
     if (st == kReadOverflow && A.lastTier) {
       st = kReadResource;

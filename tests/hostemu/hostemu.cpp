@@ -155,8 +155,10 @@ int emu_correct_reads(void* tab, const emu_params* q, const uint8_t* bases, cons
         cx->walk_done(step);
         st = cx->resume();
       }
+    } else if (wide & 4) {
+      st = cx->run(job);       // the state machines run through without a yield
     } else {
-      st = cx->run(job);
+      st = cx->run_mono(job);  // the straight-line drivers of the monolithic kernel
     }
     mine.cells_nw += cx->dps.cells_nw;
     mine.cells_lcs += cx->dps.cells_lcs;

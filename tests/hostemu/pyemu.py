@@ -92,7 +92,7 @@ class EmuTable:
         except Exception:
             pass
 
-    def correct(self, reads, offsets, arena_bytes=48 * 1024, wide=False, split=False, pause_every=0):
+    def correct(self, reads, offsets, arena_bytes=48 * 1024, wide=False, split=False, pause_every=0, state_machine=False):
         reads = np.ascontiguousarray(reads, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
@@ -101,7 +101,7 @@ class EmuTable:
         ooff = np.zeros(n + 1, dtype=np.uint64)
         status = np.zeros(max(n, 1), dtype=np.uint8)
         ctr = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
-        rc = lib().emu_correct_reads(self.h, C.byref(self.p), _ptr(reads), _ptr(offsets), n, arena_bytes, (1 if wide else 0) | (2 if split else 0) | ((pause_every & 0xFF) << 8),
+        rc = lib().emu_correct_reads(self.h, C.byref(self.p), _ptr(reads), _ptr(offsets), n, arena_bytes, (1 if wide else 0) | (2 if split else 0) | (4 if state_machine else 0) | ((pause_every & 0xFF) << 8),
                                      _ptr(out), cap, _ptr(ooff), _ptr(status), _ptr(ctr))
         if rc != 0:
             raise RuntimeError("emu output buffer too small")

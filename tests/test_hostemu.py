@@ -177,6 +177,8 @@ def test_suspend_and_resume_is_result_neutral(case_c5):
         a = et.correct(g[name + "_reads"], g[name + "_off"], arena_bytes=1 << 20, wide=True, split=True)
         assert pyemu.lib().emu_yields() > y0, "the split run must actually yield"
         b = et.correct(g[name + "_reads"], g[name + "_off"], arena_bytes=1 << 20, wide=True)
+        d = et.correct(g[name + "_reads"], g[name + "_off"], arena_bytes=1 << 20, wide=True, state_machine=True)
+        assert np.array_equal(d[0], b[0]) and np.array_equal(d[2], b[2]) and d[3] == b[3]  # state machines, no yield
         c = et.correct(g[name + "_reads"], g[name + "_off"], arena_bytes=1 << 20, wide=True, split=True, pause_every=1)
         assert np.array_equal(c[0], b[0]) and np.array_equal(c[2], b[2]) and c[3] == b[3]  # paused after every general step
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
