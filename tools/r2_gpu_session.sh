@@ -30,13 +30,34 @@ bench)
   echo "== split: $(python -c "import json;d=json.load(open('gpurun_out/r2_bench_split.json'));print(d['value'],d['e2e']['value'],d.get('parity'),d.get('table_load'),d['roofline'].get('peak_random'),d['roofline'].get('peak_random_dependent'))" 2>&1)"
   tail -2 gpurun_out/r2_bench_split.err
   ;;
+dp)
+  python tools/profile_dp.py 4096 300 > gpurun_out/r2_dp_plain.log 2>&1 && \
+  ncu --set full --import-source on --clock-control none -k regex:test_align_kernel -c 5 -o gpurun_out/r2_dp -f \
+      python tools/profile_dp.py 4096 300 > gpurun_out/r2_ncu_dp.log 2>&1
+  cat gpurun_out/r2_dp_plain.log
+  ;;
+final)
+  # what the round-end driver runs, in the same order: tests, smoke, reference arm, own arm
+  timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/r2_tests_final.log 2>&1; tail -1 gpurun_out/r2_tests_final.log
+  python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; tail -c 300 gpurun_out/r2_bench_reference.json
+  timeout 900 python bench.py --steps 6 --warmup 3 --cli-clock 1000000 > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err
+  python -c "import json;d=json.load(open('gpurun_out/r2_bench_final.json'));print('value',d['value'],'e2e',d['e2e']['value'],'parity',d['parity'],'table_load',d.get('table_load'),'cli',d.get('cli_clock'),'frac',d['roofline']['frac'],d['roofline'].get('frac_random'))" 2>&1
+  tail -2 gpurun_out/r2_bench_final.err
+  ;;
 ncu)
   K='regex:^(correct_kernel|control_kernel|walk_kernel|coverage_kernel|gather_kernel|kmer_count_kernel|len_to_u64_kernel|cost_key_kernel|ctx_init_kernel|table_.*|ctx_.*|model_tabs_kernel|random_sector_kernel.*)$'
-  ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 4000 --csv --log-file gpurun_out/r2_launches.csv \
-      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-table-load > gpurun_out/r2_ncu_launch.log 2>&1
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-table-load > gpurun_out/r2_ncu_plain.log 2>&1 && \
+  ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/r2_launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-table-load > gpurun_out/r2_ncu_launch.log 2>&1
+  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,smsp__inst_executed.sum,sm__icc_request_hit_rate.pct,smsp__cycles_active.avg,sm__cycles_elapsed.max \
+      --clock-control none -k regex:correct_kernel -c 1 --csv --log-file gpurun_out/r2_traffic_correct_kernel.csv \
+      python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-table-load > gpurun_out/r2_ncu_traffic.log 2>&1
   grep -c . gpurun_out/r2_launches.csv
+  TALC_PROFILE_CONFIG=2 ncu --set full --import-source on --clock-control none -k regex:correct_kernel -c 1 -o gpurun_out/r2_correct_kernel -f \
+      python tools/profile_case.py 40000 1 > gpurun_out/r2_ncu_correct_kernel.log 2>&1
   for kern in control_kernel walk_kernel; do
-    TALC_PROFILE_CONFIG=2 ncu --set full --import-source on --clock-control none -k regex:$kern -s 40 -c 1 -o gpurun_out/r2_$kern -f \
+    TALC_SPLIT=1 TALC_PROFILE_CONFIG=2 ncu --set full --import-source on --clock-control none -k regex:$kern -s 40 -c 1 -o gpurun_out/r2_$kern -f \
       python tools/profile_case.py 40000 1 > gpurun_out/r2_ncu_$kern.log 2>&1
   done
   ls -la gpurun_out/*.ncu-rep
