@@ -205,7 +205,17 @@ def run_gpu(args, rank, world, local_rank):
         if rank == 0:
             uid.copy_(torch.from_numpy(api.nccl_unique_id()))
         dist.broadcast(uid, 0)
-        t_bcast_ms = ctx.table_broadcast(uid.cpu().numpy(), rank, world, 0)
+        # NCCL prints its version banner on stdout when the library's communicator comes up: stdout carries exactly one
+        # JSON line, so fd 1 points at stderr while native code may print
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            t_bcast_ms = ctx.table_broadcast(uid.cpu().numpy(), rank, world, 0)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         info = ctx.table_info()
     # this rank's reads: batch_reads per step, a different slice every step (and every rank)
     nsteps = args.warmup + args.steps + 1  # +1 slice for the e2e leg warm-up
@@ -480,7 +490,10 @@ def random_sector_peaks(ctx):
     try:
         ind, _ = ctx.bench_random_sectors(4 << 30, dependent=False, warps_per_sm=64)
         dep, ns = ctx.bench_random_sectors(4 << 30, dependent=True, warps_per_sm=64)
-        return {"peak_random": ind, "peak_random_unit": "GB/s of uniformly random 32 B sectors over 4 GiB, 8 loads in flight per thread, 64 warps/SM",
+        dep8, ns8 = ctx.bench_random_sectors(4 << 30, dependent=True, warps_per_sm=8)
+        return {"dependent_8_warps_per_sm": {"gbs": dep8, "hop_ns": ns8,
+                                             "note": "one dependent chain per thread at the correction kernel's residency "
+                                                     "(8 warps per SM): hop_ns is the latency of one random sector"},"peak_random": ind, "peak_random_unit": "GB/s of uniformly random 32 B sectors over 4 GiB, 8 loads in flight per thread, 64 warps/SM",
                 "peak_random_dependent": dep, "dependent_hop_ns": ns}
     except Exception as e:  # noqa: BLE001
         return {"peak_random": None, "peak_random_error": str(e)}

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU slot, everything that needs hardware (round 2): tests, A/B of the two execution shapes, bench, ncu.
-# usage (on the box, from the repo root): bash tools/r2_gpu_session.sh [stage ...]   stages: tests ab bench ncu race
+# usage (on the box, from the repo root): bash tools/r2_gpu_session.sh [stage ...]   stages: tests ab bench rounds final dp ncu
 # Every stage writes under gpurun_out/ and never stops the ones after it.
 mkdir -p gpurun_out
 STAGES="${@:-tests ab bench}"
@@ -73,15 +73,6 @@ rounds)
     done
   done > gpurun_out/r2_rounds.log 2>&1
   grep -E "===|rounds\]|^reads" gpurun_out/r2_rounds.log
-  ;;
-race)
-  # compute-sanitizer racecheck + memcheck of a tiny batch through both execution shapes
-  for sp in 0 1; do
-    TALC_SPLIT=$sp timeout 1200 compute-sanitizer --tool racecheck --print-limit 5 python tools/profile_case.py 24 1 > gpurun_out/r2_racecheck_split$sp.log 2>&1
-    tail -3 gpurun_out/r2_racecheck_split$sp.log
-    TALC_SPLIT=$sp timeout 1200 compute-sanitizer --tool memcheck --print-limit 5 python tools/profile_case.py 200 1 > gpurun_out/r2_memcheck_split$sp.log 2>&1
-    tail -3 gpurun_out/r2_memcheck_split$sp.log
-  done
   ;;
 esac
 done
