@@ -100,13 +100,10 @@ const char* talc_last_error(talc_ctx* ctx);   /* ctx may be NULL: last create er
 /* scratch sizing (optional): bytes per thread for the first and second tier, warps (= reads in flight) of the second tier */
 int talc_ctx_set_scratch(talc_ctx* ctx, uint32_t tier1_bytes, uint32_t tier2_bytes, uint32_t tier2_threads);
 
-/* execution shape of the correction kernels; 0 keeps a value.  split_walk: 2 = one monolithic kernel per batch, one warp
- * per read; 1 = reads are suspendable programs whose long graph walks run in a separate lane-per-trail kernel
- * (csrc/walk.cuh), control and walk kernels alternating in rounds; 3 = the same suspendable reads and lane-per-trail
- * walkers fused into one persistent kernel (contexts in shared memory, three control warps + one walker warp per
- * block).  Results are identical in every shape (tests/test_gpu_parity.py); DESIGN.md section 4.1 has the timings.
- * read_contexts = reads in flight in shape 1 (each owns a first-tier arena), walk_step_cap = steps per frontier and
- * round in shape 1.  */
+/* execution shape of the correction kernels; 0 keeps a value.  split_walk: 1 (default) = reads are suspendable programs
+ * whose long graph walks run in a separate lane-per-trail kernel (csrc/walk.cuh), 2 = one monolithic kernel per batch
+ * (the round-1 shape, kept for A/B measurements).  Results are identical (tests/test_gpu_parity.py).  read_contexts =
+ * reads in flight in split mode (each owns a first-tier arena), walk_step_cap = steps per frontier and round.  */
 int talc_ctx_set_exec(talc_ctx* ctx, uint32_t split_walk, uint32_t read_contexts, uint32_t walk_step_cap);
 
 /* ---- k-mer table (main.cpp:231-232) -------------------------------------------------------- */

@@ -139,7 +139,7 @@ class Talc:
         self._check(lib().talc_ctx_set_scratch(self.h, tier1_bytes, tier2_bytes, tier2_threads), "talc_ctx_set_scratch")
 
     def set_exec(self, split_walk=0, read_contexts=0, walk_step_cap=0):
-        """split_walk: 1 = suspendable reads + walk kernel in rounds, 2 = monolithic kernel, 3 = fused persistent kernel."""
+        """split_walk: 1 = suspendable reads + walk kernel (default), 2 = monolithic kernel; 0 keeps a value."""
         self._check(lib().talc_ctx_set_exec(self.h, split_walk, read_contexts, walk_step_cap), "talc_ctx_set_exec")
 
     # ---- table

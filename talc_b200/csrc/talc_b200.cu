@@ -566,216 +566,6 @@ __global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) control_kernel(RoundArgs
     }
   }
 }
-// ---- the fused shape: suspendable reads and lane-per-trail walkers INSIDE one persistent kernel, per block.
-// A block owns kFusedCtx read contexts in SHARED memory, three control warps and one walker warp (four groups of 8
-// lanes).  A control warp runs a context until its read yields a long walk, parks it (state WalkWait) and carries on
-// with another context of its block -- a ready one first, else a new read of the queue; a walker group picks a parked
-// frontier, walks it (walk_frontier, the walk kernel's step) and hands the context back (Ready).  Nothing leaves the
-// SM: the Corrector stays in shared memory, the read's working set in this SM's L1 / the L2, the hand-over is a
-// shared-memory flag -- no HBM round trip and no global round barrier, which is what the round-based split shape
-// pays for (profiles/r02_summary.md).  Every wait is a __nanosleep poll inside the block with a spin bound that
-// raises *abort instead of hanging the GPU.
-#ifndef TALC_FUSED_CTX
-#define TALC_FUSED_CTX 10
-#endif
-enum : u32 { kFcIdle = 0, kFcReady = 1, kFcRunning = 2, kFcWalkWait = 3, kFcWalking = 4, kFcDead = 5 };
-
-__device__ __forceinline__ void finish_read(const CorrectArgs& A, Corrector& cx, Counters& mine, u32 r, u8 st, u32 lane) {
-  if (st == kReadOverflow && A.lastTier) {
-    st = kReadResource;
-    if (lane == 0) mine.reads_overflow += 1;
-  }
-  __syncwarp();
-  if (A.readStats && lane == 0 && st != kReadOverflow) {
-    u32 span = 0, nr = 0;
-    if (st == kReadOk || st == kReadNoStructure || st == kReadResource) {
-      nr = cx.nregs;
-      for (u32 i = 0; i < nr; ++i) span += cx.regs[i].end - cx.regs[i].start + 1;
-    }
-    A.readStats[2 * r] = span;
-    A.readStats[2 * r + 1] = nr;
-  }
-  if (st == kReadOverflow) {
-    if (lane == 0) {
-      A.status[r] = st;
-      const u32 slot = atomicAdd(A.nOverflow, 1u);
-      A.overflowList[slot] = r;
-    }
-  } else {
-    const u32 rlen = (u32)(A.offs[r + 1] - A.offs[r]);
-    const u32 olen = (st == kReadOk) ? cx.corrected_length() : rlen;
-    unsigned long long pos = 0;
-    if (lane == 0) pos = atomicAdd(A.outCursor, (unsigned long long)olen);
-    pos = __shfl_sync(0xffffffffu, pos, 0);
-    if (pos + olen <= A.outCap) {
-      u8* dst = A.outArena + pos;
-      if (st == kReadOk) cx.emit(dst, lane, 32);
-      else {
-        const u8* src = A.bases + A.offs[r];
-        for (u32 i = lane; i < rlen; i += 32) dst[i] = code_char(base_code(src[i]));
-      }
-    } else if (lane == 0) {
-      atomicExch(A.outFull, 1u);
-    }
-    if (lane == 0) {
-      A.outPos[r] = pos;
-      A.outLen[r] = olen;
-      A.status[r] = st;
-      mine.cells_nw += cx.dps.cells_nw;
-      mine.cells_lcs += cx.dps.cells_lcs;
-      mine.cells_ovl += cx.dps.cells_ovl;
-      mine.cells_xdrop += cx.dps.cells_xdrop;
-      mine.bases_out += olen;
-      if (st == kReadOk) mine.reads_ok += 1;
-      for (int i = 0; i < kNumCounters; ++i) {
-        const u64 v = ((const u64*)&mine)[i];
-        if (v) atomicAdd(A.counters + i, (unsigned long long)v);
-      }
-    }
-  }
-  __syncwarp();
-}
-
-__global__ void __launch_bounds__(128, TALC_MIN_BLOCKS) fused_kernel(CorrectArgs A, u32 nCtxPerBlock, u32* abortFlag) {
-  __shared__ Corrector cxs[TALC_FUSED_CTX];
-  __shared__ Counters mines[TALC_FUSED_CTX];
-  __shared__ u32 state[TALC_FUSED_CTX];
-  __shared__ u32 readOf[TALC_FUSED_CTX];
-  __shared__ u32 nDead;
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const u32 NC = nCtxPerBlock < (u32)TALC_FUSED_CTX ? nCtxPerBlock : (u32)TALC_FUSED_CTX;
-  if (threadIdx.x < TALC_FUSED_CTX) {
-    state[threadIdx.x] = threadIdx.x < NC ? kFcIdle : kFcDead;
-    readOf[threadIdx.x] = kCtxFree;
-  }
-  if (threadIdx.x == 0) nDead = 0;
-  __syncthreads();
-  volatile u32* vstate = state;
-  volatile u32* vDead = &nDead;
-  const u32 kSpinLimit = 1u << 26;  // ~20 s of 256 ns naps: a protocol bug ends the kernel instead of hanging the GPU
-  if (warp < 3) {
-    // ------------------------------------------------------------------ control warps
-    u32 spins = 0;
-    for (;;) {
-      int c = -1;
-      if (lane == 0) {
-        for (u32 i = 0; i < NC && c < 0; ++i)
-          if (vstate[i] == kFcReady && atomicCAS(&state[i], kFcReady, kFcRunning) == kFcReady) c = (int)i;
-        for (u32 i = 0; i < NC && c < 0; ++i)
-          if (vstate[i] == kFcIdle && atomicCAS(&state[i], kFcIdle, kFcRunning) == kFcIdle) c = (int)i;
-      }
-      c = __shfl_sync(0xffffffffu, c, 0);
-      if (c < 0) {
-        u32 dead = 0;
-        if (lane == 0) dead = *vDead;
-        dead = __shfl_sync(0xffffffffu, dead, 0);
-        if (dead >= NC) break;
-        if (++spins > kSpinLimit || *(volatile u32*)abortFlag) {
-          if (lane == 0) atomicExch(abortFlag, 1u);
-          break;
-        }
-        __nanosleep(256);
-        continue;
-      }
-      spins = 0;
-      __threadfence_block();
-      Corrector& cx = cxs[c];
-      Counters& mine = mines[c];
-      u8* const myArena = A.arenas + ((u64)blockIdx.x * TALC_FUSED_CTX + (u64)c) * (u64)A.arenaBytes;
-      u32 r = readOf[c];
-      u8 st = kReadYield;
-      bool have = false;
-      if (r != kCtxFree) {  // a walker handed the context back
-        cx.ctr = &mine;
-        cx.walk_done(cx.wq.step);
-        __syncwarp();
-        st = cx.resume();
-        __syncwarp();
-        have = true;
-      }
-      for (;;) {
-        if (have) {
-          if (st == kReadYield) {  // park the frontier for a walker group of this block
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0) {
-              readOf[c] = r;
-              vstate[c] = kFcWalkWait;
-            }
-            __syncwarp();
-            break;
-          }
-          finish_read(A, cx, mine, r, st, lane);
-        }
-        u32 wi = 0;
-        if (lane == 0) wi = atomicAdd(A.workCounter, 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= A.nOrder) {  // the queue is empty: this context retires
-          if (lane == 0) {
-            readOf[c] = kCtxFree;
-            vstate[c] = kFcDead;
-            atomicAdd(&nDead, 1u);
-          }
-          __syncwarp();
-          break;
-        }
-        r = A.order[wi];
-        __syncwarp();
-        cx.T = A.tv;
-        cx.CR = A.cright;
-        cx.CL = A.cleft;
-        cx.P = A.P;
-        cx.tabs = A.tabs;
-        cx.splitWalk = 1;
-        cx.pauseBudget = 0;  // no round to hold up: a read runs until it walks
-        cx.inlineInner = A.inlineInner;
-        cx.inlineBorder = A.inlineBorder;
-        for (int i = 0; i < kNumCounters; ++i) ((u64*)&mine)[i] = 0;
-        cx.ctr = &mine;
-        ReadJob job;
-        job.rd.s = A.bases + A.offs[r];
-        job.rd.len = (u32)(A.offs[r + 1] - A.offs[r]);
-        job.cov = A.cov + A.kmerOff[r];
-        job.arena = myArena;
-        job.arena_bytes = A.arenaBytes;
-        job.wide = A.wide != 0;
-        __syncwarp();
-        st = cx.start(job);
-        __syncwarp();
-        have = true;
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ walker warp: four independent groups of 8 lanes
-    const u32 gl = lane & 7u, gbase = lane & ~7u;
-    const u32 gmask = 0xFFu << gbase;
-    u32 spins = 0;
-    for (;;) {
-      int c = -1;
-      if (gl == 0) {
-        for (u32 i = 0; i < NC && c < 0; ++i)
-          if (vstate[i] == kFcWalkWait && atomicCAS(&state[i], kFcWalkWait, kFcWalking) == kFcWalkWait) c = (int)i;
-      }
-      c = __shfl_sync(gmask, c, gbase);
-      if (c < 0) {
-        u32 dead = 0;
-        if (gl == 0) dead = *vDead;
-        dead = __shfl_sync(gmask, dead, gbase);
-        if (dead >= NC) break;
-        if (++spins > kSpinLimit || *(volatile u32*)abortFlag) break;
-        __nanosleep(128);
-        continue;
-      }
-      spins = 0;
-      __threadfence_block();
-      walk_frontier(cxs[c], mines[c], ~0u, gl, gbase, gmask);
-      __threadfence_block();
-      if (gl == 0) vstate[c] = kFcReady;
-      __syncwarp(gmask);
-    }
-  }
-}
-
 __global__ void ctx_init_kernel(ReadCtx* ctxs, u32 nCtx, u32* readyList, u32* nReady) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nCtx) {
@@ -1071,7 +861,7 @@ int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out) {
                                                                   c->modelTabs + 2 * kModelTabN);
   cudaStreamSynchronize(c->stream);
   if (const char* e2 = getenv("TALC_BLOCKS_PER_SM")) c->blocksPerSm = (u32)std::max(1, atoi(e2));
-  if (const char* e2 = getenv("TALC_SPLIT")) c->splitWalk = (u32)std::max(0, std::min(2, atoi(e2)));
+  if (const char* e2 = getenv("TALC_SPLIT")) c->splitWalk = atoi(e2) != 0;
   if (const char* e2 = getenv("TALC_CTX")) c->nCtxTier1 = (u32)std::max(4, atoi(e2));
   if (const char* e2 = getenv("TALC_WALK_CAP")) c->walkStepCap = (u32)std::max(1, atoi(e2));
   if (const char* e2 = getenv("TALC_PAUSE_CYCLES")) c->pauseCycles = (u32)std::max(0, atoi(e2));
@@ -1109,7 +899,7 @@ int talc_ctx_set_scratch(talc_ctx* c, uint32_t tier1_bytes, uint32_t tier2_bytes
 // monolithic kernel (the round-1 shape, kept for A/B measurements); read_contexts in flight; steps per walk round
 int talc_ctx_set_exec(talc_ctx* c, uint32_t split_walk, uint32_t read_contexts, uint32_t walk_step_cap) {
   if (!c) return TALC_ERR_ARG;
-  if (split_walk) c->splitWalk = split_walk == 1 ? 1u : split_walk == 3 ? 2u : 0u;
+  if (split_walk) c->splitWalk = split_walk == 1 ? 1u : 0u;
   if (read_contexts) c->nCtxTier1 = read_contexts < 4 ? 4 : read_contexts;
   if (walk_step_cap) c->walkStepCap = walk_step_cap;
   return TALC_OK;
@@ -1716,18 +1506,6 @@ int talc_table_lookup(talc_ctx* c, const uint64_t* keys, uint64_t n, uint32_t* c
 // enqueues rounds and polls one counter every few rounds.  nCtx contexts are in flight, each with its own arena.
 static int run_pass(talc_ctx* c, CorrectArgs& A, u32 nCtx, u64* launches) {
   const u32 n = A.nOrder;
-  if (c->splitWalk == 2) {  // fused shape: one persistent launch, contexts per block
-    u32 blocks = (nCtx + TALC_FUSED_CTX - 1) / TALC_FUSED_CTX;
-    u32* dAbort = (u32*)c->misc.p + 200;  // beyond the counters / cursors of the misc block (zeroed with it)
-    fused_kernel<<<blocks, 128, 0, c->stream>>>(A, TALC_FUSED_CTX, dAbort);
-    CUDA_TRY(c, cudaGetLastError());
-    u32 hAbort = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(&hAbort, dAbort, 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (hAbort) { c->err = "fused correction kernel: a wait inside a block exceeded its spin bound"; return TALC_ERR_CUDA; }
-    if (launches) *launches += 1;
-    return TALC_OK;
-  }
   if (!c->splitWalk) {
     u32 blocks = (nCtx + 3) / 4;
     correct_kernel<<<blocks, 128, 0, c->stream>>>(A);
@@ -1913,12 +1691,7 @@ static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const u
   u32 blocksPerSm = c->blocksPerSm;
   u32 blocks = (u32)c->sms * blocksPerSm;
   while (blocks > (u32)c->sms && (u64)(blocks - c->sms) * 4 >= n) blocks -= c->sms;
-  u64 nWarps = (u64)blocks * 4;
-  if (c->splitWalk == 1) nWarps = (u64)std::min<u32>(n, c->nCtxTier1);
-  if (c->splitWalk == 2) {  // contexts = blocks x TALC_FUSED_CTX (arenas are indexed block * TALC_FUSED_CTX + context)
-    const u64 wantBlocks = std::min<u64>((u64)c->sms * blocksPerSm, ((u64)n + TALC_FUSED_CTX - 1) / TALC_FUSED_CTX);
-    nWarps = std::max<u64>(1, wantBlocks) * TALC_FUSED_CTX;
-  }
+  const u64 nWarps = c->splitWalk ? (u64)std::min<u32>(n, c->nCtxTier1) : (u64)blocks * 4;
   const u64 outArenaCap = 2 * totalBases + (u64)n * 64 + 4096;
   CUDA_TRY(c, c->arenas.reserve(std::max<size_t>((size_t)nWarps * c->tier1Bytes, (size_t)c->tier2Warps * c->tier2Bytes)));
   CUDA_TRY(c, c->outArena.reserve(outArenaCap));
@@ -1998,11 +1771,7 @@ static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const u
     B.nOrder = hOver;
     B.arenaBytes = c->tier2Bytes;
     B.lastTier = 1;
-    u32 ctx2 = std::max<u32>(1, std::min<u32>(c->tier2Warps, hOver));
-    if (c->splitWalk == 2) ctx2 = std::max<u32>(TALC_FUSED_CTX, (std::min<u32>(c->tier2Warps, hOver + TALC_FUSED_CTX - 1) / TALC_FUSED_CTX) * TALC_FUSED_CTX);
-    CUDA_TRY(c, c->arenas.reserve((size_t)ctx2 * c->tier2Bytes));  // the first tier is done: the buffer may move
-    B.arenas = (u8*)c->arenas.p;
-    const int rcp = run_pass(c, B, ctx2, &launches);
+    const int rcp = run_pass(c, B, std::max<u32>(1, std::min<u32>(c->tier2Warps, hOver)), &launches);
     if (rcp) return rcp;
   }
   CUDA_TRY(c, cudaEventRecord(c->ev[4], c->stream));

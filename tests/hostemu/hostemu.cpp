@@ -188,6 +188,123 @@ int emu_correct_reads(void* tab, const emu_params* q, const uint8_t* bases, cons
   return 0;
 }
 
+// Two read contexts interleaved on one thread, the way a control warp of the fused kernel multiplexes its block's
+// contexts: start A, start B, then resume whichever has been walked, alternating, until both reads are done.  Contexts are
+// REUSED from one read to the next (as on the device).  Same outputs as emu_correct_reads.
+int emu_correct_interleaved(void* tab, const emu_params* q, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                            uint32_t arena_bytes, uint8_t* out, uint64_t out_capacity, uint64_t* out_offsets, uint8_t* status,
+                            uint64_t* counters) {
+  EmuTable* t = (EmuTable*)tab;
+  Params P = to_params(q);
+  TableView tv;
+  tv.slots = t->slots.data();
+  tv.mask = t->mask;
+  Counters total;
+  memset(&total, 0, sizeof(total));
+  struct Ctx {
+    Corrector cx;
+    Counters mine;
+    std::vector<u8> arena;
+    std::vector<u32> cov;
+    u32 read = 0xFFFFFFFFu;
+    u8 st = 0;
+    bool active = false;
+  };
+  Ctx* C = new Ctx[2];
+  std::vector<std::vector<u8>> results(n_reads);
+  u32 next = 0, done = 0;
+  auto begin = [&](Ctx& c, u32 r) {
+    ReadView rd;
+    rd.s = bases + offsets[r];
+    rd.len = (u32)(offsets[r + 1] - offsets[r]);
+    c.cov.clear();
+    if (rd.len >= P.K)
+      for (u32 i = 0; i + P.K <= rd.len; ++i) {
+        bool ok;
+        u64 km = rd.kmer_at(i, P.K, ok);
+        u32 cc = 0, cl = 0;
+        if (ok) table_lookup(tv, km, cc, cl);
+        c.cov.push_back(cc);
+      }
+    c.arena.resize(arena_bytes);
+    c.cx.T = tv;
+    c.cx.P = P;
+    c.cx.tabs.n = 0;
+    c.cx.tabs.lower = c.cx.tabs.upper = c.cx.tabs.sq = nullptr;
+    memset(&c.mine, 0, sizeof(c.mine));
+    c.cx.ctr = &c.mine;
+    c.cx.splitWalk = 1;
+    c.cx.inlineInner = 0;
+    c.cx.inlineBorder = 6;
+    c.cx.pauseBudget = 0;
+    ReadJob job;
+    job.rd = rd;
+    job.cov = c.cov.data();
+    job.arena = c.arena.data();
+    job.arena_bytes = arena_bytes;
+    job.wide = true;
+    c.read = r;
+    c.active = true;
+    c.st = c.cx.start(job);
+  };
+  auto finish = [&](Ctx& c) {
+    const u32 r = c.read;
+    const u8 st = c.st;
+    c.mine.cells_nw += c.cx.dps.cells_nw;
+    c.mine.cells_lcs += c.cx.dps.cells_lcs;
+    c.mine.cells_ovl += c.cx.dps.cells_ovl;
+    c.mine.cells_xdrop += c.cx.dps.cells_xdrop;
+    if (st == kReadOverflow) total.reads_overflow++;
+    else {
+      const u64* src = (const u64*)&c.mine;
+      u64* dst = (u64*)&total;
+      for (int i = 0; i < kNumCounters; ++i) dst[i] += src[i];
+      if (st == kReadOk) total.reads_ok++;
+    }
+    status[r] = st;
+    const u32 rlen = (u32)(offsets[r + 1] - offsets[r]);
+    const u32 olen = st == kReadOk ? c.cx.corrected_length() : rlen;
+    results[r].resize(olen);
+    if (st == kReadOk) c.cx.emit(results[r].data(), 0, 1);
+    else {
+      ReadView rd;
+      rd.s = bases + offsets[r];
+      rd.len = rlen;
+      for (u32 i = 0; i < rlen; ++i) results[r][i] = code_char(rd.code(i));
+    }
+    if (st != kReadOverflow) total.bases_out += olen;
+    c.active = false;
+    ++done;
+  };
+  while (done < n_reads) {
+    for (int k = 0; k < 2; ++k) {
+      Ctx& c = C[k];
+      if (!c.active) {
+        if (next < n_reads) begin(c, next++);
+        else continue;
+      } else {  // it yielded last time: walk, then resume
+        u32 step = c.cx.wq.step;
+        if (c.cx.wq.border != 2)
+          c.cx.fast_walk_scalar(step, c.cx.wq.pathMax, c.cx.wq.aims, c.cx.wq.nAims, c.cx.wq.border != 0, ~0u);
+        c.cx.walk_done(step);
+        c.st = c.cx.resume();
+      }
+      if (c.st != kReadYield) finish(c);
+    }
+  }
+  u64 pos = 0;
+  out_offsets[0] = 0;
+  for (u32 r = 0; r < n_reads; ++r) {
+    if (pos + results[r].size() > out_capacity) { delete[] C; return -1; }
+    memcpy(out + pos, results[r].data(), results[r].size());
+    pos += results[r].size();
+    out_offsets[r + 1] = pos;
+  }
+  memcpy(counters, &total, sizeof(total));
+  delete[] C;
+  return 0;
+}
+
 int emu_num_counters() { return kNumCounters; }
 
 // ---- primitives

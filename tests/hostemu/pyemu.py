@@ -47,6 +47,8 @@ def lib():
         L.emu_table_free.argtypes = [C.c_void_p]
         L.emu_correct_reads.argtypes = [C.c_void_p, C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                         C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_correct_interleaved.argtypes = [C.c_void_p, C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                              C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_yields.restype = C.c_uint64
         L.emu_nw.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
         L.emu_lcs.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
@@ -106,3 +108,20 @@ class EmuTable:
         if rc != 0:
             raise RuntimeError("emu output buffer too small")
         return out[: int(ooff[-1])], ooff, status[:n], dict(zip(COUNTER_NAMES, [int(x) for x in ctr]))
+
+
+def correct_interleaved(table: EmuTable, reads, offsets, arena_bytes=1 << 20):
+    """Two read contexts multiplexed on one thread (the fused kernel's control warp); same outputs as EmuTable.correct."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    cap = int(offsets[-1]) * 4 + 4096 * n + 4096
+    out = np.zeros(cap, dtype=np.uint8)
+    ooff = np.zeros(n + 1, dtype=np.uint64)
+    status = np.zeros(max(n, 1), dtype=np.uint8)
+    ctr = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    rc = lib().emu_correct_interleaved(table.h, C.byref(table.p), _ptr(reads), _ptr(offsets), n, arena_bytes, _ptr(out), cap,
+                                       _ptr(ooff), _ptr(status), _ptr(ctr))
+    if rc != 0:
+        raise RuntimeError("emu output buffer too small")
+    return out[: int(ooff[-1])], ooff, status[:n], dict(zip(COUNTER_NAMES, [int(x) for x in ctr]))

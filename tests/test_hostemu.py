@@ -189,3 +189,16 @@ def test_suspend_and_resume_is_result_neutral(case_c5):
     assert np.array_equal(st, case.o_status) and np.array_equal(off, case.o_off) and np.array_equal(out, case.o_out)
     for k2 in ("lookups_walk", "steps_inner", "steps_border", "cells_xdrop", "ev_gardening", "ev_cycle"):
         assert ctr[k2] == case.o_ctr[k2], k2
+
+
+def test_two_contexts_interleaved_on_one_thread():
+    """Two read contexts multiplexed on one thread (start A, start B, resume whichever has been walked, contexts reused
+    from read to read): no state of a suspended read lives outside its Corrector and its arena."""
+    g = np.load(GOLD)
+    for name in ("c1", "c3", "c5"):
+        k = int(g[name + "_k"][0])
+        usej = len(g[name + "_jkeys"]) > 0
+        et = pyemu.EmuTable(pyemu.params_from(po.make_params(k=k)), g[name + "_keys"], g[name + "_counts"].astype(np.int64),
+                            g[name + "_jkeys"] if usej else None, g[name + "_jcounts"].astype(np.int64) if usej else None)
+        out, off, st, ctr = pyemu.correct_interleaved(et, g[name + "_reads"], g[name + "_off"])
+        assert np.array_equal(out, g[name + "_out"]) and np.array_equal(st, g[name + "_status"])
