@@ -213,6 +213,8 @@ def run_gpu(args, rank, world, local_rank):
         try:
             t_bcast_ms = ctx.table_broadcast(uid.cpu().numpy(), rank, world, 0)
         finally:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)  # NCCL writes through C stdio, which buffers when stdout is a pipe
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
