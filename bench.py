@@ -201,19 +201,19 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1:
         # replicate: ONE ncclBroadcast of the raw slot array over NVLink, issued by the library itself
         # (talc_table_broadcast); torch.distributed only carries the 128-byte NCCL id to the other ranks
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid.copy_(torch.from_numpy(api.nccl_unique_id()))
-        dist.broadcast(uid, 0)
-        # NCCL prints its version banner on stdout when the library's communicator comes up: stdout carries exactly one
-        # JSON line, so fd 1 points at stderr while native code may print
+        # NCCL prints its version banner on stdout when it is first initialised (ncclGetUniqueId / ncclCommInitRank):
+        # stdout carries exactly one JSON line, so fd 1 points at stderr while the library's NCCL calls run
+        import ctypes
         sys.stdout.flush()
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid.copy_(torch.from_numpy(api.nccl_unique_id()))
+            dist.broadcast(uid, 0)
             t_bcast_ms = ctx.table_broadcast(uid.cpu().numpy(), rank, world, 0)
         finally:
-            import ctypes
             ctypes.CDLL(None).fflush(None)  # NCCL writes through C stdio, which buffers when stdout is a pipe
             sys.stdout.flush()
             os.dup2(saved_fd, 1)

@@ -135,53 +135,55 @@ struct Batch {
 
 class ReadParser {
  public:
-  explicit ReadParser(const std::string& path) : f_(fopen(path.c_str(), "rb")) { buf_.resize(8u << 20); }
+  explicit ReadParser(const std::string& path) : f_(fopen(path.c_str(), "rb")) { buf_.resize(16u << 20); }
   ~ReadParser() { if (f_) fclose(f_); }
   bool is_open() const { return f_ != nullptr; }
   // fills `b` with up to maxReads reads / about maxBases bases; returns false on a parse error.  b.ids.empty()
-  // afterwards means the input is exhausted.
+  // afterwards means the input is exhausted.  Lines are taken straight from the read buffer (memchr for the end of
+  // line, one table-driven pass to validate + drop blanks, bulk append): the reader has to keep several GPUs fed.
   bool next_batch(Batch& b, size_t maxReads, size_t maxBases) {
     b.ids.clear();
     b.bases.clear();
     b.offs.assign(1, 0);
-    std::string line;
+    b.bases.reserve(maxBases + (1u << 20));
     if (pendingHeader_) {  // FASTA: the header that ended the previous batch opens this one
       b.ids.push_back(header_);
       pendingHeader_ = false;
       open_ = true;
     }
-    while (get_line(line)) {
+    const char* p;
+    size_t n;
+    while (get_line(p, n)) {
       if (first_) {
-        if (line.empty()) continue;
-        if (line[0] == '>') fastq_ = false;
-        else if (line[0] == '@') fastq_ = true;
+        if (n == 0) continue;
+        if (p[0] == '>') fastq_ = false;
+        else if (p[0] == '@') fastq_ = true;
         else return false;
         first_ = false;
       }
       if (!fastq_) {
-        if (!line.empty() && line[0] == '>') {
+        if (n && p[0] == '>') {
           if (open_) {
             b.offs.push_back(b.bases.size());
             if (b.ids.size() >= maxReads || b.bases.size() >= maxBases) {
-              header_.assign(line, 1, std::string::npos);
+              header_.assign(p + 1, n - 1);
               pendingHeader_ = true;
               open_ = false;
               return true;
             }
           }
-          b.ids.emplace_back(line, 1, std::string::npos);
+          b.ids.emplace_back(p + 1, n - 1);
           open_ = true;
-        } else if (!push_seq(b, line)) {
+        } else if (!push_seq(b, p, n)) {
           std::cout << "ERROR: Unexpected character found" << std::endl;
           return false;
         }
       } else {
-        if (line.empty()) continue;
-        if (line[0] != '@') return false;
-        b.ids.emplace_back(line, 1, std::string::npos);
-        std::string seq, x;
-        if (!get_line(seq) || !push_seq(b, seq)) { std::cout << "ERROR: Unexpected character found" << std::endl; return false; }
-        if (!get_line(x) || !get_line(x)) return false;
+        if (n == 0) continue;
+        if (p[0] != '@') return false;
+        b.ids.emplace_back(p + 1, n - 1);
+        if (!get_line(p, n) || !push_seq(b, p, n)) { std::cout << "ERROR: Unexpected character found" << std::endl; return false; }
+        if (!get_line(p, n) || !get_line(p, n)) return false;
         b.offs.push_back(b.bases.size());
         if (b.ids.size() >= maxReads || b.bases.size() >= maxBases) return true;
       }
@@ -191,43 +193,63 @@ class ReadParser {
   }
 
  private:
-  static bool push_seq(Batch& b, const std::string& s) {
-    for (const char ch : s) {
-      switch (ch) {
-        case 'A': case 'C': case 'G': case 'T': case 'N': case 'a': case 'c': case 'g': case 't': case 'n':
-          b.bases.push_back((uint8_t)ch);
-          break;
-        case ' ': case '\t': break;
-        default: return false;
-      }
+  // 1: a sequence letter (ACGTN either case), 2: blank to drop, 0: anything else is a parse error
+  static const unsigned char* klass() {
+    static unsigned char t[256];
+    static bool init = false;
+    if (!init) {
+      memset(t, 0, sizeof t);
+      for (const char* q = "ACGTNacgtn"; *q; ++q) t[(unsigned char)*q] = 1;
+      t[(unsigned char)' '] = t[(unsigned char)'\t'] = 2;
+      init = true;
+    }
+    return t;
+  }
+  static bool push_seq(Batch& b, const char* p, size_t n) {
+    const unsigned char* t = klass();
+    unsigned char all = 1;
+    for (size_t i = 0; i < n; ++i) all &= t[(unsigned char)p[i]];  // 1 iff every byte is a sequence letter
+    if (all == 1) {  // the common line: one bulk append
+      b.bases.insert(b.bases.end(), (const uint8_t*)p, (const uint8_t*)p + n);
+      return true;
+    }
+    for (size_t i = 0; i < n; ++i) {
+      const unsigned char k = t[(unsigned char)p[i]];
+      if (k == 1) b.bases.push_back((uint8_t)p[i]);
+      else if (k == 0) return false;
     }
     return true;
   }
-  bool get_line(std::string& out) {  // without the terminator ("\n" or "\r\n"); false at end of file
-    out.clear();
-    bool any = false;
+  // next line without its terminator ("\n" or "\r\n") as a view into the read buffer (valid until the next call);
+  // a line cut by the end of the buffer is moved to its front and completed by the next fread
+  bool get_line(const char*& line, size_t& n) {
     for (;;) {
-      if (pos_ == len_) {
-        if (eof_) break;
-        len_ = fread(&buf_[0], 1, buf_.size(), f_);
-        pos_ = 0;
-        if (len_ == 0) { eof_ = true; break; }
-      }
-      any = true;
-      const char* p = &buf_[pos_];
+      const char* p = buf_.data() + pos_;
       const void* nl = memchr(p, '\n', len_ - pos_);
       if (nl) {
-        const size_t n = (size_t)((const char*)nl - p);
-        out.append(p, n);
+        n = (size_t)((const char*)nl - p);
+        line = p;
         pos_ += n + 1;
-        while (!out.empty() && out.back() == '\r') out.pop_back();
+        while (n && line[n - 1] == '\r') --n;
         return true;
       }
-      out.append(p, len_ - pos_);
-      pos_ = len_;
+      if (eof_) {
+        if (pos_ == len_) return false;
+        n = len_ - pos_;
+        line = p;
+        pos_ = len_;
+        while (n && line[n - 1] == '\r') --n;
+        return true;
+      }
+      const size_t tail = len_ - pos_;  // incomplete line: keep it, read more behind it
+      if (tail && pos_) memmove(&buf_[0], p, tail);
+      if (tail + (1u << 20) > buf_.size()) buf_.resize(buf_.size() * 2);  // a line longer than the buffer
+      pos_ = 0;
+      len_ = tail;
+      const size_t got = fread(&buf_[len_], 1, buf_.size() - len_, f_);
+      if (got == 0) eof_ = true;
+      len_ += got;
     }
-    while (!out.empty() && out.back() == '\r') out.pop_back();
-    return any;
   }
   FILE* f_;
   std::string buf_, header_;
