@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <fstream>
@@ -340,6 +341,8 @@ int main(int argc, const char** argv) {
     return 0;
   }
 
+  const auto tStart = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
   std::vector<talc_ctx*> ctx(cli.gpus, nullptr);
   for (int g = 0; g < cli.gpus; ++g) {
     if (talc_ctx_create(&cli.p, g, &ctx[g]) != 0) {
@@ -347,6 +350,8 @@ int main(int argc, const char** argv) {
       return 2;
     }
   }
+  const double sCtx = since(tStart);
+  const auto tTable = std::chrono::steady_clock::now();
   uint64_t nLines = 0, nKept = 0;
   int rc = -1;
   // --tableCache <file> (extension): reuse the built table if the file exists, else build it from the
@@ -367,6 +372,8 @@ int main(int argc, const char** argv) {
     std::cout << "[TALC]: The de Bruijn Graph is empty...Correction aborted." << std::endl;
     return 1;  // main.cpp:320
   }
+  const double sTable = since(tTable);
+  const auto tRep = std::chrono::steady_clock::now();
   if (cli.gpus > 1) {
     double ms = 0;
     int usedNccl = 0;
@@ -377,6 +384,8 @@ int main(int argc, const char** argv) {
     if (usedNccl) std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (one NCCL broadcast, " << ms << " ms)." << std::endl;
     else std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (peer copies; NCCL not found)." << std::endl;
   }
+  const double sRep = since(tRep);
+  const auto tCorr = std::chrono::steady_clock::now();
   std::vector<talc_stream*> streams(cli.gpus, nullptr);
   for (int g = 0; g < cli.gpus; ++g) {
     if (talc_stream_open(ctx[g], cli.readStats ? 1 : 0, &streams[g]) != 0) {
@@ -471,6 +480,8 @@ int main(int argc, const char** argv) {
     return 0;
   }
   std::cout << "[TALC]: " << nReads << " long read(s) processed" << std::endl;
+  std::cout << "[TALC]: seconds: contexts " << sCtx << ", table " << sTable << ", replication " << sRep << ", correction (read + correct + write) "
+            << since(tCorr) << std::endl;
   std::cout << "[TALC]: Looks like we are done now." << std::endl;
   return 0;
 }

@@ -25,13 +25,15 @@ res = {"reads": n_reads, "bases": bases, "runs": {}}
 digests = set()
 for g in gpus:
     t0 = time.time()
-    rc = subprocess.call([cli, "reads.fa", "--SRCounts", "sr.dump", "-k", str(cfg.k), "-o", "g%d" % g, "--gpus", str(g), "-t", "16"],
-                         cwd=d, stdout=subprocess.DEVNULL)
+    pr = subprocess.run([cli, "reads.fa", "--SRCounts", "sr.dump", "-k", str(cfg.k), "-o", "g%d" % g, "--gpus", str(g), "-t", "16"],
+                        cwd=d, capture_output=True, text=True)
+    rc = pr.returncode
     secs = time.time() - t0
+    phases = [l for l in pr.stdout.splitlines() if "seconds:" in l or "replicated" in l]
     fa = hashlib.sha256(open(os.path.join(d, "g%d.fa" % g), "rb").read()).hexdigest()
     lg = hashlib.sha256(open(os.path.join(d, "g%d.log" % g), "rb").read()).hexdigest() if os.path.exists(os.path.join(d, "g%d.log" % g)) else ""
     digests.add((fa, lg))
-    res["runs"]["gpus_%d" % g] = {"rc": rc, "seconds": round(secs, 2), "mbp_per_s": round(bases / 1e6 / secs, 1), "fa_sha256": fa[:16]}
+    res["runs"]["gpus_%d" % g] = {"rc": rc, "seconds": round(secs, 2), "mbp_per_s": round(bases / 1e6 / secs, 1), "fa_sha256": fa[:16], "phases": phases}
 res["identical_outputs"] = len(digests) == 1
 shutil.rmtree(d, ignore_errors=True)
 print(json.dumps(res))
