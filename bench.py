@@ -168,7 +168,7 @@ def run_reference(args, rank, world):
                              "sample": "%d reads per step of the same read set (oracle restatement, OpenMP over reads)" % nsample},
             "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -201,23 +201,12 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1:
         # replicate: ONE ncclBroadcast of the raw slot array over NVLink, issued by the library itself
         # (talc_table_broadcast); torch.distributed only carries the 128-byte NCCL id to the other ranks
-        # NCCL prints its version banner on stdout when it is first initialised (ncclGetUniqueId / ncclCommInitRank):
-        # stdout carries exactly one JSON line, so fd 1 points at stderr while the library's NCCL calls run
-        import ctypes
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-            if rank == 0:
-                uid.copy_(torch.from_numpy(api.nccl_unique_id()))
-            dist.broadcast(uid, 0)
-            t_bcast_ms = ctx.table_broadcast(uid.cpu().numpy(), rank, world, 0)
-        finally:
-            ctypes.CDLL(None).fflush(None)  # NCCL writes through C stdio, which buffers when stdout is a pipe
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+        # (NCCL prints a version banner through C stdio when first initialised: see _claim_stdout)
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.from_numpy(api.nccl_unique_id()))
+        dist.broadcast(uid, 0)
+        t_bcast_ms = ctx.table_broadcast(uid.cpu().numpy(), rank, world, 0)
         info = ctx.table_info()
     # this rank's reads: batch_reads per step, a different slice every step (and every rank)
     nsteps = args.warmup + args.steps + 1  # +1 slice for the e2e leg warm-up
@@ -404,7 +393,7 @@ def run_gpu(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], line["parity"] = cpu_baseline(args, cfg, cpu_keys, use_j, reads, roff, (g_out, g_off, g_st))
             bad = line["parity"]["mismatch"]
-        print(json.dumps(line), flush=True)
+        emit(line)
         if bad or replica_parity == "MISMATCH":
             print("bench.py: PARITY FAILURE -- the numbers above are void", file=sys.stderr, flush=True)
             if world > 1:
@@ -532,8 +521,31 @@ def cpu_baseline(args, cfg, cpu_keys, use_j, reads, roff, gpu):
     return base, parity
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries underneath (NCCL's version banner -- torch's communicator and
+    the library's own --, anything else that writes to fd 1 through C stdio) would add lines, so the process keeps a
+    private duplicate of the real stdout for that line and points fd 1 at stderr for everything else."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

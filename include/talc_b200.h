@@ -197,6 +197,9 @@ int talc_coverage_batch(talc_ctx* ctx, const uint8_t* bases, const uint64_t* off
  * One caller thread per stream; while a stream is open its context must not be used for other correction calls.  */
 typedef struct talc_stream talc_stream;
 int talc_stream_open(talc_ctx* ctx, int want_read_stats, talc_stream** out);
+/* optional: allocate every slot's pinned / device buffers now for batches of up to max_reads reads and max_bases bases
+ * (otherwise the first batch through each slot pays for it); may be called while the table is still loading        */
+int talc_stream_reserve(talc_stream* s, uint32_t max_reads, uint64_t max_bases);
 int talc_stream_submit(talc_stream* s, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads);
 int talc_stream_next(talc_stream* s, const uint8_t** out, const uint64_t** out_offsets, const uint8_t** status,
                      uint32_t* n_reads, const uint32_t** read_stats, talc_counters* counters);

@@ -81,6 +81,7 @@ def lib():
         L.talc_table_broadcast.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.talc_stream_open.argtypes = [vp, C.c_int, C.POINTER(vp)]
         L.talc_stream_submit.argtypes = [vp, vp, vp, C.c_uint32]
+        L.talc_stream_reserve.argtypes = [vp, C.c_uint32, C.c_uint64]
         L.talc_stream_next.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(vp),
                                        C.POINTER(TalcCounters)]
         L.talc_stream_pending.restype = C.c_uint64
@@ -343,6 +344,9 @@ class TalcStream:
     def _check(self, rc, what):
         if rc != 0:
             raise TalcError("%s failed (%d): %s" % (what, rc, lib().talc_stream_last_error(self.h).decode()))
+
+    def reserve(self, max_reads: int, max_bases: int):
+        self._check(lib().talc_stream_reserve(self.h, max_reads, max_bases), "talc_stream_reserve")
 
     def submit(self, reads: np.ndarray, offsets: np.ndarray):
         reads = np.ascontiguousarray(reads, dtype=np.uint8)

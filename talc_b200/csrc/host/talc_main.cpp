@@ -30,6 +30,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "talc_b200.h"
@@ -344,13 +345,33 @@ int main(int argc, const char** argv) {
   const auto tStart = std::chrono::steady_clock::now();
   auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
   std::vector<talc_ctx*> ctx(cli.gpus, nullptr);
-  for (int g = 0; g < cli.gpus; ++g) {
-    if (talc_ctx_create(&cli.p, g, &ctx[g]) != 0) {
-      std::cerr << "talc: cannot create a GPU context on device " << g << ": " << talc_last_error(nullptr) << "\n";
-      return 2;
-    }
+  {  // one thread per device: creating a CUDA context takes a few hundred ms each
+    std::vector<int> rcs(cli.gpus, 0);
+    std::vector<std::string> errs(cli.gpus);  // the library keeps the creation error per thread
+    std::vector<std::thread> th;
+    for (int g = 0; g < cli.gpus; ++g)
+      th.emplace_back([&, g]() {
+        rcs[g] = talc_ctx_create(&cli.p, g, &ctx[g]);
+        if (rcs[g] != 0) errs[g] = talc_last_error(nullptr);
+      });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < cli.gpus; ++g)
+      if (rcs[g] != 0) {
+        std::cerr << "talc: cannot create a GPU context on device " << g << ": " << errs[g] << "\n";
+        return 2;
+      }
   }
   const double sCtx = since(tStart);
+  // the streams' pinned staging is page-locked while the table loads (one thread per device)
+  std::vector<talc_stream*> streams(cli.gpus, nullptr);
+  std::vector<int> openRc(cli.gpus, 0);
+  std::vector<std::thread> openers;
+  for (int g = 0; g < cli.gpus; ++g)
+    openers.emplace_back([&, g]() {
+      openRc[g] = talc_stream_open(ctx[g], cli.readStats ? 1 : 0, &streams[g]);
+      if (openRc[g] == 0)
+        openRc[g] = talc_stream_reserve(streams[g], (uint32_t)cli.batchReads, (uint64_t)cli.batchBases + (8u << 20));
+    });
   const auto tTable = std::chrono::steady_clock::now();
   uint64_t nLines = 0, nKept = 0;
   int rc = -1;
@@ -370,6 +391,7 @@ int main(int argc, const char** argv) {
   std::cout << "[TALC]: SR-dBG contains " << nKept << " nodes." << std::endl;
   if (nKept == 0) {
     std::cout << "[TALC]: The de Bruijn Graph is empty...Correction aborted." << std::endl;
+    for (auto& t : openers) t.join();
     return 1;  // main.cpp:320
   }
   const double sTable = since(tTable);
@@ -379,20 +401,21 @@ int main(int argc, const char** argv) {
     int usedNccl = 0;
     if (talc_table_replicate(ctx.data(), cli.gpus, &ms, &usedNccl) != 0) {
       std::cerr << "talc: " << talc_last_error(ctx[0]) << "\n";
+      for (auto& t : openers) t.join();
       return 2;
     }
     if (usedNccl) std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (one NCCL broadcast, " << ms << " ms)." << std::endl;
     else std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (peer copies; NCCL not found)." << std::endl;
   }
   const double sRep = since(tRep);
-  const auto tCorr = std::chrono::steady_clock::now();
-  std::vector<talc_stream*> streams(cli.gpus, nullptr);
+  for (auto& t : openers) t.join();
   for (int g = 0; g < cli.gpus; ++g) {
-    if (talc_stream_open(ctx[g], cli.readStats ? 1 : 0, &streams[g]) != 0) {
-      std::cerr << "talc: " << talc_last_error(ctx[g]) << "\n";
+    if (openRc[g] != 0) {
+      std::cerr << "talc: cannot open a stream on device " << g << ": " << (streams[g] ? talc_stream_last_error(streams[g]) : talc_last_error(ctx[g])) << "\n";
       return 2;
     }
   }
+  const auto tCorr = std::chrono::steady_clock::now();
 
   // ---- writer: corrected records in input order into <o>.fa.partial, renamed when the run is complete; the failed-read
   // log (input order = the reference's order under -t 1) and the optional stats rows are appended as batches arrive
@@ -402,6 +425,7 @@ int main(int argc, const char** argv) {
   IdQueue idq;
   int writerRc = 0;
   uint64_t nReads = 0, nResource = 0;
+  double sWait = 0, sFormat = 0, sWrite = 0, sParse = 0, sSubmit = 0;  // where the threads of this phase spent their time
   std::thread writer([&]() {
     std::ofstream lg, st;
     std::vector<std::string> parts;
@@ -411,7 +435,10 @@ int main(int argc, const char** argv) {
       const uint64_t* ooffs = nullptr;
       const uint32_t* stats = nullptr;
       uint32_t n = 0;
-      if (talc_stream_next(s, &out, &ooffs, &status, &n, &stats, nullptr) != 0 || n != b->ids.size()) {
+      auto t0 = std::chrono::steady_clock::now();
+      const int nrc = talc_stream_next(s, &out, &ooffs, &status, &n, &stats, nullptr);
+      sWait += since(t0);
+      if (nrc != 0 || n != b->ids.size()) {
         std::cerr << "talc: correction failed on device " << (b->seq % cli.gpus) << ": " << talc_stream_last_error(s) << "\n";
         writerRc = 2;
         while (idq.pop()) {}  // keep draining so that the reader does not block for ever
@@ -436,8 +463,12 @@ int main(int argc, const char** argv) {
              << "\t" << (v == TALC_READ_OK ? ooffs[r + 1] - ooffs[r] : 0);
         }
       }
+      t0 = std::chrono::steady_clock::now();
       format_fasta(*b, out, ooffs, cli.threads, parts);
+      sFormat += since(t0);
+      t0 = std::chrono::steady_clock::now();
       for (const auto& p : parts) fwrite(p.data(), 1, p.size(), fo);
+      sWrite += since(t0);
       nReads += n;
     }
   });
@@ -451,7 +482,10 @@ int main(int argc, const char** argv) {
     b->seq = seq;
     talc_stream* s = streams[seq % cli.gpus];
     if (b->offs.size() != b->ids.size() + 1) { inputOk = false; break; }
-    if (talc_stream_submit(s, b->bases.data(), b->offs.data(), (uint32_t)b->ids.size()) != 0) {
+    auto t0 = std::chrono::steady_clock::now();
+    const int src = talc_stream_submit(s, b->bases.data(), b->offs.data(), (uint32_t)b->ids.size());
+    sSubmit += since(t0);
+    if (src != 0) {
       std::cerr << "talc: " << talc_stream_last_error(s) << "\n";
       submitRc = 2;
       break;
@@ -461,14 +495,23 @@ int main(int argc, const char** argv) {
     ++seq;
     if (writerRc) break;
     auto nb = std::make_shared<Batch>();
-    if (!parser.next_batch(*nb, (size_t)cli.batchReads, (size_t)cli.batchBases)) { inputOk = false; break; }
+    t0 = std::chrono::steady_clock::now();
+    const bool parsed = parser.next_batch(*nb, (size_t)cli.batchReads, (size_t)cli.batchBases);
+    sParse += since(t0);
+    if (!parsed) { inputOk = false; break; }
     b = nb;
   }
   idq.finish();
   writer.join();
   fclose(fo);
-  for (auto* s : streams) talc_stream_close(s);
-  for (auto* c : ctx) talc_ctx_destroy(c);
+  const double sCorr = since(tCorr);
+  // error paths release everything in order; a complete run leaves the buffers to the process exit (unpinning and
+  // freeing several GB per device one allocation at a time took 0.3 s on one GPU and 2.5 s on two)
+  auto teardown = [&]() {
+    for (auto* s : streams) talc_stream_close(s);
+    for (auto* c : ctx) talc_ctx_destroy(c);
+  };
+  if (submitRc || writerRc || !inputOk) teardown();
   if (submitRc || writerRc) { remove(faTmp.c_str()); return 2; }
   if (!inputOk) {  // the reference would have failed while loading, before writing anything
     remove(faTmp.c_str());
@@ -481,7 +524,11 @@ int main(int argc, const char** argv) {
   }
   std::cout << "[TALC]: " << nReads << " long read(s) processed" << std::endl;
   std::cout << "[TALC]: seconds: contexts " << sCtx << ", table " << sTable << ", replication " << sRep << ", correction (read + correct + write) "
-            << since(tCorr) << std::endl;
+            << sCorr << " [reader: parse " << sParse << ", submit " << sSubmit << "; writer: wait " << sWait << ", format " << sFormat
+            << ", write " << sWrite << "]" << std::endl;
   std::cout << "[TALC]: Looks like we are done now." << std::endl;
-  return 0;
+  std::cout.flush();
+  std::cerr.flush();
+  fflush(nullptr);
+  _exit(0);  // outputs are closed and renamed; see the note on teardown above
 }

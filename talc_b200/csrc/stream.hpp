@@ -109,8 +109,7 @@ extern "C" {
 int talc_stream_open(talc_ctx* c, int want_read_stats, talc_stream** out) {
   if (!c || !out) return TALC_ERR_ARG;
   *out = nullptr;
-  if (!c->tableReady) { c->err = "no k-mer table loaded"; return TALC_ERR_NO_TABLE; }
-  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaSetDevice(c->device));  // the table may still be loading: it is only needed when a batch runs
   talc_stream* s = new talc_stream;
   s->c = c;
   s->wantStats = want_read_stats != 0;
@@ -126,6 +125,26 @@ int talc_stream_open(talc_ctx* c, int want_read_stats, talc_stream** out) {
   }
   s->worker = std::thread(stream_worker, s);
   *out = s;
+  return TALC_OK;
+}
+
+// Optional: allocate the pinned host and device buffers of every slot now, for batches of up to max_reads reads and
+// max_bases bases (page-locking hundreds of MB takes ~0.1 s per buffer and holds the driver's lock: better paid once,
+// before the first batch, and in parallel with the table load, than by the first batches).
+int talc_stream_reserve(talc_stream* s, uint32_t max_reads, uint64_t max_bases) {
+  if (!s) return TALC_ERR_ARG;
+  talc_ctx* c = s->c;
+  if (cudaSetDevice(c->device) != cudaSuccess) { s->err = "cudaSetDevice failed"; return TALC_ERR_CUDA; }
+  const u64 outCap = 2 * max_bases + (u64)max_reads * 64 + 4096;
+  for (auto& sl : s->slot) {
+    bool ok = sl.hBases.reserve(max_bases + 64) == cudaSuccess && sl.hOffs.reserve((size_t)(max_reads + 1) * 8) == cudaSuccess &&
+              sl.hOutOffs.reserve((size_t)(max_reads + 1) * 8) == cudaSuccess && sl.hStatus.reserve(max_reads + 1) == cudaSuccess &&
+              sl.hOut.reserve(max_bases + max_bases / 16 + 64) == cudaSuccess && sl.dBases.reserve(max_bases + 64) == cudaSuccess &&
+              sl.dOffs.reserve((size_t)(max_reads + 1) * 8) == cudaSuccess && sl.dOut.reserve(outCap) == cudaSuccess &&
+              sl.dOutOffs.reserve((size_t)(max_reads + 1) * 8) == cudaSuccess && sl.dStatus.reserve(max_reads + 1) == cudaSuccess;
+    if (ok && s->wantStats) ok = sl.hStats.reserve((size_t)max_reads * 8 + 8) == cudaSuccess && sl.dStats.reserve((size_t)max_reads * 8 + 8) == cudaSuccess;
+    if (!ok) { s->err = "talc_stream_reserve: out of pinned host or device memory"; return TALC_ERR_CUDA; }
+  }
   return TALC_OK;
 }
 
