@@ -345,33 +345,13 @@ int main(int argc, const char** argv) {
   const auto tStart = std::chrono::steady_clock::now();
   auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
   std::vector<talc_ctx*> ctx(cli.gpus, nullptr);
-  {  // one thread per device: creating a CUDA context takes a few hundred ms each
-    std::vector<int> rcs(cli.gpus, 0);
-    std::vector<std::string> errs(cli.gpus);  // the library keeps the creation error per thread
-    std::vector<std::thread> th;
-    for (int g = 0; g < cli.gpus; ++g)
-      th.emplace_back([&, g]() {
-        rcs[g] = talc_ctx_create(&cli.p, g, &ctx[g]);
-        if (rcs[g] != 0) errs[g] = talc_last_error(nullptr);
-      });
-    for (auto& t : th) t.join();
-    for (int g = 0; g < cli.gpus; ++g)
-      if (rcs[g] != 0) {
-        std::cerr << "talc: cannot create a GPU context on device " << g << ": " << errs[g] << "\n";
-        return 2;
-      }
+  for (int g = 0; g < cli.gpus; ++g) {  // (one thread per device was measured: no faster, the driver serialises it)
+    if (talc_ctx_create(&cli.p, g, &ctx[g]) != 0) {
+      std::cerr << "talc: cannot create a GPU context on device " << g << ": " << talc_last_error(nullptr) << "\n";
+      return 2;
+    }
   }
   const double sCtx = since(tStart);
-  // the streams' pinned staging is page-locked while the table loads (one thread per device)
-  std::vector<talc_stream*> streams(cli.gpus, nullptr);
-  std::vector<int> openRc(cli.gpus, 0);
-  std::vector<std::thread> openers;
-  for (int g = 0; g < cli.gpus; ++g)
-    openers.emplace_back([&, g]() {
-      openRc[g] = talc_stream_open(ctx[g], cli.readStats ? 1 : 0, &streams[g]);
-      if (openRc[g] == 0)
-        openRc[g] = talc_stream_reserve(streams[g], (uint32_t)cli.batchReads, (uint64_t)cli.batchBases + (8u << 20));
-    });
   const auto tTable = std::chrono::steady_clock::now();
   uint64_t nLines = 0, nKept = 0;
   int rc = -1;
@@ -391,7 +371,6 @@ int main(int argc, const char** argv) {
   std::cout << "[TALC]: SR-dBG contains " << nKept << " nodes." << std::endl;
   if (nKept == 0) {
     std::cout << "[TALC]: The de Bruijn Graph is empty...Correction aborted." << std::endl;
-    for (auto& t : openers) t.join();
     return 1;  // main.cpp:320
   }
   const double sTable = since(tTable);
@@ -401,20 +380,35 @@ int main(int argc, const char** argv) {
     int usedNccl = 0;
     if (talc_table_replicate(ctx.data(), cli.gpus, &ms, &usedNccl) != 0) {
       std::cerr << "talc: " << talc_last_error(ctx[0]) << "\n";
-      for (auto& t : openers) t.join();
       return 2;
     }
     if (usedNccl) std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (one NCCL broadcast, " << ms << " ms)." << std::endl;
     else std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (peer copies; NCCL not found)." << std::endl;
   }
   const double sRep = since(tRep);
-  for (auto& t : openers) t.join();
-  for (int g = 0; g < cli.gpus; ++g) {
-    if (openRc[g] != 0) {
-      std::cerr << "talc: cannot open a stream on device " << g << ": " << (streams[g] ? talc_stream_last_error(streams[g]) : talc_last_error(ctx[g])) << "\n";
-      return 2;
+  // one stream per device; its pinned staging is page-locked now, one thread per device, and not while the table
+  // loads or NCCL starts up: page-locking contends with every other mapping the process makes (measured: table load
+  // 0.25 -> 2.7 s, NCCL start-up 1 -> 8 s when run side by side)
+  const auto tOpen = std::chrono::steady_clock::now();
+  std::vector<talc_stream*> streams(cli.gpus, nullptr);
+  {
+    std::vector<int> openRc(cli.gpus, 0);
+    std::vector<std::thread> openers;
+    for (int g = 0; g < cli.gpus; ++g)
+      openers.emplace_back([&, g]() {
+        openRc[g] = talc_stream_open(ctx[g], cli.readStats ? 1 : 0, &streams[g]);
+        if (openRc[g] == 0)
+          openRc[g] = talc_stream_reserve(streams[g], (uint32_t)cli.batchReads, (uint64_t)cli.batchBases + (8u << 20));
+      });
+    for (auto& t : openers) t.join();
+    for (int g = 0; g < cli.gpus; ++g) {
+      if (openRc[g] != 0) {
+        std::cerr << "talc: cannot open a stream on device " << g << ": " << (streams[g] ? talc_stream_last_error(streams[g]) : talc_last_error(ctx[g])) << "\n";
+        return 2;
+      }
     }
   }
+  const double sOpen = since(tOpen);
   const auto tCorr = std::chrono::steady_clock::now();
 
   // ---- writer: corrected records in input order into <o>.fa.partial, renamed when the run is complete; the failed-read
@@ -523,7 +517,7 @@ int main(int argc, const char** argv) {
     return 0;
   }
   std::cout << "[TALC]: " << nReads << " long read(s) processed" << std::endl;
-  std::cout << "[TALC]: seconds: contexts " << sCtx << ", table " << sTable << ", replication " << sRep << ", correction (read + correct + write) "
+  std::cout << "[TALC]: seconds: contexts " << sCtx << ", table " << sTable << ", replication " << sRep << ", staging " << sOpen << ", correction (read + correct + write) "
             << sCorr << " [reader: parse " << sParse << ", submit " << sSubmit << "; writer: wait " << sWait << ", format " << sFormat
             << ", write " << sWrite << "]" << std::endl;
   std::cout << "[TALC]: Looks like we are done now." << std::endl;

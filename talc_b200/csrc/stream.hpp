@@ -11,25 +11,50 @@
 #pragma once
 #include <condition_variable>
 #include <mutex>
+#include <sys/mman.h>
 #include <thread>
 
+// Page-locked host staging.  Large buffers are anonymous mappings advised to use huge pages and then registered:
+// measured on the B200 hosts, 1 GiB costs 0.13-0.16 s that way against 0.47 s through cudaHostAlloc (4 KB pages), and
+// copies from it run at the same 56 GB/s (tools/probes/pin_probe.cu).
 struct PinBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool mapped = false;  // mmap + cudaHostRegister (else cudaHostAlloc)
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-    const size_t want = bytes + bytes / 8 + 4096;
+    release();
+    size_t want = bytes + bytes / 8 + 4096;
+    if (want >= (4u << 20)) {
+      want = (want + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+      void* q = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+      if (q != MAP_FAILED) {
+        madvise(q, want, MADV_HUGEPAGE);  // advisory: 4 KB pages still work
+        if (cudaHostRegister(q, want, cudaHostRegisterPortable) == cudaSuccess) {
+          p = q;
+          cap = want;
+          mapped = true;
+          return cudaSuccess;
+        }
+        (void)cudaGetLastError();
+        munmap(q, want);
+      }
+    }
     cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
     if (e == cudaSuccess) cap = want;
+    else p = nullptr;
     return e;
   }
   void release() {
-    if (p) cudaFreeHost(p);
+    if (p && mapped) {
+      cudaHostUnregister(p);
+      munmap(p, cap);
+    } else if (p) {
+      cudaFreeHost(p);
+    }
     p = nullptr;
     cap = 0;
+    mapped = false;
   }
 };
 
