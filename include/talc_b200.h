@@ -97,6 +97,14 @@ int talc_ctx_create(const talc_params* p, int cuda_device, talc_ctx** out);
 void talc_ctx_destroy(talc_ctx* ctx);
 const char* talc_last_error(talc_ctx* ctx);   /* ctx may be NULL: last create error */
 
+/* A lane: a second context on the same device that borrows the tables of `parent` and follows its settings, with its
+ * own CUDA stream and scratch memory.  Two host threads correcting batches through a context and its lane overlap on
+ * the device: a batch ends with a tail of a few long reads (one warp per read), and the other batch's blocks fill the
+ * SMs that tail leaves idle (+8 % on the bench workload).  The streamed calls below use a lane internally.  Table
+ * loading calls are refused on a lane; destroy it (talc_ctx_destroy) before its parent.  No reference counterpart
+ * (the reference's unit of concurrency is the OpenMP thread of main.cpp:247).                                       */
+int talc_ctx_create_lane(talc_ctx* parent, talc_ctx** lane);
+
 /* scratch sizing (optional): bytes per thread for the first and second tier, warps (= reads in flight) of the second tier */
 int talc_ctx_set_scratch(talc_ctx* ctx, uint32_t tier1_bytes, uint32_t tier2_bytes, uint32_t tier2_threads);
 

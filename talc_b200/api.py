@@ -50,6 +50,7 @@ def lib():
         L.talc_params_default.argtypes = [C.POINTER(TalcParams), C.c_uint32]
         L.talc_ctx_create.argtypes = [C.POINTER(TalcParams), C.c_int, C.POINTER(vp)]
         L.talc_ctx_destroy.argtypes = [vp]
+        L.talc_ctx_create_lane.argtypes = [vp, C.POINTER(vp)]
         L.talc_last_error.restype = C.c_char_p
         L.talc_last_error.argtypes = [vp]
         L.talc_ctx_set_scratch.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -121,6 +122,15 @@ class Talc:
         if rc != 0:
             raise TalcError("talc_ctx_create failed (%d): %s" % (rc, lib().talc_last_error(None).decode()))
 
+    def create_lane(self) -> "Talc":
+        """A second context on the same device borrowing this one's tables (talc_ctx_create_lane): batches corrected
+        through both from two threads overlap their tails on the device.  Close it before this context."""
+        lane = Talc.__new__(Talc)
+        lane.params = self.params
+        lane.h = C.c_void_p()
+        self._check(lib().talc_ctx_create_lane(self.h, C.byref(lane.h)), "talc_ctx_create_lane")
+        return lane
+
     def close(self):
         if self.h:
             lib().talc_ctx_destroy(self.h)
@@ -140,7 +150,7 @@ class Talc:
         self._check(lib().talc_ctx_set_scratch(self.h, tier1_bytes, tier2_bytes, tier2_threads), "talc_ctx_set_scratch")
 
     def set_exec(self, split_walk=0, read_contexts=0, walk_step_cap=0):
-        """split_walk: 1 = suspendable reads + walk kernel (default), 2 = monolithic kernel; 0 keeps a value."""
+        """split_walk: 1 = suspendable reads + walk kernel, 2 = one monolithic kernel (the default); 0 keeps a value."""
         self._check(lib().talc_ctx_set_exec(self.h, split_walk, read_contexts, walk_step_cap), "talc_ctx_set_exec")
 
     # ---- table

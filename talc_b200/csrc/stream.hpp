@@ -72,28 +72,36 @@ struct StreamSlot {
 
 struct talc_stream {
   static const int kSlots = 4;
+  static const int kMaxLanes = 2;
   talc_ctx* c = nullptr;
+  // Two batches may be on the device at once ("lanes"): the kernels of batch i+1 are queued on their own stream with
+  // their own scratch while batch i runs, so that its blocks start on the SMs that the last, longest reads of batch i
+  // no longer fill (the per-read program is one warp per read: a batch ends with a tail of a few long reads).  Lane 0
+  // is the caller's context, lane 1 a lane of it (talc_ctx_create_lane).
+  talc_ctx* lane[kMaxLanes] = {nullptr, nullptr};
+  int nLanes = 1;
   bool wantStats = false;
   StreamSlot slot[kSlots];
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
-  std::thread worker;
+  std::thread worker[kMaxLanes];
   std::mutex mu;
   std::condition_variable cv;
-  u64 seqSubmit = 0, seqRun = 0, seqFetch = 0;
+  u64 seqSubmit = 0, seqFetch = 0;
   bool closing = false;
   std::string err;
 };
 
-static void stream_worker(talc_stream* s) {
-  talc_ctx* c = s->c;
+static void stream_worker(talc_stream* s, int w) {
+  talc_ctx* c = s->lane[w];
   cudaSetDevice(c->device);
-  for (;;) {
-    StreamSlot* sl = nullptr;
+  for (u64 seq = (u64)w;; seq += (u64)s->nLanes) {
+    StreamSlot* sl = &s->slot[seq % talc_stream::kSlots];
     {
       std::unique_lock<std::mutex> lk(s->mu);
-      s->cv.wait(lk, [&] { return s->closing || s->slot[s->seqRun % talc_stream::kSlots].state == 1; });
-      sl = &s->slot[s->seqRun % talc_stream::kSlots];
-      if (sl->state != 1) return;  // closing and nothing left to run
+      // the slot of batch `seq` is in state 1 only once that very batch has been submitted: its previous tenant
+      // (seq - kSlots) has been fetched and released by then
+      s->cv.wait(lk, [&] { return s->closing || (s->seqSubmit > seq && sl->state == 1); });
+      if (!(s->seqSubmit > seq && sl->state == 1)) return;  // closing and nothing left to run
     }
     int rc = TALC_OK;
     cudaError_t e = cudaStreamWaitEvent(c->stream, sl->h2dDone, 0);
@@ -103,8 +111,8 @@ static void stream_worker(talc_stream* s) {
                                      sl->dOut.cap, (u64*)sl->dOutOffs.p, (u8*)sl->dStatus.p, &sl->ctr,
                                      s->wantStats ? (u32*)sl->dStats.p : nullptr);
     if (rc == TALC_OK) {
-      // the compute stream is idle here (the call above ends with a synchronize): results leave on the copy-out
-      // stream while the next batch computes
+      // this lane's compute stream is idle here (the call above ends with a synchronize): results leave on the
+      // copy-out stream while the next batch computes
       const u64 totalOut = sl->n ? sl->ctr.bases_out : 0;
       bool ok = sl->hOut.reserve(totalOut + 64) == cudaSuccess;
       ok = ok && cudaMemcpyAsync(sl->hOutOffs.p, sl->dOutOffs.p, (size_t)(sl->n + 1) * 8, cudaMemcpyDeviceToHost, s->copyOut) == cudaSuccess;
@@ -123,7 +131,6 @@ static void stream_worker(talc_stream* s) {
       std::lock_guard<std::mutex> lk(s->mu);
       sl->rc = rc;
       sl->state = 2;
-      s->seqRun++;
     }
     s->cv.notify_all();
   }
@@ -148,7 +155,16 @@ int talc_stream_open(talc_ctx* c, int want_read_stats, talc_stream** out) {
     delete s;
     return TALC_ERR_CUDA;
   }
-  s->worker = std::thread(stream_worker, s);
+  s->lane[0] = c;
+  s->nLanes = 2;
+  if (const char* e = getenv("TALC_STREAM_LANES")) s->nLanes = atoi(e) >= 2 ? 2 : 1;  // 1 = one batch at a time (A/B measurements)
+  if (s->nLanes == 2) {
+    if (c->parent || talc_ctx_create_lane(c, &s->lane[1]) != TALC_OK) {
+      s->nLanes = 1;  // no second lane (memory, or the caller's context is a lane itself): one batch at a time
+      s->lane[1] = nullptr;
+    }
+  }
+  for (int w = 0; w < s->nLanes; ++w) s->worker[w] = std::thread(stream_worker, s, w);
   *out = s;
   return TALC_OK;
 }
@@ -263,7 +279,9 @@ void talc_stream_close(talc_stream* s) {
     s->closing = true;
   }
   s->cv.notify_all();
-  if (s->worker.joinable()) s->worker.join();
+  for (auto& t : s->worker)
+    if (t.joinable()) t.join();
+  if (s->lane[1]) talc_ctx_destroy(s->lane[1]);
   cudaSetDevice(s->c->device);
   cudaStreamSynchronize(s->copyIn);
   cudaStreamSynchronize(s->copyOut);

@@ -740,6 +740,7 @@ struct talc_ctx {
   u64 nEntries = 0;
   bool tableOwned = true;
   bool tableReady = false;
+  talc_ctx* parent = nullptr;  // a lane (talc_ctx_create_lane): tables and settings are the parent's, scratch and stream its own
   // where the table came from (recorded in the binary cache so that a cache of other inputs is not reused silently)
   u32 provJunctions = 0;
   u64 provDumpSize = 0, provDumpMtime = 0, provJuncSize = 0, provJuncMtime = 0;
@@ -875,6 +876,10 @@ void talc_ctx_destroy(talc_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->parent) {  // a lane borrows its tables
+    c->slots = nullptr;
+    c->ctxRight = c->ctxLeft = nullptr;
+  }
   if (c->slots && c->tableOwned) cudaFree(c->slots);
   free_ctx_tables(c);
   if (c->modelTabs) cudaFree(c->modelTabs);
@@ -885,6 +890,43 @@ void talc_ctx_destroy(talc_ctx* c) {
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
   delete c;
+}
+
+// A lane: a second context of the same device that borrows the tables and follows the settings of `parent` but has its
+// own stream and scratch.  Batches corrected through a context and its lane from two host threads overlap on the
+// device: the blocks of one batch start on the SMs that the last, longest reads of the other no longer fill (the
+// per-read program is one warp per read, so every batch ends with a tail of a few long reads).  talc_stream uses one
+// internally.  Destroy the lane (talc_ctx_destroy) before its parent.
+static void lane_follow(talc_ctx* sh) {
+  const talc_ctx* c = sh->parent;
+  sh->params = c->params;
+  sh->P = c->P;
+  sh->slots = c->slots;
+  sh->capacity = c->capacity;
+  sh->nEntries = c->nEntries;
+  sh->tableOwned = false;
+  sh->tableReady = c->tableReady;
+  sh->ctxRight = c->ctxRight;
+  sh->ctxLeft = c->ctxLeft;
+  sh->ctxCap = c->ctxCap;
+  sh->tier1Bytes = c->tier1Bytes;
+  sh->tier2Bytes = c->tier2Bytes;
+  sh->tier2Warps = c->tier2Warps;
+  sh->blocksPerSm = c->blocksPerSm;
+  sh->splitWalk = c->splitWalk;
+  sh->nCtxTier1 = c->nCtxTier1;
+  sh->walkStepCap = c->walkStepCap;
+  sh->pauseCycles = c->pauseCycles;
+  sh->inlineInner = c->inlineInner;
+  sh->inlineBorder = c->inlineBorder;
+}
+int talc_ctx_create_lane(talc_ctx* parent, talc_ctx** out) {
+  if (!parent || !out || parent->parent) return TALC_ERR_ARG;
+  const int rc = talc_ctx_create(&parent->params, parent->device, out);
+  if (rc != TALC_OK) { parent->err = std::string("talc_ctx_create_lane: ") + g_createError; return rc; }
+  (*out)->parent = parent;
+  lane_follow(*out);
+  return TALC_OK;
 }
 
 int talc_ctx_set_scratch(talc_ctx* c, uint32_t tier1_bytes, uint32_t tier2_bytes, uint32_t tier2_threads) {
@@ -908,6 +950,7 @@ int talc_ctx_set_exec(talc_ctx* c, uint32_t split_walk, uint32_t read_contexts, 
 // ---------------------------------------------------------------------------------- table
 int talc_table_alloc(talc_ctx* c, uint64_t capacity_slots) {
   if (!c || capacity_slots < 2 || (capacity_slots & (capacity_slots - 1))) return TALC_ERR_ARG;
+  if (c->parent) { c->err = "a lane has no table of its own: load it into the context the lane was made from"; return TALC_ERR_ARG; }
   CUDA_TRY(c, cudaSetDevice(c->device));
   if (c->slots && c->tableOwned) cudaFree(c->slots);
   free_ctx_tables(c);
@@ -1673,6 +1716,7 @@ static int correct_batch_device_impl(talc_ctx* c, const uint8_t* dBases, const u
                                      uint8_t* dOut, uint64_t outCapacity, uint64_t* dOutOffs, uint8_t* dStatus,
                                      talc_counters* counters, u32* dReadStats) {
   if (!c) return TALC_ERR_ARG;
+  if (c->parent) lane_follow(c);
   if (!c->tableReady) { c->err = "no k-mer table loaded"; return TALC_ERR_NO_TABLE; }
   CUDA_TRY(c, cudaSetDevice(c->device));
   if (counters) memset(counters, 0, sizeof(*counters));

@@ -474,6 +474,47 @@ def test_stream_api_matches_single_calls(api, case_c1):
     assert np.array_equal(np.concatenate(stats), ostats)
 
 
+def test_lane_overlaps_batches_with_identical_results(api, case_c1):
+    """talc_ctx_create_lane: a context and its lane correct different halves of the reads at the same time from two
+    host threads (their kernels overlap on the device); bytes, status and counters equal the one-call result, a lane
+    refuses to load a table, and it follows a setting changed on its parent."""
+    import threading
+    case = case_c1
+    t = _ctx(api, case)
+    out, off, st, ctr = t.correct(case.reads, case.off)
+    _assert_same(case, out, off, st, ctr)
+    lane = t.create_lane()
+    with pytest.raises(Exception):
+        lane.load_packed(np.zeros(1, np.uint64), np.ones(1, np.uint32))
+    n = len(case.off) - 1
+    h = n // 2
+    spans = [(0, h), (h, n)]
+    res = [None, None]
+
+    def run(i, c):
+        a, b = spans[i]
+        for _ in range(3):  # several rounds so that the two threads really run side by side
+            res[i] = c.correct(case.reads[int(case.off[a]):int(case.off[b])], case.off[a:b + 1] - case.off[a])
+
+    for shape in ((0, 0, 0), (1, 64, 7)):  # default execution shape, then the split shape set on the parent only
+        if shape[0]:
+            t.set_exec(*shape)
+        th = [threading.Thread(target=run, args=(0, t)), threading.Thread(target=run, args=(1, lane))]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        assert res[0] is not None and res[1] is not None
+        assert np.array_equal(np.concatenate([res[0][0], res[1][0]]), out)
+        assert np.array_equal(np.concatenate([res[0][2], res[1][2]]), st)
+        tot = {k2: res[0][3][k2] + res[1][3][k2] for k2 in SHARED}
+        assert tot == {k2: ctr[k2] for k2 in SHARED}
+        if shape[0]:
+            assert res[1][3]["rounds"] > 0  # the lane ran the split shape although only the parent was told to
+    lane.close()
+    t.close()
+
+
 def test_gpu_dump_parser_semantics(api, case_c3, tmp_path):
     """Row f1: the dump text is parsed on the GPU.  (1) line semantics of buildCDBG on a hand-made file (first line
     wins, MIN_COUNT filter, malformed lines, lower case, CR LF, trailing tokens, negative and out-of-range counts,
