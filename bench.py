@@ -26,8 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "corrected long-read Mbp/s"
-TRAFFIC_SOURCE = ("profiles/r01_traffic_correct_kernel.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch "
-                  "of this workload; captured at commit c62cd49, round 1)")
+TRAFFIC_SOURCE = ("profiles/r02_traffic_correct_kernel.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch "
+                  "of this workload; captured in round 2 by `tools/r2_gpu_session.sh launches`, kernel sources unchanged since)")
 
 
 def parse_args():
@@ -51,8 +51,8 @@ def parse_args():
 
 def measured_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one correct_kernel launch of this very workload (131072 reads),
-    from the committed metrics-only ncu capture (tools/final_profiles.sh); None when the capture is absent."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic_correct_kernel.csv")
+    from the committed metrics-only ncu capture (tools/r2_gpu_session.sh launches); None when the capture is absent."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic_correct_kernel.csv")
     if not os.path.exists(p):
         return None
     import csv

@@ -45,6 +45,17 @@ final)
   python -c "import json;d=json.load(open('gpurun_out/r2_bench_final.json'));print('value',d['value'],'e2e',d['e2e']['value'],'parity',d['parity'],'table_load',d.get('table_load'),'cli',d.get('cli_clock'),'frac',d['roofline']['frac'],d['roofline'].get('frac_random'))" 2>&1
   tail -2 gpurun_out/r2_bench_final.err
   ;;
+launches)
+  # the launch list and the DRAM traffic of the bench command as it is now (two lanes; ncu serialises the launches)
+  K='regex:^(correct_kernel|control_kernel|walk_kernel|coverage_kernel|gather_kernel|kmer_count_kernel|len_to_u64_kernel|cost_key_kernel|ctx_init_kernel|table_.*|ctx_.*|model_tabs_kernel|random_sector_kernel.*)$'
+  timeout 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-table-load > gpurun_out/r2_ncu_plain.log 2>&1 && \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/r2_launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-table-load > gpurun_out/r2_ncu_launch.log 2>&1
+  timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,smsp__inst_executed.sum,sm__icc_request_hit_rate.pct,smsp__cycles_active.avg,sm__cycles_elapsed.max \
+      --clock-control none -k regex:correct_kernel -c 1 --csv --log-file gpurun_out/r2_traffic_correct_kernel.csv \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-table-load --lanes 1 > gpurun_out/r2_ncu_traffic.log 2>&1
+  grep -c . gpurun_out/r2_launches.csv; tail -3 gpurun_out/r2_traffic_correct_kernel.csv | cut -c1-300
+  ;;
 ncu)
   K='regex:^(correct_kernel|control_kernel|walk_kernel|coverage_kernel|gather_kernel|kmer_count_kernel|len_to_u64_kernel|cost_key_kernel|ctx_init_kernel|table_.*|ctx_.*|model_tabs_kernel|random_sector_kernel.*)$'
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-table-load > gpurun_out/r2_ncu_plain.log 2>&1 && \
