@@ -240,7 +240,7 @@ def run_gpu(args, rank, world, local_rank):
     # so that the tail of one batch (a few long reads, one warp each) overlaps the start of the next; --lanes 1 runs
     # them one after the other as round 1 did.  Timed with CUDA events recorded on an idle device on both sides.
     import threading
-    lanes = [ctx] + ([ctx.create_lane()] if args.lanes >= 2 else [])
+    lanes = [ctx] + [ctx.create_lane() for _ in range(max(1, min(args.lanes, 4)) - 1)]
     L = len(lanes)
     bufs = [(d_out, d_ooff, d_st)] + [(torch.empty_like(d_out), torch.zeros_like(d_ooff), torch.zeros_like(d_st)) for _ in range(L - 1)]
     for i in range(max(args.warmup, L)):
@@ -314,13 +314,15 @@ def run_gpu(args, rank, world, local_rank):
         pinned.append((r.cpu().pin_memory().numpy(), o.cpu().numpy().astype(np.uint64), nb))
     # the call a user of a multi-batch job makes: talc_stream_submit / talc_stream_next (pinned ring of slots, copies
     # of batch i+1 and i-1 overlapped with the kernels of batch i); every step's result is read back on the host
+    os.environ["TALC_STREAM_LANES"] = str(L)  # the stream keeps as many batches on the device as the leg above
     stream = ctx.stream()
-    for w_ in range(4):  # warm-up of the host path: every slot of the ring allocates its pinned / device buffers once
+    depth = L + 1  # batches in flight: the ring has L + 2 slots and one is held by the caller between two next()
+    for w_ in range(L + 2):  # warm-up of the host path: every slot of the ring allocates its pinned / device buffers once
         stream.submit(pinned[(w_ + 2) % 3][0], pinned[(w_ + 2) % 3][1])
-        if w_ >= 2:
+        if w_ >= depth - 1:
             stream.next(copy=False)
-    stream.next(copy=False)
-    stream.next(copy=False)
+    for w_ in range(depth - 1):
+        stream.next(copy=False)
     e2e_bases, h2d, d2h, e2e_dev_ms = 0, 0, 0, 0.0
     barrier()
     w0 = time.perf_counter()
@@ -330,7 +332,7 @@ def run_gpu(args, rank, world, local_rank):
         stream.submit(hr, ho)
         e2e_bases += nb
         h2d = nb + 8 * (B + 1)
-        if s_ - fetched >= 2:
+        if s_ - fetched >= depth - 1:
             out, ooff, st, _, c = stream.next(copy=False)
             e2e_dev_ms += c["ms_total"]
             d2h = int(ooff[-1]) + 8 * (B + 1) + B

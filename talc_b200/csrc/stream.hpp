@@ -6,7 +6,7 @@
 //                        copy-out stream
 //   caller thread        talc_stream_next(i-1): pinned result buffers, formatted / written by the caller
 //
-// A ring of kSlots slots bounds host and device memory whatever the number of reads; results come back in
+// A ring of kSlots (= lanes + 2) slots bounds host and device memory whatever the number of reads; results come back in
 // submission order.  Included at the end of talc_b200.cu (same translation unit as the context).
 #pragma once
 #include <condition_variable>
@@ -71,17 +71,17 @@ struct StreamSlot {
 };
 
 struct talc_stream {
-  static const int kSlots = 4;
-  static const int kMaxLanes = 2;
+  static const int kMaxLanes = 4;
+  int kSlots = 4;  // lanes + 2: one batch being filled, one per lane on the device, one held by the caller
   talc_ctx* c = nullptr;
   // Two batches may be on the device at once ("lanes"): the kernels of batch i+1 are queued on their own stream with
   // their own scratch while batch i runs, so that its blocks start on the SMs that the last, longest reads of batch i
   // no longer fill (the per-read program is one warp per read: a batch ends with a tail of a few long reads).  Lane 0
   // is the caller's context, lane 1 a lane of it (talc_ctx_create_lane).
-  talc_ctx* lane[kMaxLanes] = {nullptr, nullptr};
+  talc_ctx* lane[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   int nLanes = 1;
   bool wantStats = false;
-  StreamSlot slot[kSlots];
+  std::vector<StreamSlot> slot;
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
   std::thread worker[kMaxLanes];
   std::mutex mu;
@@ -95,7 +95,7 @@ static void stream_worker(talc_stream* s, int w) {
   talc_ctx* c = s->lane[w];
   cudaSetDevice(c->device);
   for (u64 seq = (u64)w;; seq += (u64)s->nLanes) {
-    StreamSlot* sl = &s->slot[seq % talc_stream::kSlots];
+    StreamSlot* sl = &s->slot[seq % s->kSlots];
     {
       std::unique_lock<std::mutex> lk(s->mu);
       // the slot of batch `seq` is in state 1 only once that very batch has been submitted: its previous tenant
@@ -145,6 +145,14 @@ int talc_stream_open(talc_ctx* c, int want_read_stats, talc_stream** out) {
   talc_stream* s = new talc_stream;
   s->c = c;
   s->wantStats = want_read_stats != 0;
+  s->lane[0] = c;
+  int want = 2;  // TALC_STREAM_LANES = 1 .. 4 (1 = one batch at a time, for A/B measurements; 3 or 4 for heavy-tailed inputs)
+  if (const char* e = getenv("TALC_STREAM_LANES")) want = std::min(std::max(atoi(e), 1), (int)talc_stream::kMaxLanes);
+  if (c->parent) want = 1;  // the caller's context is a lane itself
+  s->nLanes = 1;
+  while (s->nLanes < want && talc_ctx_create_lane(c, &s->lane[s->nLanes]) == TALC_OK) s->nLanes++;  // fewer if memory is short
+  s->kSlots = s->nLanes + 2;
+  s->slot = std::vector<StreamSlot>((size_t)s->kSlots);
   bool ok = cudaStreamCreateWithFlags(&s->copyIn, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&s->copyOut, cudaStreamNonBlocking) == cudaSuccess;
   for (auto& sl : s->slot)
@@ -152,17 +160,9 @@ int talc_stream_open(talc_ctx* c, int want_read_stats, talc_stream** out) {
          cudaEventCreateWithFlags(&sl.d2hDone, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     c->err = "talc_stream_open: cannot create CUDA streams / events";
+    for (int w = 1; w < s->nLanes; ++w) talc_ctx_destroy(s->lane[w]);
     delete s;
     return TALC_ERR_CUDA;
-  }
-  s->lane[0] = c;
-  s->nLanes = 2;
-  if (const char* e = getenv("TALC_STREAM_LANES")) s->nLanes = atoi(e) >= 2 ? 2 : 1;  // 1 = one batch at a time (A/B measurements)
-  if (s->nLanes == 2) {
-    if (c->parent || talc_ctx_create_lane(c, &s->lane[1]) != TALC_OK) {
-      s->nLanes = 1;  // no second lane (memory, or the caller's context is a lane itself): one batch at a time
-      s->lane[1] = nullptr;
-    }
   }
   for (int w = 0; w < s->nLanes; ++w) s->worker[w] = std::thread(stream_worker, s, w);
   *out = s;
@@ -193,7 +193,7 @@ int talc_stream_reserve(talc_stream* s, uint32_t max_reads, uint64_t max_bases) 
 int talc_stream_submit(talc_stream* s, const uint8_t* bases, const uint64_t* offsets, uint32_t n) {
   if (!s || !offsets || (n && !bases) || offsets[0] != 0) return TALC_ERR_ARG;
   talc_ctx* c = s->c;
-  StreamSlot* sl = &s->slot[s->seqSubmit % talc_stream::kSlots];
+  StreamSlot* sl = &s->slot[s->seqSubmit % s->kSlots];
   {
     std::unique_lock<std::mutex> lk(s->mu);
     s->cv.wait(lk, [&] { return sl->state == 0; });
@@ -241,7 +241,7 @@ int talc_stream_next(talc_stream* s, const uint8_t** out, const uint64_t** out_o
   {
     std::unique_lock<std::mutex> lk(s->mu);
     if (s->seqFetch > 0) {  // release the slot handed out by the previous call
-      StreamSlot* prev = &s->slot[(s->seqFetch - 1) % talc_stream::kSlots];
+      StreamSlot* prev = &s->slot[(s->seqFetch - 1) % s->kSlots];
       if (prev->state == 3) prev->state = 0;
     }
     if (s->seqFetch == s->seqSubmit) {
@@ -249,7 +249,7 @@ int talc_stream_next(talc_stream* s, const uint8_t** out, const uint64_t** out_o
       s->err = "talc_stream_next: nothing submitted";
       return TALC_ERR_ARG;
     }
-    sl = &s->slot[s->seqFetch % talc_stream::kSlots];
+    sl = &s->slot[s->seqFetch % s->kSlots];
     s->cv.notify_all();
     s->cv.wait(lk, [&] { return sl->state == 2; });
     sl->state = 3;
@@ -281,7 +281,7 @@ void talc_stream_close(talc_stream* s) {
   s->cv.notify_all();
   for (auto& t : s->worker)
     if (t.joinable()) t.join();
-  if (s->lane[1]) talc_ctx_destroy(s->lane[1]);
+  for (int w = 1; w < s->nLanes; ++w) talc_ctx_destroy(s->lane[w]);
   cudaSetDevice(s->c->device);
   cudaStreamSynchronize(s->copyIn);
   cudaStreamSynchronize(s->copyOut);
