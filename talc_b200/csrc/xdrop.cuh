@@ -94,18 +94,46 @@ TALC_HD void xd_finish(i32 d, const XdHist& h, At at, ArgMax argmax1, u32& ext_r
   }
 }
 
-// one cell: value, and its contribution to the two trimming reductions
-TALC_HD i32 xd_cell(i32 a, i32 b, i32 dg, bool match, i32 col, i32 d, i32 X, i32 minCol, i32 maxCol, i32& loC, i32& hiC) {
+// The part of the cell rule that is the same for every cell of anti-diagonal d computed with the window
+// [minCol, maxCol) (minCol < maxCol inside the loop).
+struct XdRow {
+  i32 W;      // maxCol - minCol > 0
+  i32 negX;   // survival threshold
+  i32 negd;   // boundary value
+  bool col0;  // column 0 of the matrix is still alive on this anti-diagonal (it is the cell left of the window)
+  bool row0;  // row 0 of the matrix is still alive (it is the cell right of the window)
+};
+TALC_HD XdRow xd_row(i32 d, i32 X, i32 minCol, i32 maxCol) {
+  XdRow r;
+  r.W = maxCol - minCol;
+  r.negX = -X;
+  r.negd = -d;
+  r.col0 = (minCol == 1) & (d < X);
+  r.row0 = (d == maxCol) & (d < X);
+  return r;
+}
+// One cell: value, and its contribution to the two trimming reductions.  t = column - minCol, so that every range
+// test of the original (col in [minCol, maxCol), [minCol, maxCol], [minCol-1, maxCol-1], == minCol-1, == maxCol) is
+// one unsigned comparison against W; stored values are kXdU or >= -X > kXdU, so "a or b is defined" is max(a, b) > kXdU.
+// loT / hiT are the reductions in the same shifted coordinate (xd_window_bounds turns them back into columns).
+TALC_HD i32 xd_cell(i32 a, i32 b, i32 dg, bool match, i32 t, const XdRow& R, i32& loT, i32& hiT) {
   const i32 g = (a > b ? a : b) - 1;
   const i32 s = dg - (match ? 0 : 1);
   const i32 tmp = g > s ? g : s;
-  i32 val = kXdU;
-  if ((col >= minCol) & (col < maxCol) & (tmp >= -X)) val = tmp;
-  if ((col == minCol - 1) & (minCol == 1) & (d < X)) val = -d;  // column 0 of the matrix
-  if ((col == maxCol) & (d == maxCol) & (d < X)) val = -d;      // row 0 of the matrix
-  if ((col >= minCol) & (col <= maxCol) & ((val != kXdU) | (a != kXdU))) loC = col < loC ? col : loC;
-  if ((col >= minCol - 1) & (col <= maxCol - 1) & ((val != kXdU) | (b != kXdU))) hiC = col > hiC ? col : hiC;
+  i32 val = (((u32)t < (u32)R.W) & (tmp >= R.negX)) ? tmp : kXdU;
+  if ((t == -1) & R.col0) val = R.negd;   // column 0 of the matrix
+  if ((t == R.W) & R.row0) val = R.negd;  // row 0 of the matrix
+  const i32 va = val > a ? val : a, vb = val > b ? val : b;
+  const i32 tl = (((u32)t <= (u32)R.W) & (va > kXdU)) ? t : INT32_MAX;
+  const i32 th = (((u32)(t + 1) <= (u32)R.W) & (vb > kXdU)) ? t : INT32_MIN;
+  loT = tl < loT ? tl : loT;
+  hiT = th > hiT ? th : hiT;
   return val;
+}
+// reductions in window coordinates -> the column sentinels xd_next_window expects
+TALC_HD void xd_window_bounds(i32 loT, i32 hiT, i32 minCol, i32& loC, i32& hiC) {
+  loC = (loT == INT32_MAX) ? INT32_MAX : loT + minCol;
+  hiC = (hiT == INT32_MIN) ? INT32_MIN : hiT + minCol;
 }
 
 #if defined(__CUDA_ARCH__)
@@ -149,15 +177,18 @@ __device__ __noinline__ void xdrop_extend_reg(const SeqView& queryArg, u32 qoff,
       const u32 nq = (qi < qlen) ? query.code(qoff + qi) : 6u;
       i32 aEdge = __shfl_up_sync(0xffffffffu, vO[S - 1], 1);
       if (lane == 0) aEdge = kXdU;
-      i32 loC = INT32_MAX, hiC = INT32_MIN;
+      i32 loT = INT32_MAX, hiT = INT32_MIN, loC, hiC;
+      const XdRow R = xd_row(d, X, minCol, maxCol);
+      const i32 t0 = cb + g0 - minCol;
 #pragma unroll
       for (int i = 0; i < S; ++i) {
         const i32 a = i ? vO[i - 1] : aEdge, b = vO[i], dg = vE[i];
         vOld[i] = dg;
-        vE[i] = xd_cell(a, b, dg, qc[i] == tc[i], cb + g0 + i, d, X, minCol, maxCol, loC, hiC);
+        vE[i] = xd_cell(a, b, dg, qc[i] == tc[i], t0 + i, R, loT, hiT);
       }
-      loC = __reduce_min_sync(0xffffffffu, loC);
-      hiC = __reduce_max_sync(0xffffffffu, hiC);
+      loT = __reduce_min_sync(0xffffffffu, loT);
+      hiT = __reduce_max_sync(0xffffffffu, hiT);
+      xd_window_bounds(loT, hiT, minCol, loC, hiC);
       cells += (u32)(maxCol - minCol);
       xd_next_window(d, rows, cols, loC, hiC, minCol, maxCol);
       const u32 e = __shfl_down_sync(0xffffffffu, qc[0], 1);
@@ -175,15 +206,18 @@ __device__ __noinline__ void xdrop_extend_reg(const SeqView& queryArg, u32 qoff,
       const u32 nt = (ti < dlen) ? database.code(doff + ti) : 7u;
       i32 bEdge = __shfl_down_sync(0xffffffffu, vE[0], 1);
       if (lane == 31) bEdge = kXdU;
-      i32 loC = INT32_MAX, hiC = INT32_MIN;
+      i32 loT = INT32_MAX, hiT = INT32_MIN, loC, hiC;
+      const XdRow R = xd_row(d, X, minCol, maxCol);
+      const i32 t0 = cb + g0 - minCol;
 #pragma unroll
       for (int i = 0; i < S; ++i) {
         const i32 a = vE[i], b = (i + 1 < S) ? vE[i + 1] : bEdge, dg = vO[i];
         vOld[i] = dg;
-        vO[i] = xd_cell(a, b, dg, qc[i] == tc[i], cb + g0 + i, d, X, minCol, maxCol, loC, hiC);
+        vO[i] = xd_cell(a, b, dg, qc[i] == tc[i], t0 + i, R, loT, hiT);
       }
-      loC = __reduce_min_sync(0xffffffffu, loC);
-      hiC = __reduce_max_sync(0xffffffffu, hiC);
+      loT = __reduce_min_sync(0xffffffffu, loT);
+      hiT = __reduce_max_sync(0xffffffffu, hiT);
+      xd_window_bounds(loT, hiT, minCol, loC, hiC);
       cells += (u32)(maxCol - minCol);
       xd_next_window(d, rows, cols, loC, hiC, minCol, maxCol);
       const u32 e = __shfl_up_sync(0xffffffffu, tc[S - 1], 1);

@@ -388,12 +388,14 @@ static void xdrop_reg_mirror(const SeqView& query, u32 qoff, u32 qlen, const Seq
       const i32 cb = m - 16 * S;
       const u32 qi = (u32)(m + 16 * S - 1);
       const u32 nq = (qi < qlen) ? query.code(qoff + qi) : 6u;
-      i32 loC = INT32_MAX, hiC = INT32_MIN;
+      i32 loT = INT32_MAX, hiT = INT32_MIN, loC, hiC;
+      const XdRow R = xd_row(d, X, minCol, maxCol);
       for (int g = 0; g < G; ++g) {
         const i32 a = g ? vO[g - 1] : kXdU, b = vO[g], dg = vE[g];
         vOld[g] = dg;
-        nv[g] = xd_cell(a, b, dg, qc[g] == tc[g], cb + g, d, X, minCol, maxCol, loC, hiC);
+        nv[g] = xd_cell(a, b, dg, qc[g] == tc[g], cb + g - minCol, R, loT, hiT);
       }
+      xd_window_bounds(loT, hiT, minCol, loC, hiC);
       vE = nv;
       cells += (u64)(maxCol - minCol);
       xd_next_window(d, rows, cols, loC, hiC, minCol, maxCol);
@@ -407,12 +409,14 @@ static void xdrop_reg_mirror(const SeqView& query, u32 qoff, u32 qlen, const Seq
       const i32 cb = m + 1 - 16 * S;
       const u32 ti = (u32)(m + 16 * S);
       const u32 nt = (ti < dlen) ? database.code(doff + ti) : 7u;
-      i32 loC = INT32_MAX, hiC = INT32_MIN;
+      i32 loT = INT32_MAX, hiT = INT32_MIN, loC, hiC;
+      const XdRow R = xd_row(d, X, minCol, maxCol);
       for (int g = 0; g < G; ++g) {
         const i32 a = vE[g], b = (g + 1 < G) ? vE[g + 1] : kXdU, dg = vO[g];
         vOld[g] = dg;
-        nv[g] = xd_cell(a, b, dg, qc[g] == tc[g], cb + g, d, X, minCol, maxCol, loC, hiC);
+        nv[g] = xd_cell(a, b, dg, qc[g] == tc[g], cb + g - minCol, R, loT, hiT);
       }
+      xd_window_bounds(loT, hiT, minCol, loC, hiC);
       vO = nv;
       cells += (u64)(maxCol - minCol);
       xd_next_window(d, rows, cols, loC, hiC, minCol, maxCol);
