@@ -14,7 +14,7 @@
 // batch goes through a talc_stream (copies, kernels and formatting overlapped) and a writer appends the corrected
 // records in input order.  Host memory is bounded by the batches in flight, whatever the size of the input.
 // Extensions: --gpus N deals the batches round-robin over N devices (table replicated with one NCCL broadcast issued
-// by the library), --tableCache <file>, --readStats (the per-read rows of Read.cpp:418-433 the reference left disabled
+// by the library, or with peer copies: --replicate peer), --tableCache <file>, --readStats (the per-read rows of Read.cpp:418-433 the reference left disabled
 // at main.cpp:305).
 #include <stdint.h>
 #include <stdio.h>
@@ -36,7 +36,7 @@
 #include "talc_b200.h"
 
 struct Cli {
-  std::string reads, dump, junctions, out = "out", queryMode = "memory", tableCache;
+  std::string reads, dump, junctions, out = "out", queryMode = "memory", tableCache, replicate = "nccl";
   bool useJunctions = false, reverse = false, readStats = false;
   int threads = 1, gpus = 1;
   long batchReads = 131072, batchBases = 256l << 20;
@@ -72,6 +72,7 @@ static int parse(int argc, const char** argv, Cli& c) {
     else if (a == "-SR" || a == "--SRCounts") { if (!val(c.dump)) return 1; c.haveSR = true; }
     else if (a == "-j" || a == "--junctions") { if (!val(c.junctions)) return 1; c.useJunctions = true; }
     else if (a == "--tableCache") { if (!val(c.tableCache)) return 1; }  // extension: binary cache of the built table
+    else if (a == "--replicate") { if (!val(c.replicate) || (c.replicate != "nccl" && c.replicate != "peer")) return 1; }
     else if (a == "-jf2" || a == "--pathToJF2") { if (!val(v)) return 1; }
     else if (a == "-MIN_INNER_SCORE" || a == "--MIN_INNER_SCORE") { if (!val(v) || !to_dbl(v, d) || d < 0.3 || d > 0.9) return 1; c.p.min_inner_score = d; }
     else if (a == "-MIN_BORDER_SCORE" || a == "--MIN_BORDER_SCORE") { if (!val(v) || !to_dbl(v, d) || d < 0.5 || d > 0.9) return 1; c.p.min_border_score = d; }
@@ -320,7 +321,7 @@ int main(int argc, const char** argv) {
   const int pr = parse(argc, argv, cli);
   if (pr == 2) {
     std::cout << "talc <reads> --SRCounts <dump> [--junctions <dump>] -k <K> [-o <prefix>] [-t <N>] [--gpus <N>] [--tableCache <file>]"
-                 " [--batch-reads <N>] [--batch-bases <N>] [--readStats]\n";
+                 " [--batch-reads <N>] [--batch-bases <N>] [--readStats] [--replicate nccl|peer]\n";
     return 0;
   }
   if (pr != 0) { std::cerr << "talc: PARSE_ERROR\n"; return 1; }
@@ -378,11 +379,19 @@ int main(int argc, const char** argv) {
   if (cli.gpus > 1) {
     double ms = 0;
     int usedNccl = 0;
-    if (talc_table_replicate(ctx.data(), cli.gpus, &ms, &usedNccl) != 0) {
+    if (cli.replicate == "peer") {
+      // --replicate peer: one cudaMemcpyPeer per replica instead of the NCCL broadcast -- no communicator to set up
+      // (~3 s in a process that has not used NCCL yet), at the price of N-1 sequential copies from device 0
+      for (int g = 1; g < cli.gpus; ++g)
+        if (talc_table_copy(ctx[g], ctx[0]) != 0) {
+          std::cerr << "talc: " << talc_last_error(ctx[g]) << "\n";
+          return 2;
+        }
+      std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (peer copies)." << std::endl;
+    } else if (talc_table_replicate(ctx.data(), cli.gpus, &ms, &usedNccl) != 0) {
       std::cerr << "talc: " << talc_last_error(ctx[0]) << "\n";
       return 2;
-    }
-    if (usedNccl) std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (one NCCL broadcast, " << ms << " ms)." << std::endl;
+    } else if (usedNccl) std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (one NCCL broadcast, " << ms << " ms)." << std::endl;
     else std::cout << "[TALC]: k-mer table replicated on " << cli.gpus << " GPUs (peer copies; NCCL not found)." << std::endl;
   }
   const double sRep = since(tRep);

@@ -88,8 +88,11 @@ def test_cli_two_gpus_equals_one(api, tmp_path):
     assert subprocess.call([cli] + args + ["-o", "one", "--gpus", "1"], cwd=tmp_path, stdout=subprocess.DEVNULL) == 0
     assert subprocess.call([cli] + args + ["-o", "two", "--gpus", "2", "--batch-reads", "100"], cwd=tmp_path,
                            stdout=subprocess.DEVNULL) == 0
+    assert subprocess.call([cli] + args + ["-o", "peer", "--gpus", "2", "--batch-reads", "77", "--replicate", "peer"], cwd=tmp_path,
+                           stdout=subprocess.DEVNULL) == 0
     for ext in (".fa", ".log"):
         a = open(tmp_path / ("one" + ext), "rb").read() if os.path.exists(tmp_path / ("one" + ext)) else b""
-        b = open(tmp_path / ("two" + ext), "rb").read() if os.path.exists(tmp_path / ("two" + ext)) else b""
-        assert a == b, ext
+        for other in ("two", "peer"):  # NCCL broadcast, then peer copies
+            b = open(tmp_path / (other + ext), "rb").read() if os.path.exists(tmp_path / (other + ext)) else b""
+            assert a == b, (other, ext)
     assert len(open(tmp_path / "one.fa", "rb").read()) > int(w.read_off[-1])

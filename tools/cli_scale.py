@@ -8,7 +8,7 @@ import numpy as np, torch
 from talc_b200 import api, build, synth
 
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-gpus = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "1,2").split(",")]
+gpus = [x for x in (sys.argv[2] if len(sys.argv) > 2 else "1,2").split(",")]  # "2p" = two devices, --replicate peer
 cfg = synth.baseline_config(2, 1.0)
 dev = "cuda:0"
 tr = synth.make_transcriptome(cfg, dev)
@@ -25,15 +25,17 @@ res = {"reads": n_reads, "bases": bases, "runs": {}}
 digests = set()
 for g in gpus:
     t0 = time.time()
-    pr = subprocess.run([cli, "reads.fa", "--SRCounts", "sr.dump", "-k", str(cfg.k), "-o", "g%d" % g, "--gpus", str(g), "-t", "16"],
-                        cwd=d, capture_output=True, text=True)
+    peer = g.endswith("p")
+    ng = int(g.rstrip("p"))
+    pr = subprocess.run([cli, "reads.fa", "--SRCounts", "sr.dump", "-k", str(cfg.k), "-o", "g%s" % g, "--gpus", str(ng), "-t", "16"] +
+                        (["--replicate", "peer"] if peer else []), cwd=d, capture_output=True, text=True)
     rc = pr.returncode
     secs = time.time() - t0
     phases = [l for l in pr.stdout.splitlines() if "seconds:" in l or "replicated" in l]
-    fa = hashlib.sha256(open(os.path.join(d, "g%d.fa" % g), "rb").read()).hexdigest()
-    lg = hashlib.sha256(open(os.path.join(d, "g%d.log" % g), "rb").read()).hexdigest() if os.path.exists(os.path.join(d, "g%d.log" % g)) else ""
+    fa = hashlib.sha256(open(os.path.join(d, "g%s.fa" % g), "rb").read()).hexdigest()
+    lg = hashlib.sha256(open(os.path.join(d, "g%s.log" % g), "rb").read()).hexdigest() if os.path.exists(os.path.join(d, "g%s.log" % g)) else ""
     digests.add((fa, lg))
-    res["runs"]["gpus_%d" % g] = {"rc": rc, "seconds": round(secs, 2), "mbp_per_s": round(bases / 1e6 / secs, 1), "fa_sha256": fa[:16], "phases": phases}
+    res["runs"]["gpus_%s" % g] = {"rc": rc, "seconds": round(secs, 2), "mbp_per_s": round(bases / 1e6 / secs, 1), "fa_sha256": fa[:16], "phases": phases}
 res["identical_outputs"] = len(digests) == 1
 shutil.rmtree(d, ignore_errors=True)
 print(json.dumps(res))
