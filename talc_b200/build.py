@@ -73,7 +73,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 def build_cli(force: bool = False) -> str:
     src = os.path.join(CSRC, "host", "talc_main.cpp")
     build_library()
-    if force or _stale(CLI, [src, LIB]):
+    if force or _stale(CLI, [src, os.path.join(CSRC, "host", "reads_io.hpp"), LIB]):
         os.makedirs(os.path.dirname(CLI), exist_ok=True)
         cmd = [HOSTCXX, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", CLI,
                "-L", HERE, "-ltalc_b200", "-Wl,-rpath," + HERE]
