@@ -63,6 +63,18 @@ def measured_traffic():
     return tot or None
 
 
+def measured_instructions():
+    """smsp__inst_executed.sum (warp-instructions) of the same captured launch; None when the capture is absent."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic_correct_kernel.csv")
+    if not os.path.exists(p):
+        return None
+    import csv
+    for row in csv.reader(open(p)):
+        if len(row) > 14 and row[12] == "smsp__inst_executed.sum":
+            return int(float(row[14]))
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -434,6 +446,18 @@ def run_gpu(args, rank, world, local_rank):
             line["table_load"] = table_load_timings(api, cfg, cpu_keys, use_j)
         if world == 1 and args.cli_clock:
             line["cli_clock"] = cli_clock(args, cfg, cpu_keys, use_j, tr_cli, dev)
+        # what actually bounds correct_kernel: instruction issue.  Warp-instructions of one launch (ncu capture of this
+        # workload) / (SMs x 4 schedulers x one instruction per cycle at the measured SM clock) = the shortest possible
+        # launch with this instruction count; frac = that / the measured launch
+        n_inst = measured_instructions() if B == 131072 and args.config == 2 and args.scale == 1.0 else None
+        if n_inst and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            min_ms = n_inst / (sms * 4 * clocks["sm_mhz"] * 1e6) * 1e3
+            line["roofline"]["issue"] = {"warp_instructions_per_launch": n_inst, "source": TRAFFIC_SOURCE,
+                                         "schedulers": sms * 4, "sm_mhz": clocks["sm_mhz"],
+                                         "ms_per_launch_at_one_instruction_per_cycle": min_ms, "frac": min_ms / k_ms,
+                                         "note": "the kernel is bound by instruction issue of a serial per-read program "
+                                                 "(8 warps per SM, 231 registers), not by HBM: this is its issue-slot utilisation"}
         rnd = random_sector_peaks(ctx)
         line["roofline"].update(rnd)
         if rnd.get("peak_random"):
