@@ -194,10 +194,12 @@ int talc_coverage_batch(talc_ctx* ctx, const uint8_t* bases, const uint64_t* off
 
 /* ---- streamed correction (replaces loadSeqData / outputSeqData holding every read: main.cpp:219,310, io.cpp:26-75) ----
  * Batches of reads pass through one context with the host-to-device copy of batch i+1, the kernels of batch i, the
- * device-to-host copy of batch i-1 and the caller's own work (FASTA formatting) overlapped: a ring of four slots with
- * pinned staging, two copy streams and one worker thread inside the library.  Host and device memory are bounded by
- * the batch size whatever the number of reads; results come back in submission order.
- *   submit  copies the caller's buffers (free again on return); blocks only while all four slots are busy
+ * device-to-host copy of batch i-1 and the caller's own work (FASTA formatting) overlapped: a ring of slots with pinned
+ * staging, two copy streams and one worker thread per lane inside the library.  The stream keeps TWO batches on the
+ * device (the context and one lane of it, see talc_ctx_create_lane; environment TALC_STREAM_LANES = 1..4 changes
+ * that) and has lanes + 2 slots, four by default.  Host and device memory are bounded by the batch size whatever the
+ * number of reads; results come back in submission order.
+ *   submit  copies the caller's buffers (free again on return); blocks only while all slots are busy
  *   next    blocks until the oldest unfetched batch is complete; the returned pointers (pinned host memory owned by
  *           the stream) stay valid until the following next / close.  read_stats: per read {span of the final solid
  *           regions in k-mers, number of regions} -- the columns of outputBasicReadStats (Read.cpp:418-433) that need
