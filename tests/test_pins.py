@@ -58,3 +58,27 @@ def test_device_code_on_host_reproduces_the_pinned_cases(name):
         assert ctr[k] == case.o_ctr[k], k
     if _input_digest(case) == PINS[name]["input_sha256"]:
         assert make_pins.array_digest(out, off, st) == PINS[name]["sha256"]
+
+
+def test_pin_script_runs_end_to_end(tmp_path):
+    """tools/pin_reference.py is the one command that pins the oracle the day a reference binary exists.  Its mechanics
+    (text inputs written, both programs run on them, .fa / sorted .log / .config.txt and the committed digests
+    compared, exit code) are exercised here with the oracle's own front end standing in for the reference binary --
+    this proves the script, not the oracle."""
+    import subprocess
+    import sys
+    from oracle import pyoracle as po
+    po.build()
+    root = ROOT
+    pr = subprocess.run([sys.executable, os.path.join(root, "tools", "pin_reference.py"), "--ref", po.BIN, "--configs", "3small",
+                         "--workdir", str(tmp_path)], capture_output=True, text=True, cwd=root)
+    assert pr.returncode == 0, pr.stdout + pr.stderr
+    assert "PINNED" in pr.stdout and "DIFFERENT" not in pr.stdout
+    # and it says so when the two differ: a "reference" that drops the last read
+    fake = tmp_path / "fake_talc.sh"
+    fake.write_text("#!/bin/sh\n%s \"$@\" || exit $?\nfor a in \"$@\"; do if [ \"$prev\" = -o ]; then o=$a; fi; prev=$a; done\n"
+                    "head -n -2 $o.fa > $o.fa.tmp && mv $o.fa.tmp $o.fa\n" % po.BIN)
+    fake.chmod(0o755)
+    pr = subprocess.run([sys.executable, os.path.join(root, "tools", "pin_reference.py"), "--ref", str(fake), "--configs", "3small",
+                         "--workdir", str(tmp_path)], capture_output=True, text=True, cwd=root)
+    assert pr.returncode == 1 and "NOT PINNED" in pr.stdout
