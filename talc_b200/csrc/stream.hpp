@@ -170,8 +170,9 @@ int talc_stream_open(talc_ctx* c, int want_read_stats, talc_stream** out) {
 }
 
 // Optional: allocate the pinned host and device buffers of every slot now, for batches of up to max_reads reads and
-// max_bases bases (page-locking hundreds of MB takes ~0.1 s per buffer and holds the driver's lock: better paid once,
-// before the first batch, and in parallel with the table load, than by the first batches).
+// max_bases bases (page-locking hundreds of MB takes ~0.05 s per buffer and every other mapping call of the process
+// queues behind it: better paid once, before the first batch, than by the first batches -- and not while a table
+// loads or NCCL starts up, profiles/r02_summary.md).
 int talc_stream_reserve(talc_stream* s, uint32_t max_reads, uint64_t max_bases) {
   if (!s) return TALC_ERR_ARG;
   talc_ctx* c = s->c;
